@@ -1,0 +1,33 @@
+/* Host build of the pipeline (tests only): C entry points for ctypes. */
+#include "zb_engine.h"
+
+extern "C" {
+/* single stream, one call; returns bytes written (ceil(bits/8)), *bits = total bits */
+long emu_compress(const uint8_t *data, long n, const uint8_t *hist, int hist_len, unsigned block_size, int finalize, int in_bits,
+                  uint8_t *out, long out_cap, unsigned long long *bits, unsigned tile_main,
+                  /* optional dumps, sized by caller: */ uint32_t *sa_lcp, uint16_t *match, int *nsub, int *sub_info /* 8 ints per sub */,
+                  int *lit_len, int *off_len, uint16_t *best) {
+   ZbPipe p; p.st = 0;
+   ZbStreamIn s = {data, (size_t)n, hist, (uint32_t)hist_len, finalize, (uint32_t)in_bits};
+   std::vector<uint8_t> o; std::vector<ZbStreamRes> r; ZbDump d;
+   if (zb_run_batch(p, &s, 1, block_size, o, r, &d, tile_main)) return -1;
+   if ((long)o.size() > out_cap) return -2;
+   memcpy(out, o.data(), o.size());
+   *bits = r[0].total_bits;
+   if (sa_lcp) memcpy(sa_lcp, d.sa_lcp.data(), d.sa_lcp.size() * 4);
+   if (match) memcpy(match, d.match.data(), d.match.size() * 4);
+   if (best) memcpy(best, d.best.data(), d.best.size() * 4);
+   if (nsub) {
+      *nsub = (int)d.sub.size();
+      for (size_t i = 0; i < d.sub.size(); i++) {
+         const ZbSub &b = d.sub[i];
+         int *q = sub_info + 8 * i;
+         q[0] = b.win; q[1] = b.ps; q[2] = b.pe; q[3] = b.is_dyn; q[4] = b.static_cost; q[5] = b.dynamic_cost; q[6] = b.body_bits; q[7] = b.stored | (b.ub_hit << 8);
+         for (int j = 0; j < 288; j++) lit_len[288 * i + j] = d.tabs[i].llen[j];
+         for (int j = 0; j < 32; j++) off_len[32 * i + j] = d.tabs[i].olen[j];
+      }
+   }
+   p.release_all();
+   return (long)o.size();
+}
+}

@@ -1,0 +1,537 @@
+/*
+ * zb_core.h - per-task device logic of the zultra-b200 compression path.
+ *
+ * Everything here is a __host__ __device__ function that one GPU thread runs for one task (one Huffman
+ * build, one parse chunk, one match-finder tile ...).  The CUDA kernels in zb_kernels.cu are thin
+ * task->thread mappings around these functions.  tests/emu/ compiles the same functions for the host so
+ * that the logic can be diffed against the reference without a GPU; the product library never runs them
+ * on the CPU.
+ *
+ * Reference behaviour each function reproduces is cited as file:line of emmanuel-marty/zultra.
+ */
+#ifndef ZB_CORE_H
+#define ZB_CORE_H
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define ZB_HD __host__ __device__ __forceinline__
+#define ZB_HDN __host__ __device__ __noinline__
+#else
+#define ZB_HD inline
+#define ZB_HDN inline
+#endif
+
+/* format constants (format.h:37-50, private.h:41-56) */
+#define ZB_MIN_MATCH 3
+#define ZB_MAX_MATCH 258
+#define ZB_MAX_OFFSET 32768
+#define ZB_HISTORY 32768
+#define ZB_NLIT 288
+#define ZB_NOFF 32
+#define ZB_NCL 19
+#define ZB_EOB 256
+#define ZB_NMATCH 8
+#define ZB_LEAVE_ALONE 40
+#define ZB_MAX_SPLITS 64
+#define ZB_POS_BITS 22
+#define ZB_POS_MASK 0x3fffffu
+#define ZB_LCP_MASK 0x7fc00000u
+#define ZB_VISITED 0x80000000u
+
+typedef struct { uint16_t length, offset; } zb_match_t;
+
+ZB_HD int zb_ilog2(uint32_t v) {
+#ifdef __CUDA_ARCH__
+   return 31 - __clz((int)v);
+#else
+   return 31 - __builtin_clz(v);
+#endif
+}
+
+/* ---- deflate symbol arithmetic (RFC 1951 3.2.5; tables at blockdeflate.c:45-85) ---- */
+
+/* lenidx = length-3 clamped to 255 (blockdeflate.c:203-205) -> symbol 257..285 */
+ZB_HD int zb_len_sym(uint32_t lenidx) {
+   if (lenidx > 255) lenidx = 255;
+   if (lenidx < 8) return 257 + (int)lenidx;
+   if (lenidx == 255) return 285;
+   int e = zb_ilog2(lenidx) - 2;
+   return 257 + 4 * (e + 1) + (int)((lenidx >> e) & 3);
+}
+ZB_HD int zb_len_extra_bits(uint32_t lenidx) {
+   if (lenidx > 255) lenidx = 255;
+   if (lenidx < 8 || lenidx == 255) return 0;
+   return zb_ilog2(lenidx) - 2;
+}
+/* number of extra bits of length symbol s-257 (g_nRevMatchSymbolBits) */
+ZB_HD int zb_lensym_extra(int s) { return (s < 8 || s >= 28) ? 0 : ((s - 4) >> 2); }
+/* offset 1..32768 -> distance symbol 0..29 */
+ZB_HD int zb_off_sym(uint32_t offset) {
+   uint32_t d = offset - 1;
+   if (d < 4) return (int)d;
+   int b = zb_ilog2(d);
+   return 2 * b + (int)((d >> (b - 1)) & 1);
+}
+ZB_HD int zb_off_extra_bits(uint32_t offset) {
+   uint32_t d = offset - 1;
+   if (d < 4) return 0;
+   return zb_ilog2(d) - 1;
+}
+ZB_HD int zb_offsym_extra(int s) { return (s < 4 || s >= 30) ? 0 : ((s - 2) >> 1); }
+
+/* ---- Huffman code construction (huffencoder.c) ---- */
+
+/* Sort keys ascending. Shell sort, n <= 288. */
+ZB_HD void zb_sort_u32(uint32_t *a, int n) {
+   const int gaps[6] = {132, 57, 23, 10, 4, 1};
+   for (int g = 0; g < 6; g++) {
+      int gap = gaps[g];
+      for (int i = gap; i < n; i++) {
+         uint32_t v = a[i];
+         int j = i;
+         while (j >= gap && a[j - gap] > v) { a[j] = a[j - gap]; j -= gap; }
+         a[j] = v;
+      }
+   }
+}
+
+/*
+ * Minimum-redundancy code lengths, unlimited (huffencoder.c:157-270: symbols with a non-zero count sorted by
+ * (count, index) ascending, Moffat-Katajainen in place; zero or one used symbol -> len[0] = 1 only).
+ * cnt[0..nsym) -> len[0..288).  scratch: key[288].
+ */
+ZB_HD void zb_huff_lengths(const int *cnt, int nsym, int *len, uint32_t *key) {
+   int n = 0;
+   for (int i = 0; i < ZB_NLIT; i++) len[i] = 0;
+   for (int i = 0; i < nsym; i++)
+      if (cnt[i]) key[n++] = ((uint32_t)cnt[i] << 9) | (uint32_t)i;
+   if (n <= 1) { len[0] = 1; return; }
+   zb_sort_u32(key, n);
+   /* w[] lives in the upper bits of key[]; keep symbol ids aside in the low 9 bits */
+   /* phase 1: pair up the two lightest nodes; w[t] becomes the weight of internal node t, and consumed
+      internal nodes get their parent index */
+   int leaf = 0, inode = 0;
+#define ZB_W(i) (key[i] >> 9)
+#define ZB_SETW(i, v) (key[i] = ((uint32_t)(v) << 9) | (key[i] & 511u))
+   /* weights can reach 2*sum; sum <= 2^21+1 fits in 23 bits */
+   for (int t = 0; t < n - 1; t++) {
+      uint32_t w;
+      if (leaf >= n || (inode < t && ZB_W(inode) < ZB_W(leaf))) { w = ZB_W(inode); ZB_SETW(inode, t); inode++; }
+      else { w = ZB_W(leaf); leaf++; }
+      if (leaf >= n || (inode < t && ZB_W(inode) < ZB_W(leaf))) { w += ZB_W(inode); ZB_SETW(inode, t); inode++; }
+      else { w += ZB_W(leaf); leaf++; }
+      ZB_SETW(t, w);
+   }
+   /* phase 2: internal node depths */
+   ZB_SETW(n - 2, 0);
+   for (int t = n - 3; t >= 0; t--) ZB_SETW(t, ZB_W(ZB_W(t)) + 1);
+   /* phase 3: leaf depths */
+   int avail = 1, used = 0, depth = 0, t = n - 2, x = n - 1;
+   while (avail > 0) {
+      while (t >= 0 && (int)ZB_W(t) == depth) { used++; t--; }
+      while (avail > used) { ZB_SETW(x, depth); x--; avail--; }
+      avail = used << 1; depth++; used = 0;
+   }
+   for (int i = 0; i < n; i++) len[key[i] & 511u] = (int)ZB_W(i);
+#undef ZB_W
+#undef ZB_SETW
+}
+
+/* order[] = symbols with len != 0 sorted by (len, index) ascending; returns count.  Lengths <= 287. */
+ZB_HD int zb_order_by_len(const int *len, int nsym, int16_t *order) {
+   int n = 0, maxl = 0;
+   for (int i = 0; i < nsym; i++) if (len[i] > maxl) maxl = len[i];
+   for (int l = 1; l <= maxl; l++)
+      for (int i = 0; i < nsym; i++)
+         if (len[i] == l) order[n++] = (int16_t)i;
+   return n;
+}
+
+/*
+ * Length limiting exactly as huffencoder.c:303-345 (clamp, lengthen from the long end until Kraft fits,
+ * shorten from the short end while it still fits).  The reference's last loop runs one index past the
+ * sorted list (i <= nNumSorted, huffencoder.c:334) which is undefined behaviour when Kraft slack remains
+ * after the last symbol; we stop at the last symbol and report that case through *ub_hit.
+ * Returns number of coded symbols; order[] is the final (len,index) order.
+ */
+ZB_HD int zb_huff_limit(int *len, int nsym, int maxlen, int16_t *order, int *ub_hit) {
+   int n = zb_order_by_len(len, nsym, order);
+   if (n > 0 && maxlen > 0 && len[order[n - 1]] > maxlen) {
+      int k = 0, maxk = 1 << maxlen;
+      for (int i = n - 1; i >= 0; i--) {
+         int s = order[i];
+         if (len[s] > maxlen) len[s] = maxlen;
+         k += maxk >> len[s];
+      }
+      for (int i = n - 1; k > maxk && i >= 0; i--) {
+         int s = order[i];
+         while (len[s] < maxlen && k > maxk) { len[s]++; k -= maxk >> len[s]; }
+      }
+      int i = 0;
+      for (; k < maxk && i < n; i++) {
+         int s = order[i];
+         while (k + (maxk >> len[s]) <= maxk) { k += maxk >> len[s]; len[s]--; }
+      }
+      if (k < maxk && i == n && ub_hit) *ub_hit = 1;
+      n = zb_order_by_len(len, nsym, order);
+   }
+   return n;
+}
+
+ZB_HD uint32_t zb_rev16(uint32_t v) {
+   v = ((v & 0x5555u) << 1) | ((v & 0xaaaau) >> 1);
+   v = ((v & 0x3333u) << 2) | ((v & 0xccccu) >> 2);
+   v = ((v & 0x0f0fu) << 4) | ((v & 0xf0f0u) >> 4);
+   v = ((v & 0x00ffu) << 8) | ((v & 0xff00u) >> 8);
+   return v;
+}
+
+/* canonical, bit-reversed codewords from (len,index)-ordered symbols (huffencoder.c:350-372, :120-145) */
+ZB_HD void zb_huff_codes(const int *len, const int16_t *order, int n, uint16_t *code) {
+   if (n <= 0) return;
+   uint32_t c = 0;
+   int cl = len[order[0]];
+   for (int i = 0; i < n; i++) {
+      int s = order[i];
+      code[s] = (uint16_t)(zb_rev16(c) >> (16 - cl));
+      if (i + 1 < n) { int nl = len[order[i + 1]]; c = (c + 1) << (nl - cl); cl = nl; }
+   }
+}
+
+/* build_dynamic_codewords (huffencoder.c:279-375): lengths + limit (+ codes if code != 0). key: 288 u32, order: 288 i16 */
+ZB_HD void zb_huff_build(const int *cnt, int nsym, int maxlen, int *len, uint16_t *code, uint32_t *key, int16_t *order, int *ub_hit) {
+   zb_huff_lengths(cnt, nsym, len, key);
+   int n = zb_huff_limit(len, nsym, maxlen, order, ub_hit);
+   if (code) zb_huff_codes(len, order, n, code);
+}
+
+/* HLIT / HDIST style trailing-zero trim (huffencoder.c:532-538) */
+ZB_HD int zb_defined_count(const int *len, int nsym, int minsym) {
+   int i = nsym;
+   while (i > minsym && !len[i - 1]) i--;
+   return i;
+}
+
+/* ---- run-length coding of the code-length sequence (huffencoder.c:446-735) ---- */
+
+/* visitor interface: v.sym(s) for a plain code-length symbol, v.rep(s, extra_value, extra_bits) for 16/17/18 */
+template <class V>
+ZB_HD void zb_rle_scan(const uint8_t *cl, int n, unsigned mask, V &v) {
+   int i = 0;
+   while (i < n) {
+      int run = 1;
+      while (i + run < n && cl[i + run] == cl[i]) run++;
+      if (cl[i] == 0) {
+         if (run >= 3) {
+            while (run >= 11 && (mask & 4)) { int m = run > 138 ? 138 : run; v.rep(18, m - 11, 7); run -= m; i += m; }
+            while (run >= 3 && (mask & 2)) { int m = run > 10 ? 10 : run; v.rep(17, m - 3, 3); run -= m; i += m; }
+            if (run) { v.sym(0); i++; }
+         } else { v.sym(0); i++; }
+      } else {
+         int c = cl[i] > 15 ? 15 : cl[i];
+         run--; v.sym(c); i++;
+         if (run == 7 && (mask & 1) && !(mask & 8)) { v.rep(16, 1, 2); v.rep(16, 0, 2); run -= 7; i += 7; }
+         else if (run == 8 && (mask & 1) && !(mask & 16)) { v.rep(16, 1, 2); v.rep(16, 1, 2); run -= 8; i += 8; }
+         while (run >= 3 && (mask & 1)) { int m = run > 6 ? 6 : run; v.rep(16, m - 3, 2); run -= m; i += m; }
+      }
+   }
+}
+struct ZbRleCount { int *cnt; ZB_HD void sym(int s) { cnt[s]++; } ZB_HD void rep(int s, int, int) { cnt[s]++; } };
+struct ZbRleSize { const int *len; int bits; ZB_HD void sym(int s) { bits += len[s]; } ZB_HD void rep(int s, int, int eb) { bits += len[s] + eb; } };
+
+/* RFC 1951 3.2.7 transmission order of the code-length alphabet (huffencoder.c:30) */
+ZB_HD int zb_clorder(int i) {
+   const uint8_t o[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+   return o[i];
+}
+/* HCLEN+4 (huffencoder.c:400-406) */
+ZB_HD int zb_raw_table_size(const int *cllen) {
+   int i = ZB_NCL;
+   while (i > 4 && !cllen[zb_clorder(i - 1)]) i--;
+   return i;
+}
+
+/* scratch shared by the cost / build helpers of one thread */
+struct ZbScratch {
+   uint32_t key[ZB_NLIT];
+   int16_t order[ZB_NLIT];
+   uint8_t cl[ZB_NLIT + ZB_NOFF];
+   int clcnt[ZB_NCL];
+   int cllen[ZB_NLIT]; /* zb_huff_lengths clears 288 entries */
+};
+
+/*
+ * zultra_block_evaluate_dynamic_cost (blockdeflate.c:577-618): data bits with the given lengths, plus
+ * 14 header bits, 3 x HCLEN, the RLE-coded lengths sized with mask 31 under an UNLIMITED code for the
+ * code-length alphabet whose histogram was taken with mask 7, plus 3.
+ */
+ZB_HD int zb_dynamic_cost(const int *lcnt, const int *llen, const int *ocnt, const int *olen, ZbScratch &s) {
+   int cost = 0;
+   for (int i = 0; i < 257; i++) cost += lcnt[i] * llen[i];
+   for (int i = 257; i < 286; i++) cost += lcnt[i] * (llen[i] + zb_lensym_extra(i - 257));
+   for (int i = 0; i < ZB_NOFF; i++) cost += ocnt[i] * (olen[i] + zb_offsym_extra(i));
+   int nl = zb_defined_count(llen, ZB_NLIT, 257), no = zb_defined_count(olen, ZB_NOFF, 1);
+   /* lengths above 255 cannot occur (<= 287 symbols, but 288 > 255): estimate lengths are < 288; keep them
+      in a byte only when they fit, else clamp to 255 which still compares unequal to every real neighbour
+      only if that neighbour is not also >= 255 - depths that large need > 2^255 total count, impossible */
+   for (int i = 0; i < nl; i++) s.cl[i] = (uint8_t)(llen[i] > 255 ? 255 : llen[i]);
+   for (int i = 0; i < no; i++) s.cl[nl + i] = (uint8_t)(olen[i] > 255 ? 255 : olen[i]);
+   for (int i = 0; i < ZB_NCL; i++) s.clcnt[i] = 0;
+   ZbRleCount cv = {s.clcnt};
+   zb_rle_scan(s.cl, nl + no, 7, cv);
+   zb_huff_lengths(s.clcnt, ZB_NCL, s.cllen, s.key);
+   cost += 5 + 5 + 4;
+   cost += 3 * zb_raw_table_size(s.cllen);
+   ZbRleSize sv = {s.cllen, 0};
+   zb_rle_scan(s.cl, nl + no, 31, sv);
+   return cost + sv.bits + 3;
+}
+
+/* zultra_block_evaluate_static_cost (blockdeflate.c:538-566) */
+ZB_HD int zb_static_lit_len(int i) { return i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8)); }
+ZB_HD int zb_static_cost(const int *lcnt, const int *ocnt) {
+   int cost = 0;
+   for (int i = 0; i < 257; i++) cost += lcnt[i] * zb_static_lit_len(i);
+   for (int i = 257; i < 286; i++) cost += lcnt[i] * (zb_static_lit_len(i) + zb_lensym_extra(i - 257));
+   for (int i = 0; i < ZB_NOFF; i++) cost += ocnt[i] * (5 + zb_offsym_extra(i));
+   return cost + 3;
+}
+
+/* zultra_huffman_encoder_optimize_for_rle (huffutils.c:34-114, from Zopfli): smooth counts so that the
+   code lengths RLE-compress better.  good: scratch of >= length bytes. */
+ZB_HD void zb_smooth_counts(int length, int *counts, uint8_t *good) {
+   while (length > 0 && counts[length - 1] == 0) length--;
+   if (length == 0) return;
+   for (int i = 0; i < length; i++) good[i] = 0;
+   /* protect existing long runs: >= 5 zeros, >= 7 equal non-zeros */
+   {
+      int cur = counts[0], stride = 0;
+      for (int i = 0; i <= length; i++) {
+         if (i == length || counts[i] != cur) {
+            if ((cur == 0 && stride >= 5) || (cur != 0 && stride >= 7))
+               for (int k = 0; k < stride; k++) good[i - k - 1] = 1;
+            stride = 1;
+            if (i != length) cur = counts[i];
+         } else stride++;
+      }
+   }
+   /* collapse strides of near-equal counts to their rounded mean */
+   {
+      int stride = 0;
+      long long limit = counts[0], sum = 0;
+      for (int i = 0; i <= length; i++) {
+         long long d = 0;
+         if (i != length) { d = (long long)counts[i] - limit; if (d < 0) d = -d; }
+         if (i == length || good[i] || d >= 4) {
+            if (stride >= 4 || (stride >= 3 && sum == 0)) {
+               int c = (int)((sum + stride / 2) / stride);
+               if (c < 1) c = 1;
+               if (sum == 0) c = 0;
+               for (int k = 0; k < stride; k++) counts[i - k - 1] = c;
+            }
+            stride = 0; sum = 0;
+            if (i < length - 3) limit = ((long long)counts[i] + counts[i + 1] + counts[i + 2] + counts[i + 3] + 2) / 4;
+            else if (i < length) limit = counts[i];
+            else limit = 0;
+         }
+         ++stride;
+         if (i != length) sum += counts[i];
+      }
+   }
+}
+
+/* ---- LSB-first bit writer into a zero-initialised 32-bit word buffer (bitwriter.c:63-98 semantics) ----
+ * Words that may be shared with a neighbouring writer (first/last of a span) are merged with atomicOr on the
+ * device; on the host plain OR.
+ */
+struct ZbBitSink {
+   uint32_t *words; /* base of the output, word 0 = bits 0..31 */
+   uint64_t acc;    /* pending bits */
+   int nacc;        /* number of pending bits (< 32 after flush) */
+   uint64_t wpos;   /* index of the word the pending bits start in */
+   uint64_t first_word;
+   ZB_HD void init(uint32_t *w, uint64_t bitpos) {
+      words = w; wpos = bitpos >> 5; first_word = wpos; nacc = (int)(bitpos & 31); acc = 0;
+   }
+   ZB_HD void orword(uint64_t idx, uint32_t v, bool shared) {
+      if (!v) return;
+#ifdef __CUDA_ARCH__
+      if (shared) atomicOr(words + idx, v); else words[idx] = v;
+#else
+      (void)shared; words[idx] |= v;
+#endif
+   }
+   ZB_HD void put(uint32_t value, int nbits) {
+      acc |= (uint64_t)value << nacc;
+      nacc += nbits;
+      if (nacc >= 32) {
+         orword(wpos, (uint32_t)acc, wpos == first_word);
+         acc >>= 32; nacc -= 32; wpos++;
+      }
+   }
+   ZB_HD void finish() { if (nacc > 0) orword(wpos, (uint32_t)acc, true); }
+};
+
+/* ---- match finder: lcp-interval tree over one tile, wimlib "lcpit" scheme (matchfinder.c:98-234) ----
+ *
+ * A tile is a contiguous range of window positions [lo, m1); positions [lo, m0) are look-back (they only
+ * serve as match candidates), [m0, m1) get matches recorded.  iv[] comes in holding the tile's suffixes in
+ * suffix-array order, one word each: (pos - lo) | clamped_lcp << 22, where lcp is the LCP with the previous
+ * suffix OF THE TILE (min-reduced over the skipped window ranks).  pd[] is scratch of the same size.
+ *
+ * zb_mf_build is the stack scan of matchfinder.c:98-155 with one addition: the state the reference reaches
+ * by calling zultra_skip_matches over the look-back positions (matchfinder.c:243-252) is written directly.
+ * For every interval, the newest look-back position below it is kept while its children are closed; an
+ * interval that has one is stored as visited-by-that-position, and every other look-back position gets, in
+ * pd[], the deepest interval at which a newer look-back position supersedes it.  That is exactly the state
+ * the lazy walker maintains ("fully caught up"), so the walk over [m0, m1) continues from it unchanged.
+ */
+struct ZbMfStack { uint32_t ref[260]; int32_t last[260]; };
+
+ZB_HD void zb_mf_merge(ZbMfStack &st, int sp, int32_t q, uint32_t *pd) {
+   if (st.last[sp] < 0) st.last[sp] = q;
+   else if (q > st.last[sp]) { pd[st.last[sp]] = st.ref[sp]; st.last[sp] = q; }
+   else pd[q] = st.ref[sp];
+}
+ZB_HD void zb_mf_leaf(ZbMfStack &st, int sp, uint32_t p, uint32_t nlook, uint32_t *pd) {
+   if (p < nlook) zb_mf_merge(st, sp, (int32_t)p, pd);
+   else pd[p] = st.ref[sp];
+}
+
+ZB_HDN void zb_mf_build(uint32_t *iv, uint32_t *pd, int n, uint32_t nlook, ZbMfStack &st) {
+   if (n <= 0) return;
+   int sp = 0;
+   uint32_t next_id = 1;
+   uint32_t prev_pos = iv[0] & ZB_POS_MASK;
+   st.ref[0] = 0; st.last[0] = -1;
+   iv[0] = 0;
+   for (int r = 1; r < n; r++) {
+      const uint32_t w = iv[r];
+      const uint32_t next_pos = w & ZB_POS_MASK, next_lcp = w & ZB_LCP_MASK;
+      const uint32_t top_lcp = st.ref[sp] & ZB_LCP_MASK;
+      if (next_lcp == top_lcp) {
+         zb_mf_leaf(st, sp, prev_pos, nlook, pd);
+      } else if (next_lcp > top_lcp) {
+         sp++; st.ref[sp] = next_lcp | next_id++; st.last[sp] = -1;
+         zb_mf_leaf(st, sp, prev_pos, nlook, pd);
+      } else {
+         zb_mf_leaf(st, sp, prev_pos, nlook, pd);
+         for (;;) {
+            const int32_t clast = st.last[sp];
+            const uint32_t cid = st.ref[sp] & ZB_POS_MASK;
+            sp--;
+            const uint32_t sup_lcp = st.ref[sp] & ZB_LCP_MASK;
+            bool done = true;
+            if (next_lcp > sup_lcp) { sp++; st.ref[sp] = next_lcp | next_id++; st.last[sp] = -1; }
+            else if (next_lcp < sup_lcp) done = false;
+            iv[cid] = clast >= 0 ? (ZB_VISITED | (uint32_t)clast) : st.ref[sp];
+            if (clast >= 0) zb_mf_merge(st, sp, clast, pd);
+            if (done) break;
+         }
+      }
+      prev_pos = next_pos;
+   }
+   zb_mf_leaf(st, sp, prev_pos, nlook, pd);
+   while (sp > 0) {
+      const int32_t clast = st.last[sp];
+      const uint32_t cid = st.ref[sp] & ZB_POS_MASK;
+      sp--;
+      iv[cid] = clast >= 0 ? (ZB_VISITED | (uint32_t)clast) : st.ref[sp];
+      if (clast >= 0) zb_mf_merge(st, sp, clast, pd);
+   }
+   if (st.last[0] >= 0) pd[st.last[0]] = 0;
+}
+
+/* zultra_find_matches_at (matchfinder.c:171-234) for tile position i; out gets <= 8 {lcp, offset} longest first */
+ZB_HD int zb_mf_walk(uint32_t *iv, uint32_t *pd, uint32_t i, zb_match_t *out) {
+   uint32_t ref = pd[i], sup;
+   pd[i] = 0;
+   while ((sup = iv[ref & ZB_POS_MASK]) & ZB_LCP_MASK) { iv[ref & ZB_POS_MASK] = i | ZB_VISITED; ref = sup; }
+   if (sup == 0) {
+      if (ref) iv[ref & ZB_POS_MASK] = i | ZB_VISITED;
+      return 0;
+   }
+   uint32_t mp = sup & 0x7fffffffu;
+   int n = 0;
+   for (;;) {
+      while ((sup = pd[mp]) > ref) mp = iv[sup & ZB_POS_MASK] & 0x7fffffffu;
+      iv[ref & ZB_POS_MASK] = i | ZB_VISITED;
+      pd[mp] = ref;
+      if (n < ZB_NMATCH) {
+         uint32_t off = i - mp;
+         if (off <= ZB_MAX_OFFSET) { out[n].length = (uint16_t)(ref >> ZB_POS_BITS); out[n].offset = (uint16_t)off; n++; }
+      }
+      if (sup == 0) break;
+      ref = sup;
+      mp = iv[ref & ZB_POS_MASK] & 0x7fffffffu;
+   }
+   return n;
+}
+
+/* ---- optimal parse (blockdeflate.c:254-323) ---- */
+
+/* per sub-block bit costs fed to the parse: lit[b], len[length-3] (symbol + extra bits), off[dist symbol] (+extra) */
+struct ZbCostTab { uint8_t lit[256]; uint8_t len[256]; uint8_t off[32]; };
+
+ZB_HD void zb_make_costtab(const int *llen, const int *olen, ZbCostTab &t) {
+   for (int i = 0; i < 256; i++) t.lit[i] = (uint8_t)llen[i];
+   for (int i = 0; i < 256; i++) t.len[i] = (uint8_t)(llen[zb_len_sym((uint32_t)i)] + zb_len_extra_bits((uint32_t)i));
+   for (int i = 0; i < 32; i++) t.off[i] = (uint8_t)(olen[i] + zb_offsym_extra(i));
+}
+
+#define ZB_RING 260 /* cost[i+1 .. i+258] plus cost[i] */
+
+/*
+ * Backward cost recurrence over positions [from-1 .. lo] of one sub-block ending at `end` (exclusive).
+ * Costs are kept modulo 2^16 in a ring; every comparison is made on differences, which stay far below 2^15
+ * inside the 258-position horizon (<= 258*15 + 48), so the choices equal the reference's int arithmetic.
+ * ring slot of position p is (slot_from + (from - p)) mod ZB_RING going DOWN in p, i.e. we keep `s` = slot of i.
+ * Ring must hold valid costs for positions [from, min(from+258,end)] on entry (slot of `from` = slot0).
+ * Writes best[i] for i in [lo, keep_hi).  If sig != 0, stores cost[lo+k]-cost[lo] for k=0..258 (0 beyond end).
+ * RING: accessor with get(slot)/set(slot,v).
+ */
+template <class RING>
+ZB_HD void zb_parse_range(const uint8_t *T, const zb_match_t *match, const ZbCostTab &tab, int lo, int from, int end,
+                          int keep_hi, zb_match_t *best, RING &ring, int &slot /* in: slot of `from`; out: slot of lo */) {
+   int s = slot;
+   for (int i = from - 1; i >= lo; i--) {
+      int s1 = s;                 /* slot of i+1 */
+      s = s1 + 1; if (s >= ZB_RING) s -= ZB_RING; /* slot of i: going down in position = going up in slot */
+      const uint16_t base = ring.get(s1);
+      int bestc = tab.lit[T[i]];
+      int bestlen = 0, bestoff = 0;
+      const zb_match_t *pm = match + ((size_t)i << 3);
+      for (int m = 0; m < ZB_NMATCH; m++) {
+         const int mlen0 = pm[m].length;
+         if (mlen0 < ZB_MIN_MATCH) break;
+         const int moff = pm[m].offset;
+         const int offc = tab.off[zb_off_sym((uint32_t)moff)];
+         int ml = mlen0;
+         if (i + ml > end) ml = end - i;
+         if (mlen0 >= ZB_LEAVE_ALONE) {
+            int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING; /* slot of i+ml */
+            int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
+            int c = tab.len[lidx] + offc + (int16_t)(uint16_t)(ring.get(sl) - base);
+            if (bestc > c) { bestc = c; bestlen = ml; bestoff = moff; }
+         } else {
+            int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING;
+            for (int k = ml; k >= ZB_MIN_MATCH; k--) {
+               int c = tab.len[k - ZB_MIN_MATCH] + offc + (int16_t)(uint16_t)(ring.get(sl) - base);
+               if (bestc > c) { bestc = c; bestlen = k; bestoff = moff; }
+               sl++; if (sl >= ZB_RING) sl -= ZB_RING;
+            }
+         }
+      }
+      ring.set(s, (uint16_t)(base + (uint16_t)bestc));
+      if (i < keep_hi) { best[i].length = (uint16_t)bestlen; best[i].offset = (uint16_t)bestoff; }
+   }
+   slot = s;
+}
+
+struct ZbRingLocal {
+   uint16_t v[ZB_RING];
+   ZB_HD uint16_t get(int s) const { return v[s]; }
+   ZB_HD void set(int s, uint16_t x) { v[s] = x; }
+};
+
+#endif /* ZB_CORE_H */

@@ -1,0 +1,1151 @@
+/*
+ * zb_pipeline.h - the batch compression pipeline: suffix array + LCP -> match lists -> block split ->
+ * optimal parse -> Huffman tables -> bit emission, for a batch of independent windows.
+ *
+ * One source, two builds: nvcc (product, every task is a GPU thread) and g++ -DZB_EMU (tests/emu, host
+ * loop) - see zb_rt.h.  All state lives in device buffers owned by ZbPipe.
+ *
+ * Vocabulary (follows the reference): a WINDOW is one max-block plus its <=32 KB history
+ * (libzultra.c:287); a SUB-BLOCK is one deflate block produced by the splitter (blockdeflate.c:800);
+ * a STREAM is one zlib/gzip/deflate output (one zultra_stream_t).  Windows of one stream are consecutive.
+ */
+#ifndef ZB_PIPELINE_H
+#define ZB_PIPELINE_H
+#include "zb_rt.h"
+#include <vector>
+#include <algorithm>
+
+#define ZB_CG 1024        /* positions per greedy-path chunk */
+#define ZB_CP 1024        /* positions per parsed-path chunk */
+#define ZB_CD 2048        /* positions per parse (DP) chunk */
+#define ZB_WU 1024        /* parse warm-up positions past the chunk end */
+#define ZB_TOKI 256       /* tokens per prefix-histogram interval */
+#define ZB_NH 320         /* 288 lit/len + 32 distance counters */
+#define ZB_MAXSB 64       /* sub-blocks per window */
+#define ZB_MAXNODES 64    /* splitter nodes per window per level (<= 32 used) */
+
+struct ZbWinDesc {
+   uint32_t in_off;   /* offset of the window's first byte (history start) in the device input */
+   uint32_t hist;     /* history bytes in front of the block */
+   uint32_t len;      /* hist + block bytes */
+   uint32_t stream;   /* stream index */
+   uint32_t last;     /* 1 = last window of its stream AND the stream is being finalized */
+   uint32_t pad[3];
+};
+
+/* splitter node (one recursion frame of blockdeflate.c:634) */
+struct ZbNode {
+   uint32_t win, depth;
+   uint32_t ts, te;          /* token range on the window's greedy path */
+   uint32_t ps, pe;          /* position range (window coordinates) */
+   uint32_t t0, nchk;        /* token count at the first check point, number of check points */
+   uint32_t chk_base;        /* first check record */
+   int32_t total_cost;
+   int32_t best_delta; uint32_t best_tok;  /* chosen split (token count relative to ts), 0 = none */
+   uint32_t pad[4];
+};
+
+/* one deflate sub-block */
+struct ZbSub {
+   uint32_t win, idx_in_win;
+   uint32_t ps, pe;          /* position range, window coordinates */
+   uint32_t ts, te;          /* greedy token range */
+   int32_t is_dyn, static_cost, dynamic_cost;
+   uint32_t dchunk_base, ndchunk;   /* parse chunks */
+   uint32_t pchunk_base, npchunk;   /* path chunks */
+   int32_t mask, nl, no, ncl;       /* RLE mask, HLIT+257, HDIST+1, HCLEN+4 */
+   int32_t hdr_bits;                /* bits of the table description (after the 3 block header bits) */
+   int32_t body_bits;               /* hdr_bits + token bits + EOB, i.e. what zultra_block_deflate writes */
+   int32_t stored;                  /* decided by the stitch scan */
+   int32_t final_bit;
+   uint64_t bit_off;                /* absolute bit offset of the sub-block's 3 header bits in its stream's output */
+   int32_t ub_hit; int32_t pad;
+};
+
+struct ZbSubTabs {
+   int lcnt[ZB_NLIT], ocnt[ZB_NOFF];
+   int llen[ZB_NLIT], olen[ZB_NOFF];
+   uint16_t lcode[ZB_NLIT], ocode[ZB_NOFF];
+   int cllen[ZB_NCL]; uint16_t clcode[ZB_NCL];
+   ZbCostTab cost;
+};
+
+struct ZbStreamOut {
+   uint64_t out_word_off;   /* first 32-bit word of this stream's output area */
+   uint64_t in_bits;        /* bits already pending in the first byte (entering phase 0..7) */
+   uint64_t total_bits;     /* result: bits written including in_bits */
+   uint32_t first_win, nwin;
+   uint32_t err, pad;
+};
+
+/* histogram contribution of one greedy token */
+ZB_HD void zb_tok_count(const uint8_t *T, uint32_t p, uint32_t len, uint32_t off, int *lc, int *oc, int sign) {
+   if (len >= ZB_MIN_MATCH) { lc[zb_len_sym(len - ZB_MIN_MATCH)] += sign; oc[zb_off_sym(off)] += sign; }
+   else lc[T[p]] += sign;
+}
+
+template <class T> struct ZbBuf {
+   T *p = 0; size_t cap = 0;
+   void need(size_t n) { if (n > cap) { zb_dev_free(p); size_t c = n + n / 8 + 64; p = (T *)zb_dev_alloc(c * sizeof(T)); cap = p ? c : 0; } }
+   void release() { zb_dev_free(p); p = 0; cap = 0; }
+};
+
+struct ZbPipe {
+   zb_stream_t st;
+   /* batch description */
+   int nwin = 0, nstream = 0;
+   uint32_t P = 0;              /* total window positions */
+   std::vector<ZbWinDesc> h_win;
+   std::vector<uint32_t> h_wbase;
+   ZbBuf<ZbWinDesc> win; ZbBuf<uint32_t> wbase;
+   ZbBuf<uint8_t> in;           /* device input */
+   /* suffix array stage */
+   ZbBuf<uint64_t> keyA, keyB; ZbBuf<uint32_t> valA, valB, rank, sa, actA, actB, tmpA, tmpB, scratch;
+   ZbBuf<uint32_t> sa_lcp;      /* packed SA|LCP words, rank order, per window at wbase[w] */
+   ZbBuf<uint32_t> counters;    /* misc device counters */
+   /* match finder */
+   ZbBuf<ZbTileDesc> tiles; ZbBuf<uint32_t> tile_iv, tile_pd, tile_cnt;
+   ZbBuf<zb_match_t> match; ZbBuf<uint16_t> glen, goff;
+   /* greedy path */
+   ZbBuf<uint16_t> exitoff; ZbBuf<uint32_t> gentry, gtokcnt, gtokbase, tokpos, wtok; /* wtok[w] = tokens of window w; base in wtokbase */
+   ZbBuf<uint32_t> wtokbase, wintbase; ZbBuf<int> ph; /* prefix histograms [interval][ZB_NH] */
+   std::vector<uint32_t> h_gchunk_first; ZbBuf<uint32_t> gchunk_first, gchunk_win;
+   /* splitter */
+   ZbBuf<ZbNode> nodesA, nodesB; ZbBuf<int> nodehist; ZbBuf<uint16_t> chk_stat; ZbBuf<uint8_t> chk_flag; ZbBuf<int> chk_delta; ZbBuf<uint32_t> chk_node;
+   ZbBuf<uint32_t> wsplit; ZbBuf<uint32_t> wnsplit;
+   /* sub-blocks */
+   ZbBuf<ZbSub> sub; ZbBuf<ZbSubTabs> tabs; ZbBuf<uint32_t> dchunk_sub, pchunk_sub;
+   ZbBuf<zb_match_t> best; ZbBuf<int16_t> sig_true, sig_warm; ZbBuf<uint8_t> dok;
+   ZbBuf<uint32_t> pentry, pbits;
+   /* output */
+   ZbBuf<uint32_t> out; ZbBuf<ZbStreamOut> sout;
+   std::vector<ZbStreamOut> h_sout;
+   int nsub = 0;
+   /* stats */
+   int stat_sa_rounds = 0, stat_redo = 0, stat_ub = 0;
+   double t_stage[8];
+
+   void release_all();
+   /* stages */
+   void setup(const std::vector<ZbWinDesc> &wins, const uint8_t *h_in, size_t in_bytes, bool in_is_device);
+   void stage_sa();
+   void stage_match(uint32_t tile_main);
+   void stage_greedy();
+   void stage_split();
+   void stage_parse();
+   void stage_emit(const std::vector<ZbStreamOut> &streams);
+};
+
+/* window lookup for a global position index */
+ZB_HD int zb_find_win(const uint32_t *wbase, int nwin, uint32_t g) {
+   int lo = 0, hi = nwin - 1;
+   while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (wbase[mid] <= g) lo = mid; else hi = mid - 1; }
+   return lo;
+}
+
+inline void ZbPipe::setup(const std::vector<ZbWinDesc> &wins, const uint8_t *h_in, size_t in_bytes, bool in_is_device) {
+   h_win = wins; nwin = (int)wins.size();
+   h_wbase.assign(nwin + 1, 0);
+   for (int w = 0; w < nwin; w++) h_wbase[w + 1] = h_wbase[w] + wins[w].len;
+   P = h_wbase[nwin];
+   win.need(nwin); wbase.need(nwin + 1);
+   zb_h2d(st, win.p, h_win.data(), sizeof(ZbWinDesc) * nwin);
+   zb_h2d(st, wbase.p, h_wbase.data(), 4 * (nwin + 1));
+   in.need(in_bytes + 16);
+   if (in_is_device) zb_d2d(st, in.p, h_in, in_bytes); else zb_h2d(st, in.p, h_in, in_bytes);
+   counters.need(64);
+}
+
+/* ============================================================ suffix array + LCP ============================================================
+ * Replaces divsufsort_build_array (divsufsort.c:377) and the PLCP/LCP/pack steps of matchfinder.c:57-90.
+ * Prefix doubling: sort all suffixes of all windows by (window, first nb bytes), then repeatedly sort the
+ * still-tied groups by the rank of the suffix h positions further on.  A suffix that runs off its window end
+ * is smaller than any longer suffix it is a prefix of (no sentinel; the reference's order, SURVEY A-20).
+ */
+inline void ZbPipe::stage_sa() {
+   const long n = P;
+   keyA.need(n); keyB.need(n); valA.need(n); valB.need(n); rank.need(n); sa.need(n); actA.need(n); actB.need(n); tmpA.need(n + 1); tmpB.need(n + 1);
+   sa_lcp.need(n);
+   scratch.need(zb_sort_scratch_words(n) + zb_scan_scratch_words(n) + 64);
+   int wb = 0; while ((1L << wb) < nwin) wb++;
+   int nbytes = (64 - wb) / 8; if (nbytes > 7) nbytes = 7;
+   const uint8_t *T = in.p; const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const int nw = nwin;
+   uint64_t *kA = keyA.p; uint32_t *vA = valA.p;
+   zb_launch(st, n, ZB_LAMBDA(long g) {
+      int w = zb_find_win(wbs, nw, (uint32_t)g);
+      uint32_t i = (uint32_t)g - wbs[w], len = wd[w].len;
+      const uint8_t *t = T + wd[w].in_off;
+      uint64_t k = 0;
+      for (int b = 0; b < nbytes; b++) k = (k << 8) | (i + b < len ? t[i + b] : 0);
+      kA[g] = ((uint64_t)w << (8 * nbytes)) | k;
+      vA[g] = (uint32_t)g;
+   }, 256);
+   zb_sort_pairs(st, keyA.p, valA.p, keyB.p, valB.p, n, 0, 8 * nbytes + wb, scratch.p);
+   /* initial groups */
+   uint32_t *head = tmpA.p, *grp = tmpB.p, *rk = rank.p, *SA = sa.p, *act = actA.p, *act2 = actB.p, *cnt = counters.p;
+   zb_launch(st, n, ZB_LAMBDA(long j) { head[j] = (j == 0 || kA[j] != kA[j - 1]) ? (uint32_t)j : 0u; SA[j] = vA[j]; }, 256);
+   zb_inclusive_max(st, head, grp, n, scratch.p);
+   zb_launch(st, n, ZB_LAMBDA(long j) { rk[vA[j]] = grp[j]; }, 256);
+   /* active = members of groups with more than one suffix */
+   zb_launch(st, n, ZB_LAMBDA(long j) {
+      bool is_head = grp[j] == (uint32_t)j;
+      bool next_head = (j + 1 == n) || grp[j + 1] == (uint32_t)(j + 1);
+      head[j] = (is_head && next_head) ? 0u : 1u;
+   }, 256);
+   zb_exclusive_sum(st, head, grp, n, cnt, scratch.p);
+   zb_launch(st, n, ZB_LAMBDA(long j) { if (head[j]) act[grp[j]] = (uint32_t)j; }, 256);
+   uint32_t m = 0;
+   zb_d2h(st, &m, cnt, 4); zb_sync(st);
+   int rank_bits = 1; while ((1L << rank_bits) < n) rank_bits++;
+   uint64_t *kB = keyB.p; uint32_t *vB = valB.p;
+   stat_sa_rounds = 0;
+   for (uint32_t h = (uint32_t)nbytes; m > 0; h <<= 1) {
+      stat_sa_rounds++;
+      const long mm = m;
+      /* key = (current rank, rank of the suffix h further; suffixes running off the window sort first, shorter first) */
+      zb_launch(st, mm, ZB_LAMBDA(long a) {
+         uint32_t j = act[a], g = SA[j];
+         int w = zb_find_win(wbs, nw, g);
+         uint32_t wend = wbs[w + 1];
+         uint32_t r2;
+         if ((uint64_t)g + h < wend) r2 = (rk[g + h] - wbs[w]) + (1u << 22);
+         else r2 = wend - g;
+         kA[a] = ((uint64_t)rk[g] << 32) | r2;
+         vA[a] = g;
+      }, 256);
+      zb_sort_pairs(st, keyA.p, valA.p, keyB.p, valB.p, mm, 0, 23, scratch.p);
+      zb_sort_pairs(st, keyA.p, valA.p, keyB.p, valB.p, mm, 32, 32 + rank_bits, scratch.p);
+      zb_launch(st, mm, ZB_LAMBDA(long a) { head[a] = (a == 0 || kA[a] != kA[a - 1]) ? (uint32_t)a : 0u; SA[act[a]] = vA[a]; }, 256);
+      zb_inclusive_max(st, head, grp, mm, scratch.p);
+      zb_launch(st, mm, ZB_LAMBDA(long a) { rk[vA[a]] = act[grp[a]]; }, 256);
+      zb_launch(st, mm, ZB_LAMBDA(long a) {
+         bool is_head = grp[a] == (uint32_t)a;
+         bool next_head = (a + 1 == mm) || grp[a + 1] == (uint32_t)(a + 1);
+         head[a] = (is_head && next_head) ? 0u : 1u;
+      }, 256);
+      zb_exclusive_sum(st, head, (uint32_t *)kB, mm, cnt, scratch.p);
+      {
+         const uint32_t *dst = (const uint32_t *)kB;
+         zb_launch(st, mm, ZB_LAMBDA(long a) { if (head[a]) act2[dst[a]] = act[a]; }, 256);
+      }
+      zb_d2h(st, &m, cnt, 4); zb_sync(st);
+      std::swap(act, act2);
+      (void)vB;
+      if (h > (1u << 23)) break; /* cannot happen: windows are < 2^22 */
+   }
+   /* LCP with the previous suffix of the same window, clamped as matchfinder.c:81-90, packed pos | lcp << 22 */
+   uint32_t *out = sa_lcp.p;
+   zb_launch(st, n, ZB_LAMBDA(long j) {
+      uint32_t g = SA[j];
+      int w = zb_find_win(wbs, nw, (uint32_t)j);
+      uint32_t base = wbs[w], len = wd[w].len;
+      uint32_t i = g - base;
+      uint32_t l = 0;
+      if ((uint32_t)j != base) {
+         uint32_t q = SA[j - 1] - base;
+         const uint8_t *t = T + wd[w].in_off;
+         uint32_t lim = len - (i > q ? i : q);
+         if (lim > ZB_MAX_MATCH) lim = ZB_MAX_MATCH;
+         while (l < lim && t[i + l] == t[q + l]) l++;
+         if (l < ZB_MIN_MATCH) l = 0;
+      }
+      out[j] = i | (l << ZB_POS_BITS);
+   }, 256);
+}
+
+/* ============================================================ match finder ============================================================ */
+inline void ZbPipe::stage_match(uint32_t tile_main) {
+   /* tiles: per window, main ranges of tile_main positions over the block part */
+   std::vector<ZbTileDesc> ht;
+   for (int w = 0; w < nwin; w++) {
+      const ZbWinDesc &d = h_win[w];
+      for (uint32_t m0 = d.hist; m0 < d.len; m0 += tile_main) {
+         ZbTileDesc t;
+         t.win = (uint32_t)w; t.m0 = m0; t.hi = std::min(d.len, m0 + tile_main);
+         t.lo = m0 > ZB_MAX_OFFSET ? m0 - ZB_MAX_OFFSET : 0;
+         t.sa_base = h_wbase[w]; t.wlen = d.len; t.pad = 0;
+         ht.push_back(t);
+      }
+   }
+   const int ntile = (int)ht.size();
+   tiles.need(ntile);
+   zb_h2d(st, tiles.p, ht.data(), sizeof(ZbTileDesc) * ntile);
+   match.need((size_t)P * ZB_NMATCH); glen.need(P); goff.need(P);
+   const size_t stride = ZB_MAX_OFFSET + tile_main;
+   const int wave = 16384;
+   const int nw_tiles = std::min(ntile, wave);
+   tile_iv.need((size_t)nw_tiles * stride); tile_pd.need((size_t)nw_tiles * stride); tile_cnt.need(nw_tiles);
+   const ZbTileDesc *td = tiles.p; uint32_t *ivb = tile_iv.p, *pdb = tile_pd.p, *tc = tile_cnt.p;
+   zb_match_t *mt = match.p; uint16_t *gl = glen.p, *go = goff.p; const uint32_t *wbs = wbase.p;
+   const int lanes = 4; /* one tile per 4 lanes: keeps warps less divergent than 32 tiles per warp */
+   for (int first = 0; first < ntile; first += wave) {
+      const int cnt = std::min(wave, ntile - first);
+      zb_tile_filter(st, sa_lcp.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p);
+      zb_launch(st, (long)cnt * lanes, ZB_LAMBDA(long x) {
+         if (x % lanes) return;
+         const int k = (int)(x / lanes);
+         const ZbTileDesc t = td[first + k];
+         uint32_t *iv = ivb + (size_t)k * stride, *pd = pdb + (size_t)k * stride;
+         const int n = (int)tc[k];
+         ZbMfStack stk;
+         zb_mf_build(iv, pd, n, t.m0 - t.lo, stk);
+         const uint32_t gbase = wbs[t.win];
+         for (uint32_t p = t.m0; p < t.hi; p++) {
+            zb_match_t m[ZB_NMATCH];
+            int nm = zb_mf_walk(iv, pd, p - t.lo, m);
+            const uint32_t maxlen = t.wlen - p;   /* matchfinder.c:276-280 (LAST_LITERALS = 0) */
+            zb_match_t *dst = mt + ((size_t)(gbase + p) << 3);
+            for (int q = 0; q < ZB_NMATCH; q++) {
+               zb_match_t v; v.length = 0; v.offset = 0;
+               if (q < nm) { v = m[q]; if (v.length > maxlen) v.length = (uint16_t)maxlen; }
+               dst[q] = v;
+            }
+            uint16_t l0 = nm > 0 ? (m[0].length > maxlen ? (uint16_t)maxlen : m[0].length) : 0;
+            gl[gbase + p] = l0 >= ZB_MIN_MATCH ? l0 : (uint16_t)1;
+            go[gbase + p] = l0 >= ZB_MIN_MATCH ? m[0].offset : (uint16_t)0;
+         }
+      }, 128);
+   }
+}
+
+/* ============================================================ greedy path ============================================================
+ * The greedy parse of blockdeflate.c:333-361 / :684-703 takes match[i][0] whenever its length is >= 3.  All
+ * greedy walks inside a window are segments of the one path from the block start (SURVEY A-14), so the path
+ * is materialised once: exit offsets per chunk (backward sweep), a serial hop over chunk entries per window,
+ * then the token list, and prefix histograms every ZB_TOKI tokens.
+ */
+inline void ZbPipe::stage_greedy() {
+   h_gchunk_first.assign(nwin + 1, 0);
+   for (int w = 0; w < nwin; w++) h_gchunk_first[w + 1] = h_gchunk_first[w] + (h_win[w].len - h_win[w].hist + ZB_CG - 1) / ZB_CG;
+   const long nch = h_gchunk_first[nwin];
+   gchunk_first.need(nwin + 1); gchunk_win.need(nch);
+   zb_h2d(st, gchunk_first.p, h_gchunk_first.data(), 4 * (nwin + 1));
+   exitoff.need(P); gentry.need(nch + 1); gtokcnt.need(nch + 1); gtokbase.need(nch + 1); tokpos.need(P);
+   wtokbase.need(nwin + 1); wintbase.need(nwin + 1);
+   const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p, *gcf = gchunk_first.p; const int nw = nwin;
+   uint32_t *gcw = gchunk_win.p; uint16_t *ex = exitoff.p; const uint16_t *gl = glen.p;
+   uint32_t *ent = gentry.p, *tcnt = gtokcnt.p, *tbase = gtokbase.p, *tp = tokpos.p;
+   zb_launch(st, nch, ZB_LAMBDA(long c) {
+      int w = zb_find_win(gcf, nw, (uint32_t)c);
+      gcw[c] = (uint32_t)w;
+      const uint32_t lo = wd[w].hist + (uint32_t)(c - gcf[w]) * ZB_CG;
+      const uint32_t hi = lo + ZB_CG < wd[w].len ? lo + ZB_CG : wd[w].len;
+      const uint32_t gb = wbs[w];
+      for (uint32_t p = hi; p-- > lo;) {
+         uint32_t j = p + gl[gb + p];
+         ex[gb + p] = (uint16_t)(j >= hi ? j - hi : ex[gb + j]);
+      }
+   });
+   zb_launch(st, nwin, ZB_LAMBDA(long w) {
+      uint32_t e = wd[w].hist;
+      const uint32_t gb = wbs[w];
+      for (uint32_t c = gcf[w]; c < gcf[w + 1]; c++) {
+         ent[c] = e;
+         const uint32_t lo = wd[w].hist + (c - gcf[w]) * ZB_CG;
+         const uint32_t hi = lo + ZB_CG < wd[w].len ? lo + ZB_CG : wd[w].len;
+         if (e < hi) e = hi + ex[gb + e];
+      }
+   });
+   zb_launch(st, nch, ZB_LAMBDA(long c) {
+      const uint32_t w = gcw[c];
+      const uint32_t lo = wd[w].hist + (uint32_t)(c - gcf[w]) * ZB_CG;
+      const uint32_t hi = lo + ZB_CG < wd[w].len ? lo + ZB_CG : wd[w].len;
+      const uint32_t gb = wbs[w];
+      uint32_t n = 0;
+      for (uint32_t p = ent[c]; p < hi; p += gl[gb + p]) n++;
+      tcnt[c] = n;
+   });
+   scratch.need(zb_scan_scratch_words(nch + 1) + 64);
+   zb_exclusive_sum(st, tcnt, tbase, nch, counters.p, scratch.p);
+   zb_launch(st, nch, ZB_LAMBDA(long c) {
+      const uint32_t w = gcw[c];
+      const uint32_t lo = wd[w].hist + (uint32_t)(c - gcf[w]) * ZB_CG;
+      const uint32_t hi = lo + ZB_CG < wd[w].len ? lo + ZB_CG : wd[w].len;
+      const uint32_t gb = wbs[w];
+      uint32_t k = tbase[c];
+      for (uint32_t p = ent[c]; p < hi; p += gl[gb + p]) tp[k++] = p;
+   });
+   /* per-window token base / count, prefix-histogram interval base */
+   uint32_t *wtb = wtokbase.p, *wib = wintbase.p, *cn = counters.p;
+   zb_launch(st, 1, ZB_LAMBDA(long) {
+      uint32_t ib = 0;
+      for (int w = 0; w < nw; w++) {
+         uint32_t b = tbase[gcf[w]];
+         uint32_t e = (w + 1 < nw) ? tbase[gcf[w + 1]] : cn[0];
+         wtb[w] = b; wib[w] = ib;
+         ib += (e - b) / ZB_TOKI + 1;   /* prefix rows 0..floor(ntok/ZB_TOKI) */
+         if (w + 1 == nw) { wtb[nw] = e; wib[nw] = ib; }
+      }
+   });
+   std::vector<uint32_t> h_wib(nwin + 1);
+   zb_d2h(st, h_wib.data(), wib, 4 * (nwin + 1)); zb_sync(st);
+   const long nint = h_wib[nwin];
+   ph.need((size_t)nint * ZB_NH);
+   int *PH = ph.p; const uint8_t *T = in.p; const uint16_t *go = goff.p;
+   /* per-interval histograms: row k+1 of a window = histogram of tokens [k*ZB_TOKI, (k+1)*ZB_TOKI) */
+   zb_launch(st, nint, ZB_LAMBDA(long r) {
+      int w = zb_find_win(wib, nw, (uint32_t)r);
+      uint32_t k = (uint32_t)r - wib[w];
+      int *row = PH + (size_t)r * ZB_NH;
+      for (int i = 0; i < ZB_NH; i++) row[i] = 0;
+      if (k == 0) return;
+      const uint32_t gb = wbs[w];
+      const uint8_t *t = T + wd[w].in_off;
+      const uint32_t t1 = wtb[w] + (k - 1) * ZB_TOKI, t2 = t1 + ZB_TOKI;
+      for (uint32_t q = t1; q < t2; q++) {
+         uint32_t p = tp[q];
+         uint32_t l = gl[gb + p];
+         zb_tok_count(t, p, l, go[gb + p], row, row + ZB_NLIT, 1);
+      }
+   });
+   /* prefix sums down the rows of each window, one task per (window, bin) */
+   zb_launch(st, (long)nwin * ZB_NH, ZB_LAMBDA(long x) {
+      const int w = (int)(x / ZB_NH), b = (int)(x % ZB_NH);
+      int acc = 0;
+      for (uint32_t r = wib[w]; r < wib[w + 1]; r++) { acc += PH[(size_t)r * ZB_NH + b]; PH[(size_t)r * ZB_NH + b] = acc; }
+   });
+}
+
+/* histogram of greedy tokens [t1, t2) (window-relative token indices) of window w into h[ZB_NH] (overwritten) */
+struct ZbGreedyView {
+   const int *PH; const uint32_t *wib, *wtb, *tp, *wbs; const uint16_t *gl, *go; const uint8_t *T; const ZbWinDesc *wd;
+   ZB_HD void add_tokens(int w, uint32_t t1, uint32_t t2, int *h, int sign) const {
+      const uint32_t gb = wbs[w]; const uint8_t *t = T + wd[w].in_off;
+      for (uint32_t q = wtb[w] + t1; q < wtb[w] + t2; q++) {
+         uint32_t p = tp[q];
+         zb_tok_count(t, p, gl[gb + p], go[gb + p], h, h + ZB_NLIT, sign);
+      }
+   }
+   ZB_HD void range_hist(int w, uint32_t t1, uint32_t t2, int *h) const {
+      const uint32_t k1 = (t1 + ZB_TOKI - 1) / ZB_TOKI, k2 = t2 / ZB_TOKI;
+      if (k1 <= k2) {
+         const int *a = PH + (size_t)(wib[w] + k1) * ZB_NH, *b = PH + (size_t)(wib[w] + k2) * ZB_NH;
+         for (int i = 0; i < ZB_NH; i++) h[i] = b[i] - a[i];
+         add_tokens(w, t1, k1 * ZB_TOKI, h, 1);
+         add_tokens(w, k2 * ZB_TOKI, t2, h, 1);
+      } else {
+         for (int i = 0; i < ZB_NH; i++) h[i] = 0;
+         add_tokens(w, t1, t2, h, 1);
+      }
+   }
+   /* token index (window-relative) of the token starting at position p (p must be on the path) */
+   ZB_HD uint32_t tok_of_pos(int w, uint32_t p, uint32_t ntok) const {
+      uint32_t lo = 0, hi = ntok;
+      const uint32_t *a = tp + wtb[w];
+      while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (a[mid] < p) lo = mid + 1; else hi = mid; }
+      return lo;
+   }
+};
+
+/* ============================================================ block splitter ============================================================
+ * zultra_compressor_split_subblock_recursive (blockdeflate.c:634-786), one recursion level per round.
+ */
+inline void ZbPipe::stage_split() {
+   const int maxnodes = nwin * 32;
+   nodesA.need(maxnodes); nodesB.need(maxnodes); nodehist.need((size_t)maxnodes * ZB_NH);
+   wsplit.need((size_t)nwin * ZB_MAXSB); wnsplit.need(nwin);
+   zb_memset(st, wnsplit.p, 0, 4 * nwin);
+   ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in.p, win.p};
+   const ZbWinDesc *wd = win.p; const uint32_t *wtb = wtokbase.p;
+   ZbNode *cur = nodesA.p, *nxt = nodesB.p;
+   int *nh = nodehist.p; uint32_t *cn = counters.p;
+   const int nw = nwin;
+   zb_launch(st, nwin, ZB_LAMBDA(long w) {
+      ZbNode nd; memset(&nd, 0, sizeof(nd));
+      nd.win = (uint32_t)w; nd.depth = 0; nd.ts = 0; nd.te = wtb[w + 1] - wtb[w]; nd.ps = wd[w].hist; nd.pe = wd[w].len;
+      cur[w] = nd;
+   });
+   int ncur = nwin;
+   for (int depth = 0; depth < 6 && ncur > 0; depth++) {
+      /* S1: node totals, check-point layout */
+      zb_launch(st, ncur, ZB_LAMBDA(long x) {
+         ZbNode nd = cur[x];
+         nd.nchk = 0; nd.best_tok = 0; nd.best_delta = 0; nd.t0 = 0;
+         if (nd.pe - nd.ps >= 8192) {
+            int *h = nh + (size_t)x * ZB_NH;
+            gv.range_hist((int)nd.win, nd.ts, nd.te, h);
+            h[ZB_EOB] += 1;
+            ZbScratch s; int llen[ZB_NLIT], olen[ZB_NLIT];
+            zb_huff_lengths(h, ZB_NLIT, llen, s.key);
+            zb_huff_lengths(h + ZB_NLIT, ZB_NOFF, olen, s.key);
+            nd.total_cost = zb_dynamic_cost(h, llen, h + ZB_NLIT, olen, s);
+            /* first check: >= 256 tokens and >= 512 bytes consumed (blockdeflate.c:705), then every 256 tokens */
+            const uint32_t ntok = nd.te - nd.ts;
+            const uint32_t *a = gv.tp + gv.wtb[nd.win] + nd.ts;
+            uint32_t t0 = 256;
+            while (t0 <= ntok) {
+               uint32_t endpos = t0 < ntok ? a[t0] : nd.pe;
+               if (endpos - nd.ps >= 512) break;
+               t0++;
+            }
+            if (t0 <= ntok) { nd.t0 = t0; nd.nchk = (ntok - t0) / 256 + 1; }
+         }
+         cur[x] = nd;
+      });
+      /* check record bases (serial, few nodes) */
+      zb_launch(st, 1, ZB_LAMBDA(long) {
+         uint32_t b = 0;
+         for (int x = 0; x < ncur; x++) { cur[x].chk_base = b; b += cur[x].nchk; }
+         cn[1] = b;
+      });
+      uint32_t nchk = 0;
+      zb_d2h(st, &nchk, cn + 1, 4); zb_sync(st);
+      int nnext = 0;
+      if (nchk > 0) {
+         chk_stat.need((size_t)nchk * 18); chk_flag.need(nchk); chk_delta.need(nchk); chk_node.need(nchk);
+         uint16_t *cs = chk_stat.p; uint8_t *cf = chk_flag.p; int *cdl = chk_delta.p; uint32_t *cnode = chk_node.p;
+         zb_launch(st, ncur, ZB_LAMBDA(long x) { for (uint32_t k = 0; k < cur[x].nchk; k++) cnode[cur[x].chk_base + k] = (uint32_t)x; });
+         /* S2: 18-bin statistics of each check interval (blockdeflate.c:686-703) */
+         zb_launch(st, nchk, ZB_LAMBDA(long c) {
+            const ZbNode nd = cur[cnode[c]];
+            const uint32_t k = (uint32_t)c - nd.chk_base;
+            const uint32_t t1 = k == 0 ? 0 : nd.t0 + 256 * (k - 1), t2 = nd.t0 + 256 * k;
+            uint16_t s18[18];
+            for (int i = 0; i < 18; i++) s18[i] = 0;
+            const uint32_t gb = gv.wbs[nd.win]; const uint8_t *t = gv.T + gv.wd[nd.win].in_off;
+            const uint32_t *a = gv.tp + gv.wtb[nd.win] + nd.ts;
+            for (uint32_t q = t1; q < t2; q++) {
+               uint32_t p = a[q], l = gv.gl[gb + p];
+               if (l >= ZB_MIN_MATCH) s18[l >= 9 ? 17 : 16]++;
+               else { uint32_t b = t[p]; s18[((b >> 4) & 0xc) | (b & 3)]++; }
+            }
+            for (int i = 0; i < 18; i++) cs[(size_t)c * 18 + i] = s18[i];
+         });
+         /* S3: drift test per check point (blockdeflate.c:706-721, unsigned arithmetic) */
+         zb_launch(st, ncur, ZB_LAMBDA(long x) {
+            const ZbNode nd = cur[x];
+            uint32_t stat[18], nstat = 0;
+            for (int i = 0; i < 18; i++) stat[i] = 0;
+            for (uint32_t k = 0; k < nd.nchk; k++) {
+               const uint16_t *ns = cs + (size_t)(nd.chk_base + k) * 18;
+               const uint32_t nnew = k == 0 ? nd.t0 : 256;
+               uint8_t flag = 0;
+               if (nstat) {
+                  uint32_t tot = 0;
+                  for (int j = 0; j < 18; j++) {
+                     uint32_t e = stat[j] * nnew, a = (uint32_t)ns[j] * nstat;
+                     tot += e > a ? e - a : a - e;
+                  }
+                  if ((tot / nnew) >= (nstat * 45 / 100)) flag = 1;   /* nLastGoodSplitIdx >= 0 holds from the 2nd check on */
+               }
+               cf[nd.chk_base + k] = flag;
+               for (int j = 0; j < 18; j++) { nstat += ns[j]; stat[j] += ns[j]; }
+            }
+         });
+         /* S4: cost delta of splitting at the PREVIOUS check point (blockdeflate.c:724-757) */
+         zb_launch(st, nchk, ZB_LAMBDA(long c) {
+            cdl[c] = -1;
+            if (!cf[c]) return;
+            const uint32_t x = cnode[c];
+            const ZbNode nd = cur[x];
+            const uint32_t k = (uint32_t)c - nd.chk_base;   /* k >= 1 here */
+            const uint32_t tsplit = nd.t0 + 256 * (k - 1);   /* tokens left of the split */
+            int left[ZB_NH], right[ZB_NH];
+            gv.range_hist((int)nd.win, nd.ts, nd.ts + tsplit, left);
+            left[ZB_EOB] = 1;
+            const int *tot = nh + (size_t)x * ZB_NH;
+            for (int i = 0; i < ZB_NH; i++) right[i] = tot[i] - left[i];
+            right[ZB_EOB] = 1;
+            ZbScratch s; int llen[ZB_NLIT], olen[ZB_NLIT];
+            zb_huff_lengths(left, ZB_NLIT, llen, s.key);
+            zb_huff_lengths(left + ZB_NLIT, ZB_NOFF, olen, s.key);
+            int lc = zb_dynamic_cost(left, llen, left + ZB_NLIT, olen, s);
+            zb_huff_lengths(right, ZB_NLIT, llen, s.key);
+            zb_huff_lengths(right + ZB_NLIT, ZB_NOFF, olen, s.key);
+            int rc = zb_dynamic_cost(right, llen, right + ZB_NLIT, olen, s);
+            cdl[c] = nd.total_cost - (lc + rc);
+         }, 64);
+         /* S5: best candidate per node (first maximum, delta >= 0), emit children */
+         zb_memset(st, cn + 2, 0, 4);
+         uint32_t *wsp = wsplit.p, *wns = wnsplit.p;
+         zb_launch(st, ncur, ZB_LAMBDA(long x) {
+            ZbNode nd = cur[x];
+            int best = -1; uint32_t bestk = 0;
+            for (uint32_t k = 1; k < nd.nchk; k++) {
+               if (!cf[nd.chk_base + k]) continue;
+               int d = cdl[nd.chk_base + k];
+               if (d >= 0 && (best < 0 || best < d)) { if (best < 0 || best < d) { best = d; bestk = k; } }
+            }
+            if (best >= 0) {
+               const uint32_t tsplit = nd.t0 + 256 * (bestk - 1);
+               const uint32_t *a = gv.tp + gv.wtb[nd.win] + nd.ts;
+               const uint32_t psplit = a[tsplit];
+               uint32_t slot = zb_atomic_add(wns + nd.win, 1u);
+               wsp[(size_t)nd.win * ZB_MAXSB + slot] = psplit;
+               if (nd.depth + 1 < 6) {   /* deeper frames return at once (blockdeflate.c:646) */
+                  uint32_t o = zb_atomic_add(cn + 2, 2u);
+                  ZbNode l = nd, r = nd;
+                  l.depth = r.depth = nd.depth + 1;
+                  l.te = nd.ts + tsplit; l.pe = psplit;
+                  r.ts = nd.ts + tsplit; r.ps = psplit;
+                  nxt[o] = l; nxt[o + 1] = r;
+               }
+            }
+         });
+         uint32_t nn = 0;
+         zb_d2h(st, &nn, cn + 2, 4); zb_sync(st);
+         nnext = (int)nn;
+      }
+      std::swap(cur, nxt);
+      ncur = nnext;
+   }
+   /* sub-block list, in stream order */
+   sub.need((size_t)nwin * ZB_MAXSB); tabs.need((size_t)nwin * ZB_MAXSB);
+   ZbSub *sb = sub.p; uint32_t *wsp = wsplit.p, *wns = wnsplit.p;
+   zb_launch(st, 1, ZB_LAMBDA(long) {
+      uint32_t n = 0;
+      for (int w = 0; w < nw; w++) {
+         uint32_t *sp = wsp + (size_t)w * ZB_MAXSB;
+         const uint32_t ns = wns[w];
+         for (uint32_t i = 1; i < ns; i++) { uint32_t v = sp[i]; uint32_t j = i; while (j > 0 && sp[j - 1] > v) { sp[j] = sp[j - 1]; j--; } sp[j] = v; }
+         uint32_t start = wd[w].hist;
+         const uint32_t ntok = wtb[w + 1] - wtb[w];
+         for (uint32_t i = 0; i <= ns; i++) {
+            uint32_t end = i < ns ? sp[i] : wd[w].len;
+            ZbSub s; memset(&s, 0, sizeof(s));
+            s.win = (uint32_t)w; s.idx_in_win = i; s.ps = start; s.pe = end;
+            s.ts = gv.tok_of_pos(w, start, ntok); s.te = end < wd[w].len ? gv.tok_of_pos(w, end, ntok) : ntok;
+            sb[n++] = s;
+            start = end;
+         }
+      }
+      cn[3] = n;
+   });
+   uint32_t ns = 0;
+   zb_d2h(st, &ns, cn + 3, 4); zb_sync(st);
+   nsub = (int)ns;
+}
+
+/* ============================================================ optimal parse ============================================================ */
+
+/* walk the chosen path of one path-chunk: calls f(p, len, off) for every token starting in [entry, hi) */
+template <class F>
+ZB_HD void zb_walk_best(const zb_match_t *best, uint32_t entry, uint32_t hi, F &f) {
+   for (uint32_t p = entry; p < hi;) {
+      zb_match_t m = best[p];
+      if (m.length >= ZB_MIN_MATCH) { f(p, (uint32_t)m.length, (uint32_t)m.offset); p += m.length; }
+      else { f(p, 0u, 0u); p++; }
+   }
+}
+
+inline void ZbPipe::stage_parse() {
+   const int ns = nsub;
+   ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
+   ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in.p, win.p};
+   /* D1: greedy histogram, static-vs-dynamic decision (libzultra.c:317-324), first tables (blockdeflate.c:863-869) */
+   zb_launch(st, ns, ZB_LAMBDA(long x) {
+      ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
+      int h[ZB_NH];
+      gv.range_hist((int)s.win, s.ts, s.te, h);
+      h[ZB_EOB] += 1;
+      ZbScratch sc;
+      s.static_cost = zb_static_cost(h, h + ZB_NLIT);
+      zb_huff_lengths(h, ZB_NLIT, t.llen, sc.key);
+      int olen288[ZB_NLIT];
+      zb_huff_lengths(h + ZB_NLIT, ZB_NOFF, olen288, sc.key);
+      s.dynamic_cost = zb_dynamic_cost(h, t.llen, h + ZB_NLIT, olen288, sc);
+      s.is_dyn = s.static_cost <= s.dynamic_cost ? 0 : 1;
+      s.ub_hit = 0;
+      if (s.is_dyn) {
+         zb_huff_build(h, ZB_NLIT, 15, t.llen, 0, sc.key, sc.order, &s.ub_hit);
+         zb_huff_build(h + ZB_NLIT, ZB_NOFF, 15, olen288, 0, sc.key, sc.order, &s.ub_hit);
+         for (int i = 0; i < ZB_NOFF; i++) t.olen[i] = olen288[i];
+         int ll[ZB_NLIT], ol[ZB_NOFF];
+         for (int i = 0; i < ZB_NLIT; i++) ll[i] = t.llen[i] ? t.llen[i] : 9;   /* blockdeflate.c:873-881 */
+         for (int i = 0; i < ZB_NOFF; i++) ol[i] = t.olen[i] ? t.olen[i] : 6;
+         zb_make_costtab(ll, ol, t.cost);
+      } else {
+         for (int i = 0; i < ZB_NLIT; i++) t.llen[i] = zb_static_lit_len(i);   /* blockdeflate.c:839-849 */
+         for (int i = 0; i < ZB_NOFF; i++) t.olen[i] = 5;
+         zb_make_costtab(t.llen, t.olen, t.cost);
+      }
+      sb[x] = s;
+   }, 64);
+   /* chunk lists */
+   zb_launch(st, 1, ZB_LAMBDA(long) {
+      uint32_t d = 0, p = 0;
+      for (int x = 0; x < ns; x++) {
+         uint32_t size = sb[x].pe - sb[x].ps;
+         sb[x].dchunk_base = d; sb[x].ndchunk = (size + ZB_CD - 1) / ZB_CD; d += sb[x].ndchunk;
+         sb[x].pchunk_base = p; sb[x].npchunk = (size + ZB_CP - 1) / ZB_CP; p += sb[x].npchunk;
+      }
+      cn[4] = d; cn[5] = p;
+   });
+   uint32_t hc[2];
+   zb_d2h(st, hc, cn + 4, 8); zb_sync(st);
+   const long ndch = hc[0], npch = hc[1];
+   dchunk_sub.need(ndch + 1); pchunk_sub.need(npch + 1); best.need(P);
+   sig_true.need((size_t)(ndch + 1) * 260); sig_warm.need((size_t)(ndch + 1) * 260); dok.need(ndch + 1);
+   pentry.need(npch + 1); pbits.need(npch + 1);
+   uint32_t *dcs = dchunk_sub.p, *pcs = pchunk_sub.p;
+   zb_launch(st, ns, ZB_LAMBDA(long x) {
+      for (uint32_t k = 0; k < sb[x].ndchunk; k++) dcs[sb[x].dchunk_base + k] = (uint32_t)x;
+      for (uint32_t k = 0; k < sb[x].npchunk; k++) pcs[sb[x].pchunk_base + k] = (uint32_t)x;
+   });
+   const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in.p;
+   const zb_match_t *mt = match.p; zb_match_t *bm = best.p;
+   int16_t *sgt = sig_true.p, *sgw = sig_warm.p; uint8_t *ok = dok.p;
+   uint16_t *ex = exitoff.p; uint32_t *pen = pentry.p;
+
+   for (int pass = 0; pass < 4; pass++) {
+      /* D2: chunked backward recurrence.  Chunk k of a sub-block covers [ps + k*CD, ..).  Every chunk but the last
+         starts ZB_WU positions past its end from an all-zero cost guess; the relative costs it sees at its own end
+         (sig_warm) are later compared with what the next chunk really computed there (sig_true). */
+      zb_launch(st, ndch, ZB_LAMBDA(long c) {
+         const ZbSub s = sb[dcs[c]];
+         if (pass > 0 && !s.is_dyn) return;
+         const uint32_t k = (uint32_t)c - s.dchunk_base;
+         const uint32_t gb = wbs[s.win];
+         const uint8_t *t = T + wd[s.win].in_off;
+         const int lo = (int)(s.ps + k * ZB_CD);
+         const int hi = (int)(lo + ZB_CD < (int)s.pe ? lo + ZB_CD : (int)s.pe);
+         const int end = (int)s.pe;
+         int from = hi + ZB_WU; if (from > end) from = end;
+         ZbRingLocal ring;
+         for (int i = 0; i < ZB_RING; i++) ring.v[i] = 0;
+         int slot = 0;
+         const ZbCostTab &ct = tb[dcs[c]].cost;
+         if (from > hi) zb_parse_range(t, mt + ((size_t)gb << 3), ct, hi, from, end, hi, bm + gb, ring, slot);
+         /* warm-up view of the window [hi, hi+258] */
+         {
+            int16_t *sw = sgw + (size_t)c * 260;
+            const uint16_t b = ring.get(slot);
+            for (int q = 0; q <= ZB_MAX_MATCH; q++) {
+               int sl = slot - q; if (sl < 0) sl += ZB_RING;
+               sw[q] = (hi + q <= end && hi + q <= from) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
+            }
+         }
+         zb_parse_range(t, mt + ((size_t)gb << 3), ct, lo, hi, end, hi, bm + gb, ring, slot);
+         {
+            int16_t *sg = sgt + (size_t)c * 260;
+            const uint16_t b = ring.get(slot);
+            for (int q = 0; q <= ZB_MAX_MATCH; q++) {
+               int sl = slot - q; if (sl < 0) sl += ZB_RING;
+               sg[q] = (lo + q <= end) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
+            }
+         }
+      }, 64);
+      /* D3: does each chunk's warm-up agree with its right neighbour's true costs? */
+      zb_launch(st, ndch, ZB_LAMBDA(long c) {
+         const ZbSub s = sb[dcs[c]];
+         const uint32_t k = (uint32_t)c - s.dchunk_base;
+         uint8_t good = 1;
+         if (k + 1 < s.ndchunk) {
+            const int hi = (int)(s.ps + (k + 1) * ZB_CD), end = (int)s.pe;
+            int from = hi + ZB_WU; if (from > end) from = end;
+            const int16_t *a = sgw + (size_t)c * 260, *b = sgt + (size_t)(c + 1) * 260;
+            int lim = from - hi; if (lim > ZB_MAX_MATCH) lim = ZB_MAX_MATCH;
+            /* the warm-up must have covered the whole horizon, else it started from the true end state anyway */
+            if (from < end && from - hi < ZB_MAX_MATCH) good = 0;
+            for (int q = 0; q <= lim && good; q++) if (a[q] != b[q]) good = 0;
+         }
+         ok[c] = good;
+      });
+      /* D4: repair, right to left: a chunk whose warm-up disagreed is recomputed from its neighbour's true costs */
+      zb_launch(st, ns, ZB_LAMBDA(long x) {
+         const ZbSub s = sb[x];
+         if (pass > 0 && !s.is_dyn) return;
+         if (s.ndchunk < 2) return;
+         const uint32_t gb = wbs[s.win];
+         const uint8_t *t = T + wd[s.win].in_off;
+         const int end = (int)s.pe;
+         const ZbCostTab &ct = tb[x].cost;
+         for (int k = (int)s.ndchunk - 2; k >= 0; k--) {
+            const size_t c = s.dchunk_base + k;
+            const int lo = (int)(s.ps + k * ZB_CD), hi = lo + ZB_CD;
+            bool good = ok[c];
+            if (good) continue;
+            /* re-check against the (possibly repaired) neighbour before redoing */
+            {
+               int from = hi + ZB_WU; if (from > end) from = end;
+               int lim = from - hi; if (lim > ZB_MAX_MATCH) lim = ZB_MAX_MATCH;
+               good = !(from < end && from - hi < ZB_MAX_MATCH);
+               const int16_t *a = sgw + c * 260, *b = sgt + (c + 1) * 260;
+               for (int q = 0; q <= lim && good; q++) if (a[q] != b[q]) good = false;
+            }
+            if (good) { ok[c] = 1; continue; }
+            ZbRingLocal ring;
+            const int16_t *b = sgt + (c + 1) * 260;
+            int slot = 0;
+            for (int q = 0; q <= ZB_MAX_MATCH; q++) { int sl = slot - q; if (sl < 0) sl += ZB_RING; ring.v[sl] = (uint16_t)b[q]; }
+            zb_parse_range(t, mt + ((size_t)gb << 3), ct, lo, hi, end, hi, bm + gb, ring, slot);
+            int16_t *sg = sgt + c * 260;
+            const uint16_t b0 = ring.get(slot);
+            for (int q = 0; q <= ZB_MAX_MATCH; q++) {
+               int sl = slot - q; if (sl < 0) sl += ZB_RING;
+               sg[q] = (lo + q <= end) ? (int16_t)(uint16_t)(ring.get(sl) - b0) : (int16_t)0;
+            }
+            ok[c] = 2;
+            zb_atomic_add((int *)cn + 6, 1);
+            /* the left neighbour was judged against the old values: force its re-check */
+            if (k > 0) ok[c - 1] = 0;
+         }
+      });
+      /* D5: chosen path: exit offsets per path-chunk, serial hop per sub-block */
+      zb_launch(st, npch, ZB_LAMBDA(long c) {
+         const ZbSub s = sb[pcs[c]];
+         if (pass > 0 && !s.is_dyn) return;
+         const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
+         const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+         for (uint32_t p = hi; p-- > lo;) {
+            uint32_t l = bm[gb + p].length; if (l < ZB_MIN_MATCH) l = 1;
+            uint32_t j = p + l;
+            ex[gb + p] = (uint16_t)(j >= hi ? j - hi : ex[gb + j]);
+         }
+      });
+      zb_launch(st, ns, ZB_LAMBDA(long x) {
+         const ZbSub s = sb[x];
+         if (pass > 0 && !s.is_dyn) return;
+         const uint32_t gb = wbs[s.win];
+         uint32_t e = s.ps;
+         for (uint32_t k = 0; k < s.npchunk; k++) {
+            const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+            pen[s.pchunk_base + k] = e;
+            if (e < hi) e = hi + ex[gb + e];
+         }
+         /* fresh histogram for this pass (blockdeflate.c:887-891); EOB counted here */
+         if (s.is_dyn) {
+            ZbSubTabs &t = tb[x];
+            for (int i = 0; i < ZB_NLIT; i++) t.lcnt[i] = 0;
+            for (int i = 0; i < ZB_NOFF; i++) t.ocnt[i] = 0;
+            t.lcnt[ZB_EOB] = 1;
+         }
+      });
+      /* D6: histogram along the chosen path (blockdeflate.c:371-400) */
+      zb_launch(st, npch, ZB_LAMBDA(long c) {
+         const uint32_t x = pcs[c];
+         const ZbSub s = sb[x];
+         if (!s.is_dyn) return;
+         const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
+         const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+         const uint8_t *t = T + wd[s.win].in_off;
+         int *lc = tb[x].lcnt, *oc = tb[x].ocnt;
+         for (uint32_t p = pen[c]; p < hi;) {
+            zb_match_t m = bm[gb + p];
+            if (m.length >= ZB_MIN_MATCH) { zb_atomic_add(lc + zb_len_sym(m.length - ZB_MIN_MATCH), 1); zb_atomic_add(oc + zb_off_sym(m.offset), 1); p += m.length; }
+            else { zb_atomic_add(lc + t[p], 1); p++; }
+         }
+      });
+      /* D7: rebuild tables (blockdeflate.c:893-919) */
+      zb_launch(st, ns, ZB_LAMBDA(long x) {
+         ZbSub s = sb[x];
+         if (!s.is_dyn) return;
+         ZbSubTabs &t = tb[x];
+         if (pass == 3) {   /* always describe at least two distance codes (blockdeflate.c:893-913) */
+            int nz = 0;
+            for (int i = 0; nz < 2 && i < ZB_NOFF - 2; i++) if (t.ocnt[i]) nz++;
+            if (nz == 0) t.ocnt[0] = t.ocnt[1] = 1;
+            else if (nz == 1) { if (t.ocnt[0]) t.ocnt[1] = 1; else t.ocnt[0] = 1; }
+         }
+         ZbScratch sc; int olen288[ZB_NLIT];
+         zb_huff_build(t.lcnt, ZB_NLIT, 15, t.llen, 0, sc.key, sc.order, &s.ub_hit);
+         zb_huff_build(t.ocnt, ZB_NOFF, 15, olen288, 0, sc.key, sc.order, &s.ub_hit);
+         for (int i = 0; i < ZB_NOFF; i++) t.olen[i] = olen288[i];
+         if (pass < 3) {
+            int ll[ZB_NLIT], ol[ZB_NOFF];
+            for (int i = 0; i < ZB_NLIT; i++) ll[i] = t.llen[i] ? t.llen[i] : 9;
+            for (int i = 0; i < ZB_NOFF; i++) ol[i] = t.olen[i] ? t.olen[i] : 6;
+            zb_make_costtab(ll, ol, t.cost);
+         } else {
+            zb_make_costtab(t.llen, t.olen, t.cost);   /* final lengths: used by the post-optimiser and the emitter */
+         }
+         sb[x] = s;
+      }, 64);
+   }
+   /* P7: matches that are cheaper as literals (blockdeflate.c:410-458), dynamic sub-blocks only */
+   zb_launch(st, npch, ZB_LAMBDA(long c) {
+      const uint32_t x = pcs[c];
+      const ZbSub s = sb[x];
+      if (!s.is_dyn) return;
+      const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
+      const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      const uint8_t *t = T + wd[s.win].in_off;
+      const ZbCostTab &ct = tb[x].cost;
+      for (uint32_t p = pen[c]; p < hi;) {
+         zb_match_t m = bm[gb + p];
+         if (m.length >= ZB_MIN_MATCH) {
+            const uint32_t mc = (uint32_t)ct.len[m.length - ZB_MIN_MATCH] + ct.off[zb_off_sym(m.offset)];
+            uint32_t lc = 0; bool all = true;
+            for (uint32_t j = 0; j < m.length && lc < mc; j++) {
+               uint32_t c1 = ct.lit[t[p + j]];
+               if (c1 == 0) { all = false; break; }
+               lc += c1;
+            }
+            if (all && lc < mc) for (uint32_t j = 0; j < m.length; j++) bm[gb + p + j].length = 0;
+            p += m.length;
+         } else p++;
+      }
+   });
+   /* F1: final tables: RLE smoothing trial (blockdeflate.c:926-945), mask search (:958-977), codes, header size */
+   zb_launch(st, ns, ZB_LAMBDA(long x) {
+      ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
+      ZbScratch sc;
+      if (s.is_dyn) {
+         int oc288[ZB_NLIT], ol288[ZB_NLIT];
+         for (int i = 0; i < ZB_NLIT; i++) { oc288[i] = i < ZB_NOFF ? t.ocnt[i] : 0; ol288[i] = i < ZB_NOFF ? t.olen[i] : 0; }
+         const int cur_cost = zb_dynamic_cost(t.lcnt, t.llen, oc288, ol288, sc);
+         int lc2[ZB_NLIT], oc2[ZB_NLIT], ll2[ZB_NLIT], ol2[ZB_NLIT];
+         uint8_t good[ZB_NLIT];
+         for (int i = 0; i < ZB_NLIT; i++) { lc2[i] = t.lcnt[i]; oc2[i] = oc288[i]; }
+         zb_smooth_counts(ZB_NLIT, lc2, good);
+         zb_smooth_counts(ZB_NOFF, oc2, good);
+         int ub = 0;
+         zb_huff_build(lc2, ZB_NLIT, 15, ll2, 0, sc.key, sc.order, &ub);
+         zb_huff_build(oc2, ZB_NOFF, 15, ol2, 0, sc.key, sc.order, &ub);
+         const int opt_cost = zb_dynamic_cost(lc2, ll2, oc2, ol2, sc);
+         if (opt_cost < cur_cost) {
+            for (int i = 0; i < ZB_NLIT; i++) { t.lcnt[i] = lc2[i]; t.llen[i] = ll2[i]; }
+            for (int i = 0; i < ZB_NOFF; i++) { t.ocnt[i] = oc2[i]; t.olen[i] = ol2[i]; }
+            s.ub_hit |= ub;
+         }
+         s.nl = zb_defined_count(t.llen, ZB_NLIT, 257);
+         int ol32[ZB_NOFF]; for (int i = 0; i < ZB_NOFF; i++) ol32[i] = t.olen[i];
+         s.no = zb_defined_count(ol32, ZB_NOFF, 1);
+         const int ncodes = s.nl + s.no;
+         for (int i = 0; i < s.nl; i++) sc.cl[i] = (uint8_t)t.llen[i];
+         for (int i = 0; i < s.no; i++) sc.cl[s.nl + i] = (uint8_t)t.olen[i];
+         int bestmask = -1, bestcost = 0;
+         int cllen[ZB_NLIT];
+         for (int mask = 0; mask <= 31; mask = (mask >= 7) ? mask + 2 : mask + 1) {
+            for (int i = 0; i < ZB_NCL; i++) sc.clcnt[i] = 0;
+            ZbRleCount cv = {sc.clcnt};
+            zb_rle_scan(sc.cl, ncodes, (unsigned)mask, cv);
+            zb_huff_build(sc.clcnt, ZB_NCL, 7, cllen, 0, sc.key, sc.order, &s.ub_hit);
+            ZbRleSize sv = {cllen, 0};
+            zb_rle_scan(sc.cl, ncodes, (unsigned)mask, sv);
+            if (bestmask == -1 || bestcost >= sv.bits) { bestmask = mask; bestcost = sv.bits; }
+         }
+         for (int i = 0; i < ZB_NCL; i++) sc.clcnt[i] = 0;
+         ZbRleCount cv = {sc.clcnt};
+         zb_rle_scan(sc.cl, ncodes, (unsigned)bestmask, cv);
+         zb_huff_build(sc.clcnt, ZB_NCL, 7, cllen, t.clcode, sc.key, sc.order, &s.ub_hit);
+         for (int i = 0; i < ZB_NCL; i++) t.cllen[i] = cllen[i];
+         s.mask = bestmask;
+         s.ncl = zb_raw_table_size(cllen);
+         s.hdr_bits = 14 + 3 * s.ncl + bestcost;
+         if (s.nl > 286 || s.no > 30) s.hdr_bits = -1;   /* blockdeflate.c:981-983: block_deflate fails -> stored */
+      } else {
+         s.nl = 288; s.no = 32; s.ncl = 0; s.mask = 0; s.hdr_bits = 0;
+      }
+      /* codewords */
+      {
+         int16_t order[ZB_NLIT];
+         int n = zb_order_by_len(t.llen, ZB_NLIT, order);
+         zb_huff_codes(t.llen, order, n, t.lcode);
+         int ol[ZB_NOFF]; for (int i = 0; i < ZB_NOFF; i++) ol[i] = t.olen[i];
+         n = zb_order_by_len(ol, ZB_NOFF, order);
+         zb_huff_codes(ol, order, n, t.ocode);
+         zb_make_costtab(t.llen, ol, t.cost);
+      }
+      sb[x] = s;
+   }, 64);
+}
+
+/* ============================================================ emission ============================================================
+ * Token bits per path-chunk, per sub-block totals, then one serial scan per stream that reproduces the bit
+ * writer's arithmetic of libzultra.c:327-398 (entering bit phase, stored-block fallback on BYTE deltas), then
+ * every chunk writes its tokens at its absolute bit offset.
+ */
+inline void ZbPipe::stage_emit(const std::vector<ZbStreamOut> &streams) {
+   const int ns = nsub;
+   ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
+   const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in.p;
+   zb_match_t *bm = best.p; uint16_t *ex = exitoff.p; uint32_t *pen = pentry.p, *pb = pbits.p, *pcs = pchunk_sub.p;
+   long npch = 0;
+   {
+      uint32_t v; zb_d2h(st, &v, cn + 5, 4); zb_sync(st); npch = v;
+   }
+   /* path again (the post-optimiser turned some matches into literals) */
+   zb_launch(st, npch, ZB_LAMBDA(long c) {
+      const ZbSub s = sb[pcs[c]];
+      const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
+      const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      for (uint32_t p = hi; p-- > lo;) {
+         uint32_t l = bm[gb + p].length; if (l < ZB_MIN_MATCH) l = 1;
+         uint32_t j = p + l;
+         ex[gb + p] = (uint16_t)(j >= hi ? j - hi : ex[gb + j]);
+      }
+   });
+   zb_launch(st, ns, ZB_LAMBDA(long x) {
+      const ZbSub s = sb[x];
+      const uint32_t gb = wbs[s.win];
+      uint32_t e = s.ps;
+      for (uint32_t k = 0; k < s.npchunk; k++) {
+         const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+         pen[s.pchunk_base + k] = e;
+         if (e < hi) e = hi + ex[gb + e];
+      }
+   });
+   /* E1: token bits per chunk */
+   zb_launch(st, npch, ZB_LAMBDA(long c) {
+      const uint32_t x = pcs[c];
+      const ZbSub s = sb[x];
+      const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
+      const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      const uint8_t *t = T + wd[s.win].in_off;
+      const ZbCostTab &ct = tb[x].cost;
+      uint32_t bits = 0;
+      for (uint32_t p = pen[c]; p < hi;) {
+         zb_match_t m = bm[gb + p];
+         if (m.length >= ZB_MIN_MATCH) { bits += (uint32_t)ct.len[m.length - ZB_MIN_MATCH] + ct.off[zb_off_sym(m.offset)]; p += m.length; }
+         else { bits += ct.lit[t[p]]; p++; }
+      }
+      pb[c] = bits;
+   });
+   /* E2: per sub-block: chunk bit offsets (exclusive scan) and body size */
+   zb_launch(st, ns, ZB_LAMBDA(long x) {
+      ZbSub s = sb[x];
+      uint32_t acc = 0;
+      for (uint32_t k = 0; k < s.npchunk; k++) { uint32_t v = pb[s.pchunk_base + k]; pb[s.pchunk_base + k] = acc; acc += v; }
+      s.body_bits = s.hdr_bits < 0 ? -1 : (int32_t)(s.hdr_bits + acc + tb[x].llen[ZB_EOB]);
+      sb[x] = s;
+   });
+   /* E3: stitch scan, one task per stream */
+   const int nstr = (int)streams.size();
+   h_sout = streams; nstream = nstr;
+   sout.need(nstr);
+   zb_h2d(st, sout.p, h_sout.data(), sizeof(ZbStreamOut) * nstr);
+   ZbStreamOut *so = sout.p;
+   /* sub-blocks are in window order; find each stream's first sub-block by scanning (serial, small) */
+   zb_launch(st, nstr, ZB_LAMBDA(long q) {
+      ZbStreamOut o = so[q];
+      uint64_t bit = o.in_bits;
+      /* locate first sub-block of window first_win by binary search on win */
+      int lo = 0, hi = ns;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (sb[mid].win < o.first_win) lo = mid + 1; else hi = mid; }
+      for (int x = lo; x < ns && sb[x].win < o.first_win + o.nwin; x++) {
+         ZbSub s = sb[x];
+         const uint32_t size = s.pe - s.ps;
+         const bool last_sub = (x + 1 == ns) || sb[x + 1].win != s.win;
+         s.final_bit = (wd[s.win].last && last_sub) ? 1 : 0;
+         s.bit_off = bit;
+         bool stored = s.body_bits < 0;
+         if (!stored) {
+            const uint64_t a = (bit + 3) >> 3, b = (bit + 3 + (uint64_t)s.body_bits) >> 3;
+            if (b - a > size) stored = true;   /* libzultra.c:345-347 */
+         }
+         s.stored = stored ? 1 : 0;
+         if (!stored) bit += 3 + (uint64_t)s.body_bits;
+         else {
+            uint32_t rem = size;
+            while (rem) {   /* libzultra.c:354-397 */
+               uint32_t n = rem > 65535 ? 65535 : rem;
+               bit += 3; bit = (bit + 7) & ~7ull; bit += 32 + 8ull * n;
+               rem -= n;
+            }
+         }
+         sb[x] = s;
+      }
+      o.total_bits = bit;
+      so[q] = o;
+   });
+   zb_d2h(st, h_sout.data(), so, sizeof(ZbStreamOut) * nstr); zb_sync(st);
+   /* output area: every stream gets a zeroed, word-aligned span */
+   {
+      uint64_t w = 0;
+      for (int q = 0; q < nstr; q++) { h_sout[q].out_word_off = w; w += (h_sout[q].total_bits + 31) / 32 + 2; }
+      out.need(w + 4);
+      zb_memset(st, out.p, 0, (w + 4) * 4);
+      zb_h2d(st, so, h_sout.data(), sizeof(ZbStreamOut) * nstr);
+   }
+   uint32_t *ow = out.p;
+   /* E4: tokens */
+   zb_launch(st, npch, ZB_LAMBDA(long c) {
+      const uint32_t x = pcs[c];
+      const ZbSub s = sb[x];
+      if (s.stored) return;
+      const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
+      const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      const uint8_t *t = T + wd[s.win].in_off;
+      const ZbSubTabs &tt = tb[x];
+      ZbBitSink sink;
+      sink.init(ow + so[wd[s.win].stream].out_word_off, s.bit_off + 3 + (uint64_t)s.hdr_bits + pb[c]);
+      for (uint32_t p = pen[c]; p < hi;) {
+         zb_match_t m = bm[gb + p];
+         if (m.length >= ZB_MIN_MATCH) {
+            const uint32_t li = m.length - ZB_MIN_MATCH;
+            const int lsym = zb_len_sym(li), leb = zb_len_extra_bits(li);
+            sink.put(tt.lcode[lsym], tt.llen[lsym]);
+            if (leb) sink.put(li & ((1u << leb) - 1u), leb);
+            const int osym = zb_off_sym(m.offset), oeb = zb_off_extra_bits(m.offset);
+            sink.put(tt.ocode[osym], tt.olen[osym]);
+            if (oeb) sink.put((m.offset - 1u) & ((1u << oeb) - 1u), oeb);
+            p += m.length;
+         } else { sink.put(tt.lcode[t[p]], tt.llen[t[p]]); p++; }
+      }
+      if (k + 1 == s.npchunk) sink.put(tt.lcode[ZB_EOB], tt.llen[ZB_EOB]);
+      sink.finish();
+   });
+   /* E5: block headers and table descriptions, or stored-block headers */
+   zb_launch(st, ns, ZB_LAMBDA(long x) {
+      const ZbSub s = sb[x];
+      const ZbSubTabs &tt = tb[x];
+      uint32_t *base = ow + so[wd[s.win].stream].out_word_off;
+      ZbBitSink sink;
+      sink.init(base, s.bit_off);
+      if (!s.stored) {
+         sink.put((uint32_t)s.final_bit, 1);
+         sink.put(1u + (uint32_t)s.is_dyn, 2);
+         if (s.is_dyn) {
+            sink.put((uint32_t)(s.nl - 257), 5); sink.put((uint32_t)(s.no - 1), 5); sink.put((uint32_t)(s.ncl - 4), 4);
+            for (int i = 0; i < s.ncl; i++) sink.put((uint32_t)tt.cllen[zb_clorder(i)], 3);
+            uint8_t cl[ZB_NLIT + ZB_NOFF];
+            for (int i = 0; i < s.nl; i++) cl[i] = (uint8_t)tt.llen[i];
+            for (int i = 0; i < s.no; i++) cl[s.nl + i] = (uint8_t)tt.olen[i];
+            struct W { ZbBitSink *k; const ZbSubTabs *t;
+               ZB_HD void sym(int y) { k->put(t->clcode[y], t->cllen[y]); }
+               ZB_HD void rep(int y, int ev, int eb) { k->put(t->clcode[y], t->cllen[y]); k->put((uint32_t)ev, eb); } } wv = {&sink, &tt};
+            zb_rle_scan(cl, s.nl + s.no, (unsigned)s.mask, wv);
+         }
+         sink.finish();
+      } else {
+         uint64_t bit = s.bit_off;
+         uint32_t rem = s.pe - s.ps;
+         uint8_t *bytes = (uint8_t *)base;
+         while (rem) {
+            const uint32_t n = rem > 65535 ? 65535 : rem;
+            const uint32_t fin = (rem > 65535) ? 0u : (uint32_t)s.final_bit;
+            ZbBitSink hs; hs.init(base, bit); hs.put(fin, 1); hs.put(0, 2); hs.finish();
+            bit += 3; bit = (bit + 7) & ~7ull;
+            /* LEN / NLEN: bytes of their own, but their word may hold a neighbour's bits */
+            ZbBitSink ls; ls.init(base, bit); ls.put(n & 0xffffu, 16); ls.put((n ^ 0xffffu) & 0xffffu, 16); ls.finish();
+            bit += 32 + 8ull * n;
+            rem -= n;
+         }
+         (void)bytes;
+      }
+   });
+   /* E6: stored payload bytes, one task per 256 bytes of a stored sub-block */
+   {
+      /* count tasks on the host side from nothing: launch over all positions/256 and filter by sub-block (stored is rare) */
+      zb_launch(st, ns, ZB_LAMBDA(long x) {
+         const ZbSub s = sb[x];
+         if (!s.stored) return;
+         uint8_t *bytes = (uint8_t *)(ow + so[wd[s.win].stream].out_word_off);
+         const uint8_t *t = T + wd[s.win].in_off;
+         uint64_t bit = s.bit_off;
+         uint32_t rem = s.pe - s.ps, src = s.ps;
+         while (rem) {
+            const uint32_t n = rem > 65535 ? 65535 : rem;
+            bit += 3; bit = (bit + 7) & ~7ull; bit += 32;
+            /* payload bytes are byte aligned; first/last bytes may share a 32-bit word with bit-packed neighbours,
+               which write with atomicOr into zeroed memory - byte stores to distinct bytes do not conflict */
+            uint8_t *d = bytes + (bit >> 3);
+            for (uint32_t i = 0; i < n; i++) d[i] = t[src + i];
+            bit += 8ull * n; src += n; rem -= n;
+         }
+      });
+   }
+}
+
+inline void ZbPipe::release_all() {
+   win.release(); wbase.release(); in.release(); keyA.release(); keyB.release(); valA.release(); valB.release(); rank.release(); sa.release();
+   actA.release(); actB.release(); tmpA.release(); tmpB.release(); scratch.release(); sa_lcp.release(); counters.release(); tiles.release();
+   tile_iv.release(); tile_pd.release(); tile_cnt.release(); match.release(); glen.release(); goff.release(); exitoff.release(); gentry.release();
+   gtokcnt.release(); gtokbase.release(); tokpos.release(); wtok.release(); wtokbase.release(); wintbase.release(); ph.release();
+   gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
+   chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();
+   best.release(); sig_true.release(); sig_warm.release(); dok.release(); pentry.release(); pbits.release(); out.release(); sout.release();
+}
+
+#endif

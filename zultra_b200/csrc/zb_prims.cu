@@ -1,0 +1,272 @@
+/*
+ * zb_prims.cu - cooperative sm_100a primitives: stable LSD radix sort (8-bit digits, warp-match ranking,
+ * shared-memory histograms), device-wide scans (warp-shuffle), and the warp-per-tile suffix filter.
+ *
+ * These replace what libdivsufsort does on the CPU (reference divsufsort.c / sssort.c / trsort.c build the
+ * suffix array with induced copying; here it is radix sort + prefix doubling, see zb_pipeline.h) and feed
+ * the tile match finder.
+ */
+#include "zb_rt.h"
+
+void zb_cuda_fail(cudaError_t e) {
+   (void)e;
+   /* no CPU fallback: a CUDA failure is fatal for the engine call; the C-ABI layer catches this flag */
+   extern int g_zb_cuda_error;
+   g_zb_cuda_error = 1;
+}
+int g_zb_cuda_error = 0;
+
+void *zb_dev_alloc(size_t n) {
+   void *p = 0;
+   cudaError_t e = cudaMalloc(&p, n ? n : 256);
+   if (e != cudaSuccess) { fprintf(stderr, "zultra-b200: cudaMalloc(%zu) failed: %s\n", n, cudaGetErrorString(e)); g_zb_cuda_error = 1; return 0; }
+   return p;
+}
+void zb_dev_free(void *p) { if (p) cudaFree(p); }
+
+/* ------------------------------------------------------------------ scans ------------------------------------------------------------------ */
+
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+struct OpSum { __device__ static uint32_t id() { return 0; } __device__ static uint32_t op(uint32_t a, uint32_t b) { return a + b; } };
+struct OpMax { __device__ static uint32_t id() { return 0; } __device__ static uint32_t op(uint32_t a, uint32_t b) { return a > b ? a : b; } };
+
+/* block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block total (all threads) */
+template <class Op>
+__device__ __forceinline__ uint32_t block_exclusive(uint32_t v, uint32_t *total) {
+   __shared__ uint32_t wsum[SCAN_THREADS / 32];
+   __shared__ uint32_t wtot;
+   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+   uint32_t inc = v;
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc = Op::op(inc, o);
+   }
+   if (lane == 31) wsum[warp] = inc;
+   __syncthreads();
+   if (warp == 0) {
+      uint32_t w = lane < SCAN_THREADS / 32 ? wsum[lane] : Op::id();
+      uint32_t winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+         uint32_t o = __shfl_up_sync(0xffffffffu, winc, d);
+         if (lane >= d) winc = Op::op(winc, o);
+      }
+      uint32_t wexc = __shfl_up_sync(0xffffffffu, winc, 1);
+      if (lane == 0) wexc = Op::id();
+      if (lane < SCAN_THREADS / 32) wsum[lane] = wexc;
+      if (lane == SCAN_THREADS / 32 - 1) wtot = winc;
+   }
+   __syncthreads();
+   uint32_t exc = __shfl_up_sync(0xffffffffu, inc, 1);
+   if (lane == 0) exc = Op::id();
+   exc = Op::op(exc, wsum[warp]);
+   *total = wtot;
+   __syncthreads();
+   return exc;
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_k(const uint32_t *in, uint32_t *partial, long n) {
+   const long base = (long)blockIdx.x * SCAN_TILE + (long)threadIdx.x * SCAN_ITEMS;
+   uint32_t acc = Op::id();
+#pragma unroll
+   for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) acc = Op::op(acc, in[base + k]);
+   uint32_t tot;
+   block_exclusive<Op>(acc, &tot);
+   if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+/* out = scan(in) seeded with prefix[blockIdx] (or identity if prefix == 0); optionally writes the grand total */
+template <class Op, bool INCLUSIVE>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_k(const uint32_t *in, uint32_t *out, const uint32_t *prefix, long n, uint32_t *total_dev) {
+   const long base = (long)blockIdx.x * SCAN_TILE + (long)threadIdx.x * SCAN_ITEMS;
+   uint32_t v[SCAN_ITEMS];
+   uint32_t acc = Op::id();
+#pragma unroll
+   for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = (base + k < n) ? in[base + k] : Op::id(); acc = Op::op(acc, v[k]); }
+   uint32_t tot;
+   uint32_t exc = block_exclusive<Op>(acc, &tot);
+   uint32_t seed = prefix ? prefix[blockIdx.x] : Op::id();
+   exc = Op::op(exc, seed);
+#pragma unroll
+   for (int k = 0; k < SCAN_ITEMS; k++) {
+      uint32_t inc = Op::op(exc, v[k]);
+      if (base + k < n) out[base + k] = INCLUSIVE ? inc : exc;
+      exc = inc;
+   }
+   if (total_dev && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) *total_dev = exc;
+}
+
+size_t zb_scan_scratch_words(long n) {
+   size_t tot = 0;
+   long m = n;
+   while (m > SCAN_TILE) { m = (m + SCAN_TILE - 1) / SCAN_TILE; tot += (size_t)((m + 63) & ~63L); }
+   return tot + 64;
+}
+
+template <class Op, bool INCLUSIVE>
+static void scan_impl(cudaStream_t st, const uint32_t *in, uint32_t *out, long n, uint32_t *total_dev, uint32_t *scratch) {
+   if (n <= 0) { if (total_dev) ZB_CUDA_CHECK(cudaMemsetAsync(total_dev, 0, 4, st)); return; }
+   long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+   if (nb == 1) {
+      scan_apply_k<Op, INCLUSIVE><<<1, SCAN_THREADS, 0, st>>>(in, out, 0, n, total_dev);
+   } else {
+      scan_reduce_k<Op><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, scratch, n);
+      scan_impl<Op, false>(st, scratch, scratch, nb, 0, scratch + ((nb + 63) & ~63L));
+      scan_apply_k<Op, INCLUSIVE><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, scratch, n, total_dev);
+   }
+   ZB_CUDA_CHECK(cudaGetLastError());
+}
+
+void zb_exclusive_sum(zb_stream_t st, const uint32_t *in, uint32_t *out, long n, uint32_t *total_dev, uint32_t *scratch) {
+   scan_impl<OpSum, false>(st, in, out, n, total_dev, scratch);
+}
+void zb_inclusive_max(zb_stream_t st, const uint32_t *in, uint32_t *out, long n, uint32_t *scratch) {
+   scan_impl<OpMax, true>(st, in, out, n, 0, scratch);
+}
+
+/* --------------------------------------------------------------- radix sort --------------------------------------------------------------- */
+
+#define RS_THREADS 256
+#define RS_ITEMS 8
+#define RS_TILE (RS_THREADS * RS_ITEMS)
+#define RS_WARPS (RS_THREADS / 32)
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_k(const uint64_t *keys, long n, int shift, uint32_t mask, uint32_t *hist, int ntiles) {
+   __shared__ uint32_t h[256];
+   h[threadIdx.x] = 0;
+   __syncthreads();
+   const long base = (long)blockIdx.x * RS_TILE;
+#pragma unroll
+   for (int k = 0; k < RS_ITEMS; k++) {
+      long idx = base + k * RS_THREADS + threadIdx.x;
+      if (idx < n) atomicAdd(&h[(uint32_t)(keys[idx] >> shift) & mask], 1u);
+   }
+   __syncthreads();
+   hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_k(const uint64_t *kin, const uint32_t *vin, uint64_t *kout, uint32_t *vout, long n,
+                                                          int shift, uint32_t mask, const uint32_t *hist_scanned, int ntiles) {
+   __shared__ uint32_t cnt[RS_WARPS][256];
+   __shared__ uint32_t gbase[256];
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+   for (int w = 0; w < RS_WARPS; w++) cnt[w][tid] = 0;
+   gbase[tid] = hist_scanned[(size_t)tid * ntiles + blockIdx.x];
+   __syncthreads();
+   const long base = (long)blockIdx.x * RS_TILE + (long)warp * (32 * RS_ITEMS);
+   uint64_t key[RS_ITEMS];
+   uint32_t val[RS_ITEMS], rk[RS_ITEMS];
+   const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+   for (int k = 0; k < RS_ITEMS; k++) {
+      const long idx = base + k * 32 + lane;
+      const bool valid = idx < n;
+      key[k] = valid ? kin[idx] : 0;
+      val[k] = valid ? vin[idx] : 0;
+      const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & mask) : 0xffffffffu;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t pre = __popc(peers & lt);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (valid && lane == leader) { old = cnt[warp][d]; cnt[warp][d] = old + __popc(peers); }
+      old = __shfl_sync(0xffffffffu, old, leader);
+      rk[k] = old + pre;
+      __syncwarp();
+   }
+   __syncthreads();
+   {
+      uint32_t acc = 0;
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; w++) { uint32_t t = cnt[w][tid]; cnt[w][tid] = acc; acc += t; }
+   }
+   __syncthreads();
+#pragma unroll
+   for (int k = 0; k < RS_ITEMS; k++) {
+      const long idx = base + k * 32 + lane;
+      if (idx < n) {
+         const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
+         const size_t dst = (size_t)gbase[d] + cnt[warp][d] + rk[k];
+         kout[dst] = key[k];
+         vout[dst] = val[k];
+      }
+   }
+}
+
+size_t zb_sort_scratch_words(long n) {
+   long ntiles = (n + RS_TILE - 1) / RS_TILE;
+   if (ntiles < 1) ntiles = 1;
+   return (size_t)256 * ntiles + zb_scan_scratch_words(256 * ntiles) + 64;
+}
+
+void zb_sort_pairs(zb_stream_t st, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, long n, int bit_lo, int bit_hi, uint32_t *scratch) {
+   if (n <= 1 || bit_hi <= bit_lo) return;
+   const int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+   uint32_t *hist = scratch;
+   uint32_t *scan_scratch = scratch + (size_t)256 * ntiles;
+   uint64_t *kin = keys, *kout = keys_tmp;
+   uint32_t *vin = vals, *vout = vals_tmp;
+   int npass = 0;
+   for (int shift = bit_lo; shift < bit_hi; shift += 8, npass++) {
+      const int w = (bit_hi - shift) < 8 ? (bit_hi - shift) : 8;
+      const uint32_t mask = (1u << w) - 1u;
+      rs_hist_k<<<ntiles, RS_THREADS, 0, st>>>(kin, n, shift, mask, hist, ntiles);
+      scan_impl<OpSum, false>(st, hist, hist, (long)256 * ntiles, 0, scan_scratch);
+      rs_scatter_k<<<ntiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, mask, hist, ntiles);
+      uint64_t *tk = kin; kin = kout; kout = tk;
+      uint32_t *tv = vin; vin = vout; vout = tv;
+   }
+   ZB_CUDA_CHECK(cudaGetLastError());
+   if (npass & 1) { /* result sits in the tmp buffers */
+      ZB_CUDA_CHECK(cudaMemcpyAsync(keys, keys_tmp, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+      ZB_CUDA_CHECK(cudaMemcpyAsync(vals, vals_tmp, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+   }
+}
+
+/* --------------------------------------------------------------- tile filter --------------------------------------------------------------- */
+
+__global__ void __launch_bounds__(128) tile_filter_k(const uint32_t *sa_lcp, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt) {
+   const int wid = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5);
+   if (wid >= ntiles) return;
+   const int lane = threadIdx.x & 31;
+   const ZbTileDesc t = tiles[first_tile + wid];
+   const uint32_t *src = sa_lcp + t.sa_base;
+   uint32_t *dst = out + (size_t)wid * stride;
+   const uint32_t n = t.wlen;
+   const uint32_t lt = (1u << lane) - 1u;
+   uint32_t carry = 0x1ffu, count = 0;
+   for (uint32_t r0 = 0; r0 < n; r0 += 32) {
+      const uint32_t r = r0 + lane;
+      const bool valid = r < n;
+      const uint32_t w = valid ? __ldg(src + r) : 0u;
+      const uint32_t pos = w & ZB_POS_MASK;
+      uint32_t v = valid ? ((w >> ZB_POS_BITS) & 0x1ffu) : 0x1ffu;
+      const bool keep = valid && pos >= t.lo && pos < t.hi;
+      const uint32_t kmask = __ballot_sync(0xffffffffu, keep);
+      const uint32_t below = kmask & lt;
+      const int start = below ? (32 - __clz((int)below)) : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+         uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+         if (lane >= start + d) v = min(v, o);
+      }
+      if (start == 0) v = min(v, carry);
+      if (keep) dst[count + __popc(below)] = (pos - t.lo) | (v << ZB_POS_BITS);
+      const uint32_t v31 = __shfl_sync(0xffffffffu, v, 31);
+      carry = (kmask >> 31) ? 0x1ffu : v31;
+      count += __popc(kmask);
+   }
+   if (lane == 0) cnt[wid] = count;
+}
+
+void zb_tile_filter(zb_stream_t st, const uint32_t *sa_lcp, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt) {
+   if (ntiles <= 0) return;
+   const int wpb = 4;
+   tile_filter_k<<<(ntiles + wpb - 1) / wpb, wpb * 32, 0, st>>>(sa_lcp, tiles, ntiles, first_tile, out, stride, cnt);
+   ZB_CUDA_CHECK(cudaGetLastError());
+}

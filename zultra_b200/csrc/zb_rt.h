@@ -1,0 +1,85 @@
+/*
+ * zb_rt.h - tiny runtime layer under the pipeline: device memory, task launch, atomics, and the
+ * cooperative primitives (radix sort, scans, tile filter) the pipeline calls.
+ *
+ * Product build (nvcc, ZB_EMU undefined): everything runs on the GPU; a missing device is a hard error.
+ * Test build (g++ -DZB_EMU, tests/emu only): tasks run in a host loop so the per-task logic can be diffed
+ * against the reference without a GPU.  The product library never contains this mode.
+ */
+#ifndef ZB_RT_H
+#define ZB_RT_H
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "zb_core.h"
+
+#ifdef ZB_EMU
+/* ---------------- host emulation (tests only) ---------------- */
+typedef int zb_stream_t;
+#define ZB_LAMBDA [=]
+#define ZB_DEV
+template <class F> static inline void zb_launch(zb_stream_t, long n, F f, int = 128) { for (long i = 0; i < n; i++) f(i); }
+static inline void *zb_dev_alloc(size_t n) { void *p = malloc(n ? n : 1); if (!p) { fprintf(stderr, "emu alloc fail\n"); abort(); } return p; }
+static inline void zb_dev_free(void *p) { free(p); }
+static inline void zb_memset(zb_stream_t, void *p, int v, size_t n) { memset(p, v, n); }
+static inline void zb_h2d(zb_stream_t, void *d, const void *h, size_t n) { memcpy(d, h, n); }
+static inline void zb_d2h(zb_stream_t, void *h, const void *d, size_t n) { memcpy(h, d, n); }
+static inline void zb_d2d(zb_stream_t, void *d, const void *s, size_t n) { memcpy(d, s, n); }
+static inline void zb_sync(zb_stream_t) {}
+static inline int zb_atomic_add(int *p, int v) { int o = *p; *p += v; return o; }
+static inline unsigned zb_atomic_add(unsigned *p, unsigned v) { unsigned o = *p; *p += v; return o; }
+static inline int zb_atomic_max(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
+static inline unsigned zb_atomic_or(unsigned *p, unsigned v) { unsigned o = *p; *p |= v; return o; }
+#else
+/* ---------------- CUDA ---------------- */
+#include <cuda_runtime.h>
+typedef cudaStream_t zb_stream_t;
+#define ZB_LAMBDA [=] __device__
+#define ZB_DEV __device__
+#define ZB_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "zultra-b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); zb_cuda_fail(e_); } } while (0)
+void zb_cuda_fail(cudaError_t e);
+template <class F> __global__ void zb_task_kernel(long n, F f) {
+   long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+   if (i < n) f(i);
+}
+template <class F> static inline void zb_launch(zb_stream_t st, long n, F f, int blk = 128) {
+   if (n <= 0) return;
+   zb_task_kernel<<<(unsigned)((n + blk - 1) / blk), blk, 0, st>>>(n, f);
+   ZB_CUDA_CHECK(cudaGetLastError());
+}
+void *zb_dev_alloc(size_t n);
+void zb_dev_free(void *p);
+static inline void zb_memset(zb_stream_t st, void *p, int v, size_t n) { if (n) ZB_CUDA_CHECK(cudaMemsetAsync(p, v, n, st)); }
+static inline void zb_h2d(zb_stream_t st, void *d, const void *h, size_t n) { if (n) ZB_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st)); }
+static inline void zb_d2h(zb_stream_t st, void *h, const void *d, size_t n) { if (n) ZB_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st)); }
+static inline void zb_d2d(zb_stream_t st, void *d, const void *s, size_t n) { if (n) ZB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st)); }
+static inline void zb_sync(zb_stream_t st) { ZB_CUDA_CHECK(cudaStreamSynchronize(st)); }
+__device__ __forceinline__ int zb_atomic_add(int *p, int v) { return atomicAdd(p, v); }
+__device__ __forceinline__ unsigned zb_atomic_add(unsigned *p, unsigned v) { return atomicAdd(p, v); }
+__device__ __forceinline__ int zb_atomic_max(int *p, int v) { return atomicMax(p, v); }
+__device__ __forceinline__ unsigned zb_atomic_or(unsigned *p, unsigned v) { return atomicOr(p, v); }
+#endif
+
+/* ---- cooperative primitives (zb_prims.cu on the GPU, zb_prims_emu.cpp in the test build) ---- */
+
+/* stable LSD radix sort of (key,val) pairs on key bits [lo,hi); result ends in keys/vals (tmp are scratch) */
+void zb_sort_pairs(zb_stream_t st, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp, long n, int bit_lo, int bit_hi,
+                   uint32_t *scratch /* >= zb_sort_scratch_words(n) */);
+size_t zb_sort_scratch_words(long n);
+/* out[i] = sum_{j<i} in[j]; returns nothing, total written to *total_dev (device ptr, may be null). in==out allowed */
+void zb_exclusive_sum(zb_stream_t st, const uint32_t *in, uint32_t *out, long n, uint32_t *total_dev, uint32_t *scratch /* >= zb_scan_scratch_words(n) */);
+/* out[i] = max_{j<=i} in[j] */
+void zb_inclusive_max(zb_stream_t st, const uint32_t *in, uint32_t *out, long n, uint32_t *scratch);
+size_t zb_scan_scratch_words(long n);
+
+/*
+ * Tile filter: for each tile t, stream the packed SA|LCP words of its window (rank order), keep the suffixes
+ * whose position lies in [lo, hi), min-reduce the LCP over skipped ranks, and write (pos-lo)|lcp<<22 words
+ * to out + t*stride (count to cnt[t]).
+ */
+struct ZbTileDesc { uint32_t win; uint32_t lo, m0, hi; uint64_t sa_base; uint32_t wlen; uint32_t pad; };
+void zb_tile_filter(zb_stream_t st, const uint32_t *sa_lcp, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt);
+
+#endif
