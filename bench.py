@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py - headline metric of BASELINE.json: input MB/s of the zultra compression hot path on N B200s.
+
+One "step" = one pass of the whole pipeline (suffix array + LCP, match lists, block split, optimal parse, Huffman,
+bit emission) over the workload.  N=1 workload: configs[1] of BASELINE.json, a synthetic 100 000 000 B
+enwik8-shaped XML/wiki text, deflate format, default 1 MiB max-block (96 blocks).
+  value      MB/s (10^6 B/s) with the input already resident in HBM (zultra_cuda_compress_blocks_device), timed
+             with CUDA events on the library's stream, max over ranks
+  e2e        same metric through the public zultra_memory_compress call with pinned HOST buffers, H2D/D2H inside
+  roofline   dominant kernel: algorithmic bytes / its average CUDA-event duration vs the measured HBM copy peak
+  cpu_baseline   the reference's own CPU code (oracle/_ref) on a bounded sample, one thread
+--impl reference times the reference CPU implementation on the host cores instead (no GPU work).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "enwik100m": dict(size=100_000_000, flags=0, fmt="deflate", gen="enwik"),
+    "mozilla51m": dict(size=51_220_480, flags=2, fmt="gzip", gen="mozilla"),
+    "mix1g": dict(size=1 << 30, flags=2, fmt="gzip", gen="mix"),
+}
+# algorithmic bytes per unit for the kernels that can dominate
+KERNEL_BYTES = {
+    "mf_build_walk": ("per block byte: 4 B SA|LCP word in (x1.031 window) + 32 B match list out", lambda n, P: 4.0 * P + 32.0 * n),
+    "mf_tile_filter": ("per window position: 4 B word read + 4 B tile word written", lambda n, P: 8.0 * P),
+    "parse_dp": ("per block byte and pass: 32 B match list + 1 B text read, 4 B choice written; 4 passes", lambda n, P: 4 * 37.0 * n),
+    "rs_scatter": ("per sorted element and pass: 12 B key+index read, 12 B written", lambda n, P: 24.0 * P),
+    "rs_hist": ("per sorted element and pass: 8 B key read", lambda n, P: 8.0 * P),
+    "lcp_pack": ("per window position: 4 B SA read, 1 B text, 4 B word written", lambda n, P: 9.0 * P),
+}
+
+
+def gen_workload(name, size=None):
+    from zultra_b200 import synth
+    w = WORKLOADS[name]
+    n = size or w["size"]
+    cache = os.path.join("/tmp", "zb_%s_%d.npy" % (name, n))
+    if os.path.exists(cache):
+        return np.load(cache)
+    d = getattr(synth, w["gen"])(n)
+    try:
+        np.save(cache, d)
+    except OSError:
+        pass
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.rows, self.p, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index),
+                                       "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                                       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+def cpu_reference_timing(data, flags, threads, slice_bytes):
+    """Reference CPU code (oracle/_ref): `threads` workers, each compressing its own slice of the workload with the stock
+    zultra_memory_compress.  Returns (MB/s aggregate, seconds)."""
+    import refharness
+    if not os.path.exists(refharness.REF_SO):
+        return None, None, "oracle/_ref missing"
+    lib = C.CDLL(refharness.REF_SO)
+    lib.zultra_memory_compress.restype = C.c_size_t
+    lib.zultra_memory_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint]
+    lib.zultra_memory_bound.restype = C.c_size_t
+    lib.zultra_memory_bound.argtypes = [C.c_size_t, C.c_uint, C.c_uint]
+    slices = [np.ascontiguousarray(data[i * slice_bytes:(i + 1) * slice_bytes]) for i in range(threads)]
+    slices = [s for s in slices if len(s)]
+    outs = [np.empty(lib.zultra_memory_bound(len(s), flags, 0), dtype=np.uint8) for s in slices]
+
+    def work(i):
+        lib.zultra_memory_compress(slices[i].ctypes.data, len(slices[i]), outs[i].ctypes.data, len(outs[i]), flags, 0)
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(slices))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    total = sum(len(s) for s in slices)
+    return total / dt / 1e6, dt, "%d thread(s) x %d B slices of the workload, stock zultra_memory_compress" % (len(slices), slice_bytes)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    name = args.workload
+    w = WORKLOADS[name]
+    data = gen_workload(name, args.size)
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    slice_bytes = 2 << 20
+    vals = []
+    for it in range(args.warmup + args.steps):
+        v, dt, sample = cpu_reference_timing(data[(it * cores * slice_bytes) % max(1, len(data) - cores * slice_bytes):], w["flags"], cores, slice_bytes)
+        if v is None:
+            print(json.dumps({"impl": "reference", "unavailable": sample}))
+            return
+        if it >= args.warmup:
+            vals.append((v, dt))
+    v = sum(x[0] for x in vals) / len(vals)
+    ms = 1000.0 * sum(x[1] for x in vals) / len(vals)
+    print(json.dumps({"impl": "reference", "metric": "input MB/s (zultra compression hot path)", "value": round(v, 3), "unit": "MB/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                      "config": {"workload": name, "bytes": int(len(data)), "format": w["fmt"], "max_block": 1048576},
+                      "cpu_baseline": {"value": round(v, 3), "unit": "MB/s", "cores": cores, "kind": "reference", "sample": sample},
+                      "e2e": {"value": round(v, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="enwik100m")
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import zultra_b200 as z
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    name = args.workload
+    w = WORKLOADS[name]
+    data = gen_workload(name, args.size)
+    n = len(data)
+    block = 1 << 20
+    nblocks = (n + block - 1) // block
+    # shard by contiguous max-block ranges; every rank keeps the 32 KiB before its first block as history
+    per = (nblocks + world - 1) // world
+    b0, b1 = min(nblocks, rank * per), min(nblocks, (rank + 1) * per)
+    lo, hi = b0 * block, min(n, b1 * block)
+    L = z.load()
+    L.zultra_cuda_profile.argtypes = [C.c_int]
+    L.zultra_cuda_profile_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    ctx = z.CudaCtx(local)
+    from bench_shard import ShardRunner
+    runner = ShardRunner(z, ctx, data, lo, hi, w["flags"], block, rank, world, dist, torch)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def step(profile):
+        flush.fill_(1)   # L2 flush between iterations
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        L.zultra_cuda_profile(1 if profile else 0)
+        ms = runner.step_device()
+        L.zultra_cuda_profile(0)
+        return ms
+
+    for _ in range(args.warmup):
+        step(False)
+    L.zultra_cuda_profile_collect(None, None, None, 0) if False else None
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    times, launches = [], 0
+    for _ in range(args.steps):
+        times.append(step(True))
+        launches += ctx.counters()["launches"]
+    clocks = sampler.stop() if rank == 0 else None
+    names = C.create_string_buffer(32 * 256); kms = (C.c_float * 256)(); kcnt = (C.c_int * 256)()
+    nk = L.zultra_cuda_profile_collect(names, kms, kcnt, 256)
+    ktab = sorted([(names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), kms[i], kcnt[i]) for i in range(nk)], key=lambda r: -r[1])
+    t = torch.tensor([sum(times)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = n / (ms_per_step / 1e3) / 1e6
+    stages = ctx.timings()
+    # end to end through the public API with pinned host buffers
+    e2e_ms, h2d, d2h = runner.e2e(args.steps)
+    if dist is not None:
+        t2 = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2.item())
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        top = next((r for r in ktab if r[0] in KERNEL_BYTES), ktab[0] if ktab else ("none", 0.0, 1))
+        P_local = (hi - lo) + (b1 - b0) * 32768
+        desc, fn = KERNEL_BYTES.get(top[0], ("unknown", lambda a, b: 0.0))
+        alg_bytes_per_step = fn(hi - lo, P_local)
+        per_launch_ms = top[1] / max(1, top[2])
+        launches_per_step = top[2] / args.steps
+        achieved = (alg_bytes_per_step / launches_per_step) / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
+        out = {"metric": "input MB/s (zultra compression hot path, byte-identical to CPU zultra)", "value": round(value, 2), "unit": "MB/s",
+               "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
+               "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+               "config": {"workload": name, "bytes": int(n), "format": w["fmt"], "max_block": block, "blocks": int(nblocks),
+                          "parallelism": "block-range shards x%d" % world, "l2": "256 MiB flush write between iterations"},
+               "clocks": clocks,
+               "e2e": {"value": round(n / (e2e_ms / 1e3) / 1e6, 2), "unit": "MB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "kernel": top[0], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
+                            "traffic": None, "algorithmic_bytes": desc, "kernel_ms_per_step": round(top[1] / args.steps, 3),
+                            "kernel_share_of_step": round(top[1] / args.steps / ms_per_step, 4),
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s"},
+               "stages_ms": {k: round(v, 3) for k, v in stages.items()},
+               "kernels_ms_per_step": {r[0]: round(r[1] / args.steps, 3) for r in ktab[:12]},
+               "compressed_bytes": runner.last_out_bytes}
+        if not args.no_cpu_baseline and world == 1:
+            v, dt, sample = cpu_reference_timing(data, w["flags"], 1, 24 << 20)
+            if v is not None:
+                out["cpu_baseline"] = {"value": round(v, 3), "unit": "MB/s", "cores": 1, "kind": "reference",
+                                       "sample": "first 24 MiB of the workload, " + sample + ", %.1f s" % dt}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -6,11 +6,13 @@ extern "C" {
 long emu_compress(const uint8_t *data, long n, const uint8_t *hist, int hist_len, unsigned block_size, int finalize, int in_bits,
                   uint8_t *out, long out_cap, unsigned long long *bits, unsigned tile_main,
                   /* optional dumps, sized by caller: */ uint32_t *sa_lcp, uint16_t *match, int *nsub, int *sub_info /* 8 ints per sub */,
-                  int *lit_len, int *off_len, uint16_t *best) {
+                  int *lit_len, int *off_len, uint16_t *best, unsigned *crc) {
    ZbPipe p; p.st = 0;
-   ZbStreamIn s = {data, (size_t)n, hist, (uint32_t)hist_len, finalize, (uint32_t)in_bits};
+   ZbStreamIn s = {data, (size_t)n, hist, (uint32_t)hist_len, finalize, (uint32_t)in_bits, 0};
    std::vector<uint8_t> o; std::vector<ZbStreamRes> r; ZbDump d;
-   if (zb_run_batch(p, &s, 1, block_size, o, r, &d, tile_main)) return -1;
+   ZbRunOpts opt; opt.tile_main = tile_main; opt.dump = &d; opt.checksum_kind = 2;
+   if (zb_run_batch(p, &s, 1, block_size, o, r, opt)) return -1;
+   if (crc) *crc = r[0].checksum;
    if ((long)o.size() > out_cap) return -2;
    memcpy(out, o.data(), o.size());
    *bits = r[0].total_bits;

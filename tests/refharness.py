@@ -69,7 +69,7 @@ class Emu:
         hist = np.zeros(0, dtype=np.uint8) if hist is None else np.ascontiguousarray(hist, dtype=np.uint8)
         cap = len(data) + len(data) // 4 + 4096
         out = np.zeros(cap, dtype=np.uint8)
-        bits = C.c_ulonglong(0)
+        bits = C.c_ulonglong(0); crc = C.c_uint(0)
         nwin = max(1, (len(data) + block - 1) // block)
         P = len(data) + len(hist) + (nwin - 1) * 32768
         d = {}
@@ -80,7 +80,8 @@ class Emu:
         n = self.lib.emu_compress(_p(data), C.c_long(len(data)), _p(hist) if len(hist) else None, len(hist), C.c_uint(block), finalize, in_bits,
                                   _p(out), C.c_long(cap), C.byref(bits), C.c_uint(tile),
                                   _p(d.get("sa_lcp")), _p(d.get("match")), C.byref(d["nsub"]) if dump else None, _p(d.get("sub")),
-                                  _p(d.get("ll")), _p(d.get("ol")), _p(d.get("best")))
+                                  _p(d.get("ll")), _p(d.get("ol")), _p(d.get("best")), C.byref(crc))
+        d["crc"] = crc.value
         assert n >= 0, n
         if dump:
             k = d["nsub"].value

@@ -15,7 +15,7 @@
 
 #ifdef __CUDACC__
 #define ZB_HD __host__ __device__ __forceinline__
-#define ZB_HDN __host__ __device__ __noinline__
+#define ZB_HDN static __host__ __device__ __noinline__
 #else
 #define ZB_HD inline
 #define ZB_HDN inline

@@ -5,18 +5,30 @@
 #ifndef ZB_ENGINE_H
 #define ZB_ENGINE_H
 #include "zb_pipeline.h"
+#include <chrono>
 
 struct ZbStreamIn {
    const uint8_t *data; size_t n;          /* bytes to compress in this call (whole max-blocks except possibly the last) */
    const uint8_t *hist; uint32_t hist_len; /* <= 32768 bytes preceding data (previous block tail or preset dictionary) */
    int finalize;                           /* 1: the last window is the end of the stream (BFINAL) */
    uint32_t in_bits;                       /* bits already pending in the current output byte (0..7) */
+   uint32_t checksum;                      /* running checksum in */
 };
-struct ZbStreamRes { uint64_t total_bits; size_t out_off; int err; };
+struct ZbStreamRes { uint64_t total_bits; size_t out_off; int err; uint32_t checksum; };
 
 struct ZbDump {   /* optional stage dumps for tests (host copies) */
    std::vector<uint32_t> sa_lcp; std::vector<zb_match_t> match; std::vector<ZbSub> sub; std::vector<ZbSubTabs> tabs; std::vector<zb_match_t> best;
    std::vector<uint32_t> wbase;
+};
+
+struct ZbRunOpts {
+   uint32_t tile_main = 0;
+   int checksum_kind = 0;          /* 0 none, 1 Adler-32, 2 CRC-32 (frame.c:473) */
+   const uint8_t *dev_in = 0;      /* single stream whose data is already in device memory (hist_len must be 0) */
+   uint8_t *dev_out = 0; size_t dev_out_cap = 0;   /* leave the bitstream of stream 0 in device memory instead of copying back */
+   ZbDump *dump = 0;
+   int stop_after = 99;            /* 1 = SA, 2 = match (stage dumps) */
+   float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* h2d, sa, match, greedy+split, parse, emit, d2h, total */
 };
 
 static inline uint32_t zb_pick_tile(size_t total) {
@@ -25,23 +37,36 @@ static inline uint32_t zb_pick_tile(size_t total) {
    return 4096;
 }
 
+struct ZbTimer {
+   std::chrono::steady_clock::time_point t0;
+   ZbTimer() : t0(std::chrono::steady_clock::now()) {}
+   float lap() { auto t = std::chrono::steady_clock::now(); float ms = std::chrono::duration<float, std::milli>(t - t0).count(); t0 = t; return ms; }
+};
+
 /* Returns 0 on success.  out receives, per stream, ceil(total_bits/8) bytes at res[i].out_off; the pending bits of the
    first byte are zero (the caller ORs its carried partial byte in). */
 static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t block_size, std::vector<uint8_t> &out,
-                               std::vector<ZbStreamRes> &res, ZbDump *dump = 0, uint32_t tile_main = 0) {
+                               std::vector<ZbStreamRes> &res, ZbRunOpts &o) {
    std::vector<ZbWinDesc> wins;
    std::vector<ZbStreamOut> so(ns);
+   std::vector<uint64_t> ck_off(ns), ck_len(ns);
    size_t in_bytes = 0;
    for (int i = 0; i < ns; i++) in_bytes += s[i].hist_len + s[i].n;
-   std::vector<uint8_t> stage;   /* contiguous [hist|data] per stream; TODO pinned staging / direct copies */
-   stage.resize(in_bytes);
+   if (in_bytes >= ((size_t)1 << 31)) return -1;
+   ZbTimer tm, tot;
+   std::vector<uint8_t> stage;
+   const bool single_direct = (ns == 1 && s[0].hist_len == 0 && !o.dev_in);   /* copy straight from the caller's buffer */
+   if (!o.dev_in && !single_direct) stage.resize(in_bytes);
    size_t off = 0, total_block = 0;
    for (int i = 0; i < ns; i++) {
-      if (s[i].hist_len) memcpy(stage.data() + off, s[i].hist, s[i].hist_len);
-      memcpy(stage.data() + off + s[i].hist_len, s[i].data, s[i].n);
+      if (!o.dev_in && !single_direct) {
+         if (s[i].hist_len) memcpy(stage.data() + off, s[i].hist, s[i].hist_len);
+         memcpy(stage.data() + off + s[i].hist_len, s[i].data, s[i].n);
+      }
       memset(&so[i], 0, sizeof(ZbStreamOut));
       so[i].first_win = (uint32_t)wins.size();
       so[i].in_bits = s[i].in_bits;
+      ck_off[i] = off + s[i].hist_len; ck_len[i] = s[i].n;
       size_t done = 0; uint32_t k = 0;
       while (done < s[i].n) {
          ZbWinDesc d; memset(&d, 0, sizeof(d));
@@ -59,31 +84,67 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
       total_block += s[i].n;
    }
    res.assign(ns, ZbStreamRes());
+   for (int i = 0; i < ns; i++) res[i].checksum = s[i].checksum;
    if (wins.empty()) { out.clear(); return 0; }
-   p.setup(wins, stage.data(), in_bytes, false);
+   p.setup(wins, o.dev_in ? o.dev_in : (single_direct ? s[0].data : stage.data()), in_bytes, o.dev_in != 0);
+   zb_sync(p.st); o.ms[0] = tm.lap();
    p.stage_sa();
-   p.stage_match(tile_main ? tile_main : zb_pick_tile(total_block));
-   p.stage_greedy();
-   p.stage_split();
-   p.stage_parse();
-   p.stage_emit(so);
-   /* bring the bitstreams back */
-   size_t total_words = 0;
-   for (int i = 0; i < ns; i++) total_words = std::max<size_t>(total_words, p.h_sout[i].out_word_off + (p.h_sout[i].total_bits + 31) / 32);
-   std::vector<uint32_t> words(total_words + 1);
-   zb_d2h(p.st, words.data(), p.out.p, total_words * 4);
-   zb_sync(p.st);
-   size_t ob = 0;
-   for (int i = 0; i < ns; i++) { res[i].total_bits = p.h_sout[i].total_bits; res[i].out_off = ob; res[i].err = 0; ob += (size_t)((p.h_sout[i].total_bits + 7) / 8); }
-   out.resize(ob);
-   for (int i = 0; i < ns; i++) memcpy(out.data() + res[i].out_off, (const uint8_t *)(words.data() + p.h_sout[i].out_word_off), (size_t)((p.h_sout[i].total_bits + 7) / 8));
-   if (dump) {
+   zb_sync(p.st); o.ms[1] = tm.lap();
+   if (o.stop_after >= 2) {
+      p.stage_match(o.tile_main ? o.tile_main : zb_pick_tile(total_block));
+      zb_sync(p.st); o.ms[2] = tm.lap();
+   }
+   if (o.stop_after >= 3) {
+      p.stage_greedy();
+      p.stage_split();
+      zb_sync(p.st); o.ms[3] = tm.lap();
+      p.stage_parse();
+      zb_sync(p.st); o.ms[4] = tm.lap();
+      p.stage_emit(so);
+      if (o.checksum_kind) {
+         std::vector<uint32_t> sums;
+         if (ns == 1) { p.stage_checksum(o.checksum_kind, ck_off, ck_len, sums, s[0].checksum); res[0].checksum = sums[0]; }
+         else { p.stage_checksum(o.checksum_kind, ck_off, ck_len, sums, 0); for (int i = 0; i < ns; i++) res[i].checksum = sums[i]; }
+      }
+      zb_sync(p.st); o.ms[5] = tm.lap();
+      size_t ob = 0;
+      for (int i = 0; i < ns; i++) { res[i].total_bits = p.h_sout[i].total_bits; res[i].out_off = ob; res[i].err = 0; ob += (size_t)((p.h_sout[i].total_bits + 7) / 8); }
+      if (o.dev_out) {
+         const size_t nb = (size_t)((p.h_sout[0].total_bits + 7) / 8);
+         if (nb > o.dev_out_cap) return -2;
+         zb_d2d(p.st, o.dev_out, p.out.p + p.h_sout[0].out_word_off, nb);
+         zb_sync(p.st);
+         out.clear();
+      } else {
+         size_t total_words = 0;
+         for (int i = 0; i < ns; i++) total_words = std::max<size_t>(total_words, p.h_sout[i].out_word_off + (p.h_sout[i].total_bits + 31) / 32);
+         if (ns == 1) {   /* straight into the result vector */
+            out.resize(total_words * 4 + 4);
+            zb_d2h(p.st, out.data(), p.out.p, total_words * 4);
+            zb_sync(p.st);
+            out.resize(ob);
+         } else {
+            std::vector<uint32_t> words(total_words + 1);
+            zb_d2h(p.st, words.data(), p.out.p, total_words * 4);
+            zb_sync(p.st);
+            out.resize(ob);
+            for (int i = 0; i < ns; i++)
+               memcpy(out.data() + res[i].out_off, (const uint8_t *)(words.data() + p.h_sout[i].out_word_off), (size_t)((p.h_sout[i].total_bits + 7) / 8));
+         }
+      }
+      o.ms[6] = tm.lap();
+   }
+   o.ms[7] = tot.lap();
+   if (o.dump) {
+      ZbDump *dump = o.dump;
       dump->wbase = p.h_wbase;
       dump->sa_lcp.resize(p.P); zb_d2h(p.st, dump->sa_lcp.data(), p.sa_lcp.p, (size_t)p.P * 4);
-      dump->match.resize((size_t)p.P * 8); zb_d2h(p.st, dump->match.data(), p.match.p, (size_t)p.P * 8 * sizeof(zb_match_t));
-      dump->best.resize(p.P); zb_d2h(p.st, dump->best.data(), p.best.p, (size_t)p.P * sizeof(zb_match_t));
-      dump->sub.resize(p.nsub); zb_d2h(p.st, dump->sub.data(), p.sub.p, sizeof(ZbSub) * p.nsub);
-      dump->tabs.resize(p.nsub); zb_d2h(p.st, dump->tabs.data(), p.tabs.p, sizeof(ZbSubTabs) * p.nsub);
+      if (o.stop_after >= 2) { dump->match.resize((size_t)p.P * 8); zb_d2h(p.st, dump->match.data(), p.match.p, (size_t)p.P * 8 * sizeof(zb_match_t)); }
+      if (o.stop_after >= 3) {
+         dump->best.resize(p.P); zb_d2h(p.st, dump->best.data(), p.best.p, (size_t)p.P * sizeof(zb_match_t));
+         dump->sub.resize(p.nsub); zb_d2h(p.st, dump->sub.data(), p.sub.p, sizeof(ZbSub) * p.nsub);
+         dump->tabs.resize(p.nsub); zb_d2h(p.st, dump->tabs.data(), p.tabs.p, sizeof(ZbSubTabs) * p.nsub);
+      }
       zb_sync(p.st);
    }
    return 0;

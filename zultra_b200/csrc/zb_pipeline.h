@@ -98,7 +98,8 @@ struct ZbPipe {
    std::vector<ZbWinDesc> h_win;
    std::vector<uint32_t> h_wbase;
    ZbBuf<ZbWinDesc> win; ZbBuf<uint32_t> wbase;
-   ZbBuf<uint8_t> in;           /* device input */
+   ZbBuf<uint8_t> in;           /* device input (owned copy) */
+   const uint8_t *in_ptr = 0;   /* input actually used by the stages (in.p or a caller's device buffer) */
    /* suffix array stage */
    ZbBuf<uint64_t> keyA, keyB; ZbBuf<uint32_t> valA, valB, rank, sa, actA, actB, tmpA, tmpB, scratch;
    ZbBuf<uint32_t> sa_lcp;      /* packed SA|LCP words, rank order, per window at wbase[w] */
@@ -134,6 +135,9 @@ struct ZbPipe {
    void stage_split();
    void stage_parse();
    void stage_emit(const std::vector<ZbStreamOut> &streams);
+   /* checksum partials of byte ranges of the device input: kind 1 = Adler-32, 2 = CRC-32 */
+   ZbBuf<uint32_t> ck_tab, ck_part; ZbBuf<uint64_t> ck_rng; bool ck_tab_ready = false;
+   void stage_checksum(int kind, const std::vector<uint64_t> &range_off, const std::vector<uint64_t> &range_len, std::vector<uint32_t> &sums, uint32_t init_first);
 };
 
 /* window lookup for a global position index */
@@ -151,8 +155,8 @@ inline void ZbPipe::setup(const std::vector<ZbWinDesc> &wins, const uint8_t *h_i
    win.need(nwin); wbase.need(nwin + 1);
    zb_h2d(st, win.p, h_win.data(), sizeof(ZbWinDesc) * nwin);
    zb_h2d(st, wbase.p, h_wbase.data(), 4 * (nwin + 1));
-   in.need(in_bytes + 16);
-   if (in_is_device) zb_d2d(st, in.p, h_in, in_bytes); else zb_h2d(st, in.p, h_in, in_bytes);
+   if (in_is_device) in_ptr = h_in;
+   else { in.need(in_bytes + 16); zb_h2d(st, in.p, h_in, in_bytes); in_ptr = in.p; }
    counters.need(64);
 }
 
@@ -169,8 +173,9 @@ inline void ZbPipe::stage_sa() {
    scratch.need(zb_sort_scratch_words(n) + zb_scan_scratch_words(n) + 64);
    int wb = 0; while ((1L << wb) < nwin) wb++;
    int nbytes = (64 - wb) / 8; if (nbytes > 7) nbytes = 7;
-   const uint8_t *T = in.p; const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const int nw = nwin;
+   const uint8_t *T = in_ptr; const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const int nw = nwin;
    uint64_t *kA = keyA.p; uint32_t *vA = valA.p;
+   zb_tag("sa_keys");
    zb_launch(st, n, ZB_LAMBDA(long g) {
       int w = zb_find_win(wbs, nw, (uint32_t)g);
       uint32_t i = (uint32_t)g - wbs[w], len = wd[w].len;
@@ -203,6 +208,7 @@ inline void ZbPipe::stage_sa() {
       stat_sa_rounds++;
       const long mm = m;
       /* key = (current rank, rank of the suffix h further; suffixes running off the window sort first, shorter first) */
+      zb_tag("sa_round_keys");
       zb_launch(st, mm, ZB_LAMBDA(long a) {
          uint32_t j = act[a], g = SA[j];
          int w = zb_find_win(wbs, nw, g);
@@ -235,6 +241,7 @@ inline void ZbPipe::stage_sa() {
    }
    /* LCP with the previous suffix of the same window, clamped as matchfinder.c:81-90, packed pos | lcp << 22 */
    uint32_t *out = sa_lcp.p;
+   zb_tag("lcp_pack");
    zb_launch(st, n, ZB_LAMBDA(long j) {
       uint32_t g = SA[j];
       int w = zb_find_win(wbs, nw, (uint32_t)j);
@@ -281,6 +288,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    for (int first = 0; first < ntile; first += wave) {
       const int cnt = std::min(wave, ntile - first);
       zb_tile_filter(st, sa_lcp.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p);
+   zb_tag("mf_build_walk");
       zb_launch(st, (long)cnt * lanes, ZB_LAMBDA(long x) {
          if (x % lanes) return;
          const int k = (int)(x / lanes);
@@ -381,7 +389,7 @@ inline void ZbPipe::stage_greedy() {
    zb_d2h(st, h_wib.data(), wib, 4 * (nwin + 1)); zb_sync(st);
    const long nint = h_wib[nwin];
    ph.need((size_t)nint * ZB_NH);
-   int *PH = ph.p; const uint8_t *T = in.p; const uint16_t *go = goff.p;
+   int *PH = ph.p; const uint8_t *T = in_ptr; const uint16_t *go = goff.p;
    /* per-interval histograms: row k+1 of a window = histogram of tokens [k*ZB_TOKI, (k+1)*ZB_TOKI) */
    zb_launch(st, nint, ZB_LAMBDA(long r) {
       int w = zb_find_win(wib, nw, (uint32_t)r);
@@ -445,7 +453,7 @@ inline void ZbPipe::stage_split() {
    nodesA.need(maxnodes); nodesB.need(maxnodes); nodehist.need((size_t)maxnodes * ZB_NH);
    wsplit.need((size_t)nwin * ZB_MAXSB); wnsplit.need(nwin);
    zb_memset(st, wnsplit.p, 0, 4 * nwin);
-   ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in.p, win.p};
+   ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in_ptr, win.p};
    const ZbWinDesc *wd = win.p; const uint32_t *wtb = wtokbase.p;
    ZbNode *cur = nodesA.p, *nxt = nodesB.p;
    int *nh = nodehist.p; uint32_t *cn = counters.p;
@@ -533,6 +541,7 @@ inline void ZbPipe::stage_split() {
             }
          });
          /* S4: cost delta of splitting at the PREVIOUS check point (blockdeflate.c:724-757) */
+         zb_tag("split_eval");
          zb_launch(st, nchk, ZB_LAMBDA(long c) {
             cdl[c] = -1;
             if (!cf[c]) return;
@@ -631,7 +640,7 @@ ZB_HD void zb_walk_best(const zb_match_t *best, uint32_t entry, uint32_t hi, F &
 inline void ZbPipe::stage_parse() {
    const int ns = nsub;
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
-   ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in.p, win.p};
+   ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in_ptr, win.p};
    /* D1: greedy histogram, static-vs-dynamic decision (libzultra.c:317-324), first tables (blockdeflate.c:863-869) */
    zb_launch(st, ns, ZB_LAMBDA(long x) {
       ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
@@ -682,7 +691,7 @@ inline void ZbPipe::stage_parse() {
       for (uint32_t k = 0; k < sb[x].ndchunk; k++) dcs[sb[x].dchunk_base + k] = (uint32_t)x;
       for (uint32_t k = 0; k < sb[x].npchunk; k++) pcs[sb[x].pchunk_base + k] = (uint32_t)x;
    });
-   const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in.p;
+   const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
    const zb_match_t *mt = match.p; zb_match_t *bm = best.p;
    int16_t *sgt = sig_true.p, *sgw = sig_warm.p; uint8_t *ok = dok.p;
    uint16_t *ex = exitoff.p; uint32_t *pen = pentry.p;
@@ -691,6 +700,7 @@ inline void ZbPipe::stage_parse() {
       /* D2: chunked backward recurrence.  Chunk k of a sub-block covers [ps + k*CD, ..).  Every chunk but the last
          starts ZB_WU positions past its end from an all-zero cost guess; the relative costs it sees at its own end
          (sig_warm) are later compared with what the next chunk really computed there (sig_true). */
+      zb_tag("parse_dp");
       zb_launch(st, ndch, ZB_LAMBDA(long c) {
          const ZbSub s = sb[dcs[c]];
          if (pass > 0 && !s.is_dyn) return;
@@ -742,6 +752,7 @@ inline void ZbPipe::stage_parse() {
          ok[c] = good;
       });
       /* D4: repair, right to left: a chunk whose warm-up disagreed is recomputed from its neighbour's true costs */
+      zb_tag("parse_repair");
       zb_launch(st, ns, ZB_LAMBDA(long x) {
          const ZbSub s = sb[x];
          if (pass > 0 && !s.is_dyn) return;
@@ -949,7 +960,7 @@ inline void ZbPipe::stage_parse() {
 inline void ZbPipe::stage_emit(const std::vector<ZbStreamOut> &streams) {
    const int ns = nsub;
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
-   const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in.p;
+   const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
    zb_match_t *bm = best.p; uint16_t *ex = exitoff.p; uint32_t *pen = pentry.p, *pb = pbits.p, *pcs = pchunk_sub.p;
    long npch = 0;
    {
@@ -1050,6 +1061,7 @@ inline void ZbPipe::stage_emit(const std::vector<ZbStreamOut> &streams) {
    }
    uint32_t *ow = out.p;
    /* E4: tokens */
+   zb_tag("emit_tokens");
    zb_launch(st, npch, ZB_LAMBDA(long c) {
       const uint32_t x = pcs[c];
       const ZbSub s = sb[x];
@@ -1146,6 +1158,102 @@ inline void ZbPipe::release_all() {
    gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
    chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();
    best.release(); sig_true.release(); sig_warm.release(); dok.release(); pentry.release(); pbits.release(); out.release(); sout.release();
+}
+
+
+/* ============================================================ checksums ============================================================
+ * frame.c:74 (Adler-32) and frame.c:324 (CRC-32), computed where the data already is.  One task per 4 KiB chunk
+ * produces a partial; the host folds the partials with the usual combine algebra.
+ */
+#define ZB_CK_CHUNK 4096
+static inline uint32_t zb_gf2_times(const uint32_t *mat, uint32_t vec) { uint32_t s = 0; for (int i = 0; vec; vec >>= 1, i++) if (vec & 1) s ^= mat[i]; return s; }
+static inline void zb_gf2_square(uint32_t *sq, const uint32_t *mat) { for (int i = 0; i < 32; i++) sq[i] = zb_gf2_times(mat, mat[i]); }
+/* crc of A||B from crc(A), crc(B), len(B): apply len(B) zero bytes to crc(A) */
+static inline uint32_t zb_crc32_combine(uint32_t c1, uint32_t c2, uint64_t len2) {
+   if (!len2) return c1;
+   uint32_t even[32], odd[32];
+   odd[0] = 0xedb88320u;
+   uint32_t row = 1;
+   for (int i = 1; i < 32; i++) { odd[i] = row; row <<= 1; }
+   zb_gf2_square(even, odd);
+   zb_gf2_square(odd, even);
+   do {
+      zb_gf2_square(even, odd);
+      if (len2 & 1) c1 = zb_gf2_times(even, c1);
+      len2 >>= 1;
+      if (!len2) break;
+      zb_gf2_square(odd, even);
+      if (len2 & 1) c1 = zb_gf2_times(odd, c1);
+      len2 >>= 1;
+   } while (len2);
+   return c1 ^ c2;
+}
+
+inline void ZbPipe::stage_checksum(int kind, const std::vector<uint64_t> &range_off, const std::vector<uint64_t> &range_len, std::vector<uint32_t> &sums, uint32_t init_first) {
+   const int nr = (int)range_off.size();
+   sums.assign(nr, kind == 1 ? 1u : 0u);
+   if (nr == 0) return;
+   if (nr == 1) sums[0] = init_first;
+   std::vector<uint64_t> h(2 * (size_t)nr + 1);
+   uint64_t nchunk = 0;
+   for (int i = 0; i < nr; i++) { h[2 * i] = range_off[i]; h[2 * i + 1] = nchunk; nchunk += (range_len[i] + ZB_CK_CHUNK - 1) / ZB_CK_CHUNK; }
+   h[2 * (size_t)nr] = nchunk;
+   if (nchunk == 0) return;
+   ck_rng.need(3 * (size_t)nr + 2);
+   std::vector<uint64_t> hh(3 * (size_t)nr);
+   for (int i = 0; i < nr; i++) { hh[3 * i] = h[2 * i + 1]; hh[3 * i + 1] = range_off[i]; hh[3 * i + 2] = range_len[i]; }
+   zb_h2d(st, ck_rng.p, hh.data(), hh.size() * 8);
+   if (!ck_tab_ready) {
+      uint32_t tab[256];
+      for (uint32_t i = 0; i < 256; i++) { uint32_t c = i; for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1) ? 0xedb88320u : 0u); tab[i] = c; }
+      ck_tab.need(256);
+      zb_h2d(st, ck_tab.p, tab, sizeof(tab)); zb_sync(st);
+      ck_tab_ready = true;
+   }
+   ck_part.need(2 * nchunk);
+   const uint64_t *rg = ck_rng.p; const uint32_t *tab = ck_tab.p; uint32_t *part = ck_part.p; const uint8_t *T = in_ptr;
+   zb_launch(st, (long)nchunk, ZB_LAMBDA(long c) {
+      int lo = 0, hi = nr - 1;
+      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (rg[3 * mid] <= (uint64_t)c) lo = mid; else hi = mid - 1; }
+      const uint64_t k = (uint64_t)c - rg[3 * lo];
+      const uint8_t *p = T + rg[3 * lo + 1] + k * ZB_CK_CHUNK;
+      uint64_t rem = rg[3 * lo + 2] - k * ZB_CK_CHUNK;
+      const uint32_t L = rem > ZB_CK_CHUNK ? ZB_CK_CHUNK : (uint32_t)rem;
+      if (kind == 1) {
+         uint32_t a = 0, b = 0;
+         for (uint32_t i = 0; i < L; i++) { uint32_t v = p[i]; a += v; b += (L - i) * v; }
+         part[2 * c] = a % 65521u; part[2 * c + 1] = b % 65521u;
+      } else {
+         uint32_t crc = 0xffffffffu;
+         for (uint32_t i = 0; i < L; i++) crc = tab[(crc ^ p[i]) & 255u] ^ (crc >> 8);
+         part[2 * c] = ~crc; part[2 * c + 1] = L;
+      }
+   });
+   std::vector<uint32_t> hp(2 * nchunk);
+   zb_d2h(st, hp.data(), part, hp.size() * 4); zb_sync(st);
+   /* fixed-length CRC operator for full chunks */
+   uint32_t op[32];
+   if (kind == 2) for (int i = 0; i < 32; i++) op[i] = zb_crc32_combine(1u << i, 0, ZB_CK_CHUNK);
+   for (int i = 0; i < nr; i++) {
+      const uint64_t c0 = h[2 * i + 1], c1 = h[2 * i + 3 > 2 * (size_t)nr ? 2 * (size_t)nr : 2 * i + 3];
+      if (kind == 1) {
+         uint64_t s1 = sums[i] & 0xffff, s2 = (sums[i] >> 16) & 0xffff, left = range_len[i];
+         for (uint64_t c = c0; c < c1; c++) {
+            const uint64_t L = left > ZB_CK_CHUNK ? ZB_CK_CHUNK : left;
+            s2 = (s2 + L * s1 + hp[2 * c + 1]) % 65521u;
+            s1 = (s1 + hp[2 * c]) % 65521u;
+            left -= L;
+         }
+         sums[i] = (uint32_t)(s1 | (s2 << 16));
+      } else {
+         uint32_t crc = sums[i];
+         for (uint64_t c = c0; c < c1; c++) {
+            const uint32_t L = hp[2 * c + 1];
+            crc = (L == ZB_CK_CHUNK ? zb_gf2_times(op, crc) : zb_crc32_combine(crc, 0, L)) ^ hp[2 * c];
+         }
+         sums[i] = crc;
+      }
+   }
 }
 
 #endif

@@ -15,6 +15,47 @@ void zb_cuda_fail(cudaError_t e) {
    g_zb_cuda_error = 1;
 }
 int g_zb_cuda_error = 0;
+long long g_zb_launches = 0;
+
+/* ---- per-kernel timing ---- */
+#include <vector>
+#include <string>
+#include <map>
+int g_zb_prof_on = 0;
+struct ZbProfRec { std::string tag; cudaEvent_t a, b; };
+static std::vector<ZbProfRec> g_prof;
+static const char *g_next_tag = 0;
+void zb_tag(const char *tag) { g_next_tag = tag; }
+void zb_prof_begin(int line, cudaStream_t st) {
+   ZbProfRec r;
+   if (g_next_tag) r.tag = g_next_tag; else { char b[32]; snprintf(b, sizeof b, "L%d", line); r.tag = b; }
+   g_next_tag = 0;
+   cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+   cudaEventRecord(r.a, st);
+   g_prof.push_back(r);
+}
+void zb_prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
+/* aggregate and clear; writes up to cap rows: name (32 bytes each), total ms, launches */
+extern "C" int zultra_cuda_profile_collect(char *names, float *ms, int *counts, int cap) {
+   std::map<std::string, std::pair<float, int> > agg;
+   cudaDeviceSynchronize();
+   for (size_t i = 0; i < g_prof.size(); i++) {
+      float t = 0;
+      cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b);
+      agg[g_prof[i].tag].first += t; agg[g_prof[i].tag].second += 1;
+      cudaEventDestroy(g_prof[i].a); cudaEventDestroy(g_prof[i].b);
+   }
+   g_prof.clear();
+   int n = 0;
+   for (std::map<std::string, std::pair<float, int> >::iterator it = agg.begin(); it != agg.end() && n < cap; ++it, ++n) {
+      snprintf(names + 32 * n, 32, "%s", it->first.c_str());
+      ms[n] = it->second.first; counts[n] = it->second.second;
+   }
+   return n;
+}
+extern "C" void zultra_cuda_profile(int on) { g_zb_prof_on = on; }
+#define PROF_K(tag, st) do { if (g_zb_prof_on) { zb_tag(tag); zb_prof_begin(0, st); } } while (0)
+#define PROF_E(st) do { if (g_zb_prof_on) zb_prof_end(st); } while (0)
 
 void *zb_dev_alloc(size_t n) {
    void *p = 0;
@@ -114,10 +155,12 @@ static void scan_impl(cudaStream_t st, const uint32_t *in, uint32_t *out, long n
    long nb = (n + SCAN_TILE - 1) / SCAN_TILE;
    if (nb == 1) {
       scan_apply_k<Op, INCLUSIVE><<<1, SCAN_THREADS, 0, st>>>(in, out, 0, n, total_dev);
+      g_zb_launches++;
    } else {
       scan_reduce_k<Op><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, scratch, n);
       scan_impl<Op, false>(st, scratch, scratch, nb, 0, scratch + ((nb + 63) & ~63L));
       scan_apply_k<Op, INCLUSIVE><<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, out, scratch, n, total_dev);
+      g_zb_launches += 2;
    }
    ZB_CUDA_CHECK(cudaGetLastError());
 }
@@ -215,9 +258,14 @@ void zb_sort_pairs(zb_stream_t st, uint64_t *keys, uint32_t *vals, uint64_t *key
    for (int shift = bit_lo; shift < bit_hi; shift += 8, npass++) {
       const int w = (bit_hi - shift) < 8 ? (bit_hi - shift) : 8;
       const uint32_t mask = (1u << w) - 1u;
+      PROF_K("rs_hist", st);
       rs_hist_k<<<ntiles, RS_THREADS, 0, st>>>(kin, n, shift, mask, hist, ntiles);
+      PROF_E(st);
       scan_impl<OpSum, false>(st, hist, hist, (long)256 * ntiles, 0, scan_scratch);
+      PROF_K("rs_scatter", st);
       rs_scatter_k<<<ntiles, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, shift, mask, hist, ntiles);
+      PROF_E(st);
+      g_zb_launches += 2;
       uint64_t *tk = kin; kin = kout; kout = tk;
       uint32_t *tv = vin; vin = vout; vout = tv;
    }
@@ -267,6 +315,9 @@ __global__ void __launch_bounds__(128) tile_filter_k(const uint32_t *sa_lcp, con
 void zb_tile_filter(zb_stream_t st, const uint32_t *sa_lcp, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt) {
    if (ntiles <= 0) return;
    const int wpb = 4;
+   PROF_K("mf_tile_filter", st);
    tile_filter_k<<<(ntiles + wpb - 1) / wpb, wpb * 32, 0, st>>>(sa_lcp, tiles, ntiles, first_tile, out, stride, cnt);
+   PROF_E(st);
+   g_zb_launches++;
    ZB_CUDA_CHECK(cudaGetLastError());
 }

@@ -20,7 +20,8 @@
 typedef int zb_stream_t;
 #define ZB_LAMBDA [=]
 #define ZB_DEV
-template <class F> static inline void zb_launch(zb_stream_t, long n, F f, int = 128) { for (long i = 0; i < n; i++) f(i); }
+template <class F> static inline void zb_launch_(int, zb_stream_t, long n, F f, int = 128) { for (long i = 0; i < n; i++) f(i); }
+static inline void zb_tag(const char *) {}
 static inline void *zb_dev_alloc(size_t n) { void *p = malloc(n ? n : 1); if (!p) { fprintf(stderr, "emu alloc fail\n"); abort(); } return p; }
 static inline void zb_dev_free(void *p) { free(p); }
 static inline void zb_memset(zb_stream_t, void *p, int v, size_t n) { memset(p, v, n); }
@@ -40,13 +41,22 @@ typedef cudaStream_t zb_stream_t;
 #define ZB_DEV __device__
 #define ZB_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "zultra-b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); zb_cuda_fail(e_); } } while (0)
 void zb_cuda_fail(cudaError_t e);
+extern long long g_zb_launches;   /* kernels launched by this library (bench.py reports it) */
 template <class F> __global__ void zb_task_kernel(long n, F f) {
    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
    if (i < n) f(i);
 }
-template <class F> static inline void zb_launch(zb_stream_t st, long n, F f, int blk = 128) {
-   if (n <= 0) return;
+/* optional per-kernel timing (CUDA events on the launching stream), enabled by zultra_cuda_profile() */
+extern int g_zb_prof_on;
+void zb_tag(const char *tag);                                /* name the next launch */
+void zb_prof_begin(int line, cudaStream_t st);
+void zb_prof_end(cudaStream_t st);
+template <class F> static inline void zb_launch_(int line, zb_stream_t st, long n, F f, int blk = 128) {
+   if (n <= 0) { zb_tag(0); return; }
+   if (g_zb_prof_on) zb_prof_begin(line, st);
    zb_task_kernel<<<(unsigned)((n + blk - 1) / blk), blk, 0, st>>>(n, f);
+   if (g_zb_prof_on) zb_prof_end(st);
+   g_zb_launches++;
    ZB_CUDA_CHECK(cudaGetLastError());
 }
 void *zb_dev_alloc(size_t n);
@@ -61,6 +71,8 @@ __device__ __forceinline__ unsigned zb_atomic_add(unsigned *p, unsigned v) { ret
 __device__ __forceinline__ int zb_atomic_max(int *p, int v) { return atomicMax(p, v); }
 __device__ __forceinline__ unsigned zb_atomic_or(unsigned *p, unsigned v) { return atomicOr(p, v); }
 #endif
+
+#define zb_launch(...) zb_launch_(__LINE__, __VA_ARGS__)
 
 /* ---- cooperative primitives (zb_prims.cu on the GPU, zb_prims_emu.cpp in the test build) ---- */
 
