@@ -4,6 +4,7 @@
 #include "zb_engine.h"
 #include "../../include/zultra_cuda.h"
 #include <new>
+#include <mutex>
 
 extern int g_zb_cuda_error;
 
@@ -130,7 +131,6 @@ int zultra_cuda_compress_blocks_device(zultra_cuda_ctx_t *c, const void *dev_in,
 }
 
 /* ---- context pool: contexts (device buffers, stream) are expensive to build; the libzultra front end borrows them ---- */
-#include <mutex>
 static std::mutex g_pool_mu;
 static std::vector<zultra_cuda_ctx_t *> g_pool;
 
