@@ -116,3 +116,39 @@ def test_synthetic_generators_are_deterministic():
     assert hashlib.sha256(synth.js48k().tobytes()).hexdigest() == hashlib.sha256(synth.js48k().tobytes()).hexdigest()
     assert len(synth.js48k()) == 48944 and len(synth.enwik(100001)) == 100001 and len(synth.mozilla(123457)) == 123457
     assert len(synth.batch(5)) == 5
+
+
+# ---------------------------------------------------------------- the plain-C oracle (oracle/zultra_oracle.c) ----------------------------------------------------------------
+import oracle_py  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(cases.small_cases().keys()))
+def test_oracle_vs_golden(name):
+    """Pins the oracle: its output equals the reference's golden output for every format."""
+    data = cases.small_cases()[name]
+    for flags, fmt in ((0, "deflate"), (1, "zlib"), (2, "gzip")):
+        assert _gold_ok("%s/%s" % (name, fmt), oracle_py.compress(data, flags))
+
+
+def test_oracle_stages_vs_golden():
+    w1 = synth.js48k()[:12000]
+    w2 = synth.mozilla(60000, seed=77)
+    for tag, win, hist in (("stage_js12k", w1, 0), ("stage_moz60k_h32k", w2, 32768)):
+        assert np.array_equal(oracle_py.sa_lcp(win), GOLD[tag + "/sa_lcp"])
+        assert np.array_equal(oracle_py.matches(win, hist), GOLD[tag + "/match"])
+    out, d = oracle_py.compress(w1, 0, dump=True)
+    tag = "stage_js12k"
+    assert np.array_equal(d["end"], GOLD[tag + "/split"]) and np.array_equal(d["dyn"], GOLD[tag + "/dyn"])
+    assert np.array_equal(d["ll"], GOLD[tag + "/ll"]) and np.array_equal(d["ol"], GOLD[tag + "/ol"]) and np.array_equal(d["bits"], GOLD[tag + "/bits"])
+    assert np.array_equal(d["best"][:len(w1)], GOLD[tag + "/best"])
+
+
+def test_oracle_multi_block_dictionary_and_errors(ref):
+    name, data, block = cases.multi_block_cases()[1]
+    assert _gold_ok("%s/gzip" % name, oracle_py.compress(data, 2, block))
+    dic = synth.enwik(20000, seed=31)
+    body = synth.enwik(90000, seed=32)
+    assert _gold_ok("dict/zlib", oracle_py.compress(body, 1, dic=dic))
+    assert oracle_py.compress(np.zeros(0, dtype=np.uint8), 1) is None
+    big = synth.mix(1500000, seed=4, seg_lo=100000, seg_hi=400000)
+    assert oracle_py.compress(big, 0, 262144) == ref.compress(big, flags=0, block=262144)
