@@ -27,16 +27,18 @@ void zb_inclusive_max(zb_stream_t, const uint32_t *in, uint32_t *out, long n, ui
    uint32_t acc = 0;
    for (long i = 0; i < n; i++) { acc = std::max(acc, in[i]); out[i] = acc; }
 }
-void zb_tile_filter(zb_stream_t, const uint32_t *sa_lcp, const ZbTileDesc *tiles, int ntiles, int first, uint32_t *out, size_t stride, uint32_t *cnt) {
+void zb_tile_filter(zb_stream_t, const uint32_t *srcw, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first, uint32_t *out, size_t stride, uint32_t *cnt) {
    for (int k = 0; k < ntiles; k++) {
       const ZbTileDesc t = tiles[first + k];
-      const uint32_t *src = sa_lcp + t.sa_base;
+      const uint32_t *src = srcw + t.src_base;
+      const uint32_t n = t.src_cnt_idx >= 0 ? src_cnt[t.src_cnt_idx] : t.src_n;
+      const uint32_t lo = t.lo - t.src_lo, hi = t.hi - t.src_lo;
       uint32_t *dst = out + (size_t)k * stride;
       uint32_t carry = 0x1ff, c = 0;
-      for (uint32_t r = 0; r < t.wlen; r++) {
+      for (uint32_t r = 0; r < n; r++) {
          uint32_t w = src[r], pos = w & ZB_POS_MASK, l = (w >> ZB_POS_BITS) & 0x1ff;
          carry = std::min(carry, l);
-         if (pos >= t.lo && pos < t.hi) { dst[c++] = (pos - t.lo) | (carry << ZB_POS_BITS); carry = 0x1ff; }
+         if (pos >= lo && pos < hi) { dst[c++] = (pos - lo) | (carry << ZB_POS_BITS); carry = 0x1ff; }
       }
       cnt[k] = c;
    }

@@ -67,6 +67,7 @@ struct ZbSubTabs {
    int llen[ZB_NLIT], olen[ZB_NOFF];
    uint16_t lcode[ZB_NLIT], ocode[ZB_NOFF];
    int cllen[ZB_NCL]; uint16_t clcode[ZB_NCL];
+   uint8_t cl[ZB_NLIT + ZB_NOFF]; int mask_cost[20];
    ZbCostTab cost;
 };
 
@@ -105,7 +106,7 @@ struct ZbPipe {
    ZbBuf<uint32_t> sa_lcp;      /* packed SA|LCP words, rank order, per window at wbase[w] */
    ZbBuf<uint32_t> counters;    /* misc device counters */
    /* match finder */
-   ZbBuf<ZbTileDesc> tiles; ZbBuf<uint32_t> tile_iv, tile_pd, tile_cnt;
+   ZbBuf<ZbTileDesc> tiles, units; ZbBuf<uint32_t> tile_iv, tile_pd, tile_cnt, unit_words, unit_cnt;
    ZbBuf<zb_match_t> match; ZbBuf<uint16_t> glen, goff;
    /* greedy path */
    ZbBuf<uint16_t> exitoff; ZbBuf<uint32_t> gentry, gtokcnt, gtokbase, tokpos, wtok; /* wtok[w] = tokens of window w; base in wtokbase */
@@ -123,7 +124,7 @@ struct ZbPipe {
    std::vector<ZbStreamOut> h_sout;
    int nsub = 0;
    /* stats */
-   int stat_sa_rounds = 0, stat_redo = 0, stat_ub = 0;
+   int stat_sa_rounds = 0, stat_redo = 0, stat_ub = 0, stat_tiles = 0;
    double t_stage[8];
 
    void release_all();
@@ -262,33 +263,48 @@ inline void ZbPipe::stage_sa() {
 
 /* ============================================================ match finder ============================================================ */
 inline void ZbPipe::stage_match(uint32_t tile_main) {
-   /* tiles: per window, main ranges of tile_main positions over the block part */
-   std::vector<ZbTileDesc> ht;
+   /* Two filter levels.  Units: per window, 32768 main positions + the 32768 before them, filtered from the window's
+      packed words.  Tiles: tile_main main positions (a divisor of 32768) + look-back, filtered from their unit. */
+   while (ZB_MAX_OFFSET % tile_main) tile_main >>= 1;
+   std::vector<ZbTileDesc> hu, ht;
    for (int w = 0; w < nwin; w++) {
       const ZbWinDesc &d = h_win[w];
-      for (uint32_t m0 = d.hist; m0 < d.len; m0 += tile_main) {
-         ZbTileDesc t;
-         t.win = (uint32_t)w; t.m0 = m0; t.hi = std::min(d.len, m0 + tile_main);
-         t.lo = m0 > ZB_MAX_OFFSET ? m0 - ZB_MAX_OFFSET : 0;
-         t.sa_base = h_wbase[w]; t.wlen = d.len; t.pad = 0;
-         ht.push_back(t);
+      for (uint32_t u0 = d.hist; u0 < d.len; u0 += ZB_MAX_OFFSET) {
+         ZbTileDesc u; memset(&u, 0, sizeof(u));
+         u.win = (uint32_t)w; u.m0 = u0; u.hi = std::min(d.len, u0 + ZB_MAX_OFFSET);
+         u.lo = u0 > ZB_MAX_OFFSET ? u0 - ZB_MAX_OFFSET : 0;
+         u.src_base = h_wbase[w]; u.src_n = d.len; u.src_lo = 0; u.src_cnt_idx = -1; u.wlen = d.len;
+         const int ui = (int)hu.size();
+         hu.push_back(u);
+         for (uint32_t m0 = u0; m0 < u.hi; m0 += tile_main) {
+            ZbTileDesc t; memset(&t, 0, sizeof(t));
+            t.win = (uint32_t)w; t.m0 = m0; t.hi = std::min(u.hi, m0 + tile_main);
+            t.lo = m0 > ZB_MAX_OFFSET ? m0 - ZB_MAX_OFFSET : 0;
+            t.src_base = (uint64_t)ui * (2 * ZB_MAX_OFFSET); t.src_n = 0; t.src_lo = u.lo; t.src_cnt_idx = ui; t.wlen = d.len;
+            ht.push_back(t);
+         }
       }
    }
-   const int ntile = (int)ht.size();
-   tiles.need(ntile);
+   const int nunit = (int)hu.size(), ntile = (int)ht.size();
+   units.need(nunit); tiles.need(ntile);
+   zb_h2d(st, units.p, hu.data(), sizeof(ZbTileDesc) * nunit);
    zb_h2d(st, tiles.p, ht.data(), sizeof(ZbTileDesc) * ntile);
    match.need((size_t)P * ZB_NMATCH); glen.need(P); goff.need(P);
+   unit_words.need((size_t)nunit * (2 * ZB_MAX_OFFSET)); unit_cnt.need(nunit);
+   zb_tile_filter(st, sa_lcp.p, 0, units.p, nunit, 0, unit_words.p, 2 * ZB_MAX_OFFSET, unit_cnt.p);
    const size_t stride = ZB_MAX_OFFSET + tile_main;
    const int wave = 16384;
    const int nw_tiles = std::min(ntile, wave);
    tile_iv.need((size_t)nw_tiles * stride); tile_pd.need((size_t)nw_tiles * stride); tile_cnt.need(nw_tiles);
    const ZbTileDesc *td = tiles.p; uint32_t *ivb = tile_iv.p, *pdb = tile_pd.p, *tc = tile_cnt.p;
    zb_match_t *mt = match.p; uint16_t *gl = glen.p, *go = goff.p; const uint32_t *wbs = wbase.p;
-   const int lanes = 4; /* one tile per 4 lanes: keeps warps less divergent than 32 tiles per warp */
+   /* one tile per warp, lane 0 walks: the walk is a chain of dependent loads and 32 tiles in one warp would serialise */
+   const int lanes = 32;
+   stat_tiles = ntile;
    for (int first = 0; first < ntile; first += wave) {
       const int cnt = std::min(wave, ntile - first);
-      zb_tile_filter(st, sa_lcp.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p);
-   zb_tag("mf_build_walk");
+      zb_tile_filter(st, unit_words.p, unit_cnt.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p);
+      zb_tag("mf_build_walk");
       zb_launch(st, (long)cnt * lanes, ZB_LAMBDA(long x) {
          if (x % lanes) return;
          const int k = (int)(x / lanes);
@@ -637,6 +653,123 @@ ZB_HD void zb_walk_best(const zb_match_t *best, uint32_t entry, uint32_t hi, F &
    }
 }
 
+#ifndef ZB_EMU
+/* ---- warp-cooperative form of the chunked backward recurrence (same arithmetic as zb_parse_range) ----
+ * One warp per parse chunk.  The 260-entry cost ring and the sub-block's cost table live in shared memory; per position
+ * lanes 0..7 hold the 8 match candidates (one coalesced 32-byte load, prefetched one position ahead), the >= 40
+ * "leave alone" matches are priced in one round (one lane each) and every shorter match in rounds of 32 lengths;
+ * each round is one redux.min on (cost << 5 | lane), which keeps the reference's order on ties (literal, then matches
+ * longest first, lengths descending, strict >, blockdeflate.c:272-312). */
+__device__ __forceinline__ void zb_parse_range_warp(const uint8_t *t, const uint32_t *mtw, const uint8_t *tlit, const uint8_t *tlen, const uint8_t *toff,
+                                                    int lo, int from, int end, int keep_hi, zb_match_t *best, uint16_t *ring, int &slot, int lane) {
+   int i = from - 1;
+   uint32_t mm = 0, tb_ = 0;
+   if (i >= lo) { mm = lane < 8 ? __ldg(mtw + ((size_t)i << 3) + lane) : 0u; tb_ = t[i]; }
+   for (; i >= lo; i--) {
+      const uint32_t cur = mm, lit = tb_;
+      if (i - 1 >= lo) { mm = lane < 8 ? __ldg(mtw + ((size_t)(i - 1) << 3) + lane) : 0u; tb_ = t[i - 1]; }
+      const int s1 = slot;
+      slot = s1 + 1; if (slot >= ZB_RING) slot -= ZB_RING;
+      const uint16_t base = ring[s1];
+      int bestc = tlit[lit], bestlen = 0, bestoff = 0;
+      const int len0 = (int)(cur & 0xffffu), moff = (int)(cur >> 16);
+      const bool valid = lane < 8 && len0 >= ZB_MIN_MATCH;
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      if (vmask) {
+         int ml = len0; if (i + ml > end) ml = end - i;
+         const int offc = valid ? (int)toff[zb_off_sym((uint32_t)moff)] : 0;
+         const bool leave = valid && len0 >= ZB_LEAVE_ALONE;
+         const unsigned lmask = __ballot_sync(0xffffffffu, leave);
+         if (lmask) {
+            unsigned key = 0xffffffffu;
+            if (leave) {
+               int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING;
+               int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
+               const int cnd = (int)tlen[lidx] + offc + (int)(int16_t)(uint16_t)(ring[sl] - base);
+               key = ((unsigned)(cnd + 8192) << 5) | (unsigned)lane;
+            }
+            const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+            const int cnd = (int)(kmin >> 5) - 8192;
+            const int wl = (int)(kmin & 31u);
+            const int wml = __shfl_sync(0xffffffffu, ml, wl), wof = __shfl_sync(0xffffffffu, moff, wl);
+            if (cnd < bestc) { bestc = cnd; bestlen = wml; bestoff = wof; }
+         }
+         unsigned smask = vmask & ~lmask;
+         while (smask) {
+            const int m = __ffs((int)smask) - 1;
+            smask &= smask - 1;
+            const int mlm = __shfl_sync(0xffffffffu, ml, m), offm = __shfl_sync(0xffffffffu, offc, m), moffm = __shfl_sync(0xffffffffu, moff, m);
+            const int cntm = mlm - 2;
+            for (int r0 = 0; r0 < cntm; r0 += 32) {
+               const int idx = r0 + lane;
+               unsigned key = 0xffffffffu;
+               if (idx < cntm) {
+                  const int k = mlm - idx;
+                  int sl = s1 - (k - 1); if (sl < 0) sl += ZB_RING;
+                  const int cnd = (int)tlen[k - ZB_MIN_MATCH] + offm + (int)(int16_t)(uint16_t)(ring[sl] - base);
+                  key = ((unsigned)(cnd + 8192) << 5) | (unsigned)lane;
+               }
+               const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+               const int cnd = (int)(kmin >> 5) - 8192;
+               if (cnd < bestc) { bestc = cnd; bestlen = mlm - (r0 + (int)(kmin & 31u)); bestoff = moffm; }
+            }
+         }
+      }
+      if (lane == 0) {
+         ring[slot] = (uint16_t)(base + (uint16_t)bestc);
+         if (i < keep_hi) { zb_match_t b; b.length = (uint16_t)bestlen; b.offset = (uint16_t)bestoff; best[i] = b; }
+      }
+      __syncwarp();
+   }
+}
+
+__global__ void __launch_bounds__(128) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
+                                                     const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw) {
+   __shared__ uint16_t ring_s[4][ZB_RING + 4];
+   __shared__ uint32_t tab_s[4][(sizeof(ZbCostTab) + 3) / 4];
+   const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+   const long c = (long)blockIdx.x * 4 + wl;
+   if (c >= ndch) return;
+   const uint32_t x = dcs[c];
+   const ZbSub s = sb[x];
+   if (pass > 0 && !s.is_dyn) return;
+   const uint32_t k = (uint32_t)c - s.dchunk_base;
+   const uint32_t gb = wbs[s.win];
+   const uint8_t *t = T + wd[s.win].in_off;
+   const int lo = (int)(s.ps + k * ZB_CD);
+   const int hi = (int)(lo + ZB_CD < (int)s.pe ? lo + ZB_CD : (int)s.pe);
+   const int end = (int)s.pe;
+   int from = hi + ZB_WU; if (from > end) from = end;
+   const uint32_t *tsrc = (const uint32_t *)&tb[x].cost;
+   for (int j = lane; j < (int)(sizeof(ZbCostTab) / 4); j += 32) tab_s[wl][j] = tsrc[j];
+   uint16_t *ring = ring_s[wl];
+   for (int j = lane; j < ZB_RING; j += 32) ring[j] = 0;
+   __syncwarp();
+   const uint8_t *tlit = (const uint8_t *)tab_s[wl], *tlen = tlit + 256, *toff = tlit + 512;
+   const uint32_t *mtw = (const uint32_t *)(mt + ((size_t)gb << 3));
+   int slot = 0;
+   if (from > hi) zb_parse_range_warp(t, mtw, tlit, tlen, toff, hi, from, end, hi, bm + gb, ring, slot, lane);
+   {
+      int16_t *sw = sgw + (size_t)c * 260;
+      const uint16_t b = ring[slot];
+      for (int q = lane; q <= ZB_MAX_MATCH; q += 32) {
+         int sl = slot - q; if (sl < 0) sl += ZB_RING;
+         sw[q] = (hi + q <= end && hi + q <= from) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
+      }
+   }
+   __syncwarp();
+   zb_parse_range_warp(t, mtw, tlit, tlen, toff, lo, hi, end, hi, bm + gb, ring, slot, lane);
+   {
+      int16_t *sg = sgt + (size_t)c * 260;
+      const uint16_t b = ring[slot];
+      for (int q = lane; q <= ZB_MAX_MATCH; q += 32) {
+         int sl = slot - q; if (sl < 0) sl += ZB_RING;
+         sg[q] = (lo + q <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
+      }
+   }
+}
+#endif
+
 inline void ZbPipe::stage_parse() {
    const int ns = nsub;
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
@@ -700,6 +833,15 @@ inline void ZbPipe::stage_parse() {
       /* D2: chunked backward recurrence.  Chunk k of a sub-block covers [ps + k*CD, ..).  Every chunk but the last
          starts ZB_WU positions past its end from an all-zero cost guess; the relative costs it sees at its own end
          (sig_warm) are later compared with what the next chunk really computed there (sig_true). */
+#ifndef ZB_EMU
+      if (ndch > 0) {
+         if (g_zb_prof_on) { zb_tag("parse_dp"); zb_prof_begin(0, st); }
+         zb_parse_dp_k<<<(unsigned)((ndch + 3) / 4), 128, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw);
+         if (g_zb_prof_on) zb_prof_end(st);
+         g_zb_launches++;
+         ZB_CUDA_CHECK(cudaGetLastError());
+      }
+#else
       zb_tag("parse_dp");
       zb_launch(st, ndch, ZB_LAMBDA(long c) {
          const ZbSub s = sb[dcs[c]];
@@ -735,6 +877,7 @@ inline void ZbPipe::stage_parse() {
             }
          }
       }, 64);
+#endif
       /* D3: does each chunk's warm-up agree with its right neighbour's true costs? */
       zb_launch(st, ndch, ZB_LAMBDA(long c) {
          const ZbSub s = sb[dcs[c]];
@@ -887,7 +1030,7 @@ inline void ZbPipe::stage_parse() {
          } else p++;
       }
    });
-   /* F1: final tables: RLE smoothing trial (blockdeflate.c:926-945), mask search (:958-977), codes, header size */
+   /* F1a: RLE smoothing trial (blockdeflate.c:926-945); the code-length sequence to be described */
    zb_launch(st, ns, ZB_LAMBDA(long x) {
       ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
       ZbScratch sc;
@@ -912,33 +1055,50 @@ inline void ZbPipe::stage_parse() {
          s.nl = zb_defined_count(t.llen, ZB_NLIT, 257);
          int ol32[ZB_NOFF]; for (int i = 0; i < ZB_NOFF; i++) ol32[i] = t.olen[i];
          s.no = zb_defined_count(ol32, ZB_NOFF, 1);
-         const int ncodes = s.nl + s.no;
-         for (int i = 0; i < s.nl; i++) sc.cl[i] = (uint8_t)t.llen[i];
-         for (int i = 0; i < s.no; i++) sc.cl[s.nl + i] = (uint8_t)t.olen[i];
-         int bestmask = -1, bestcost = 0;
-         int cllen[ZB_NLIT];
-         for (int mask = 0; mask <= 31; mask = (mask >= 7) ? mask + 2 : mask + 1) {
-            for (int i = 0; i < ZB_NCL; i++) sc.clcnt[i] = 0;
-            ZbRleCount cv = {sc.clcnt};
-            zb_rle_scan(sc.cl, ncodes, (unsigned)mask, cv);
-            zb_huff_build(sc.clcnt, ZB_NCL, 7, cllen, 0, sc.key, sc.order, &s.ub_hit);
-            ZbRleSize sv = {cllen, 0};
-            zb_rle_scan(sc.cl, ncodes, (unsigned)mask, sv);
-            if (bestmask == -1 || bestcost >= sv.bits) { bestmask = mask; bestcost = sv.bits; }
+         for (int i = 0; i < s.nl; i++) t.cl[i] = (uint8_t)t.llen[i];
+         for (int i = 0; i < s.no; i++) t.cl[s.nl + i] = (uint8_t)t.olen[i];
+      } else {
+         s.nl = 288; s.no = 32; s.ncl = 0; s.mask = 0; s.hdr_bits = 0;
+      }
+      sb[x] = s;
+   }, 64);
+   /* F1b: the 20 RLE masks {0..7, 9, 11, .., 31} in parallel (blockdeflate.c:958-974) */
+   zb_launch(st, (long)ns * 20, ZB_LAMBDA(long y) {
+      const long x = y / 20; const int mi = (int)(y % 20);
+      const ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
+      if (!s.is_dyn) return;
+      const int mask = mi < 8 ? mi : 9 + 2 * (mi - 8);
+      int clcnt[ZB_NCL], cllen[ZB_NLIT]; uint32_t key[ZB_NLIT]; int16_t order[ZB_NLIT]; int ub = 0;
+      for (int i = 0; i < ZB_NCL; i++) clcnt[i] = 0;
+      ZbRleCount cv = {clcnt};
+      zb_rle_scan(t.cl, s.nl + s.no, (unsigned)mask, cv);
+      zb_huff_build(clcnt, ZB_NCL, 7, cllen, 0, key, order, &ub);
+      ZbRleSize sv = {cllen, 0};
+      zb_rle_scan(t.cl, s.nl + s.no, (unsigned)mask, sv);
+      t.mask_cost[mi] = sv.bits | (ub << 30);
+   }, 64);
+   /* F1c: pick the mask (later one wins ties, :966), final code-length code, codewords, header size */
+   zb_launch(st, ns, ZB_LAMBDA(long x) {
+      ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
+      if (s.is_dyn) {
+         int bestmi = -1, bestcost = 0;
+         for (int mi = 0; mi < 20; mi++) {
+            const int c = t.mask_cost[mi] & 0x3fffffff;
+            if (t.mask_cost[mi] >> 30) s.ub_hit = 1;
+            if (bestmi == -1 || bestcost >= c) { bestmi = mi; bestcost = c; }
          }
-         for (int i = 0; i < ZB_NCL; i++) sc.clcnt[i] = 0;
-         ZbRleCount cv = {sc.clcnt};
-         zb_rle_scan(sc.cl, ncodes, (unsigned)bestmask, cv);
-         zb_huff_build(sc.clcnt, ZB_NCL, 7, cllen, t.clcode, sc.key, sc.order, &s.ub_hit);
+         const int bestmask = bestmi < 8 ? bestmi : 9 + 2 * (bestmi - 8);
+         int clcnt[ZB_NCL], cllen[ZB_NLIT]; uint32_t key[ZB_NLIT]; int16_t order[ZB_NLIT];
+         for (int i = 0; i < ZB_NCL; i++) clcnt[i] = 0;
+         ZbRleCount cv = {clcnt};
+         zb_rle_scan(t.cl, s.nl + s.no, (unsigned)bestmask, cv);
+         zb_huff_build(clcnt, ZB_NCL, 7, cllen, t.clcode, key, order, &s.ub_hit);
          for (int i = 0; i < ZB_NCL; i++) t.cllen[i] = cllen[i];
          s.mask = bestmask;
          s.ncl = zb_raw_table_size(cllen);
          s.hdr_bits = 14 + 3 * s.ncl + bestcost;
          if (s.nl > 286 || s.no > 30) s.hdr_bits = -1;   /* blockdeflate.c:981-983: block_deflate fails -> stored */
-      } else {
-         s.nl = 288; s.no = 32; s.ncl = 0; s.mask = 0; s.hdr_bits = 0;
       }
-      /* codewords */
       {
          int16_t order[ZB_NLIT];
          int n = zb_order_by_len(t.llen, ZB_NLIT, order);
@@ -1153,7 +1313,7 @@ inline void ZbPipe::stage_emit(const std::vector<ZbStreamOut> &streams) {
 inline void ZbPipe::release_all() {
    win.release(); wbase.release(); in.release(); keyA.release(); keyB.release(); valA.release(); valB.release(); rank.release(); sa.release();
    actA.release(); actB.release(); tmpA.release(); tmpB.release(); scratch.release(); sa_lcp.release(); counters.release(); tiles.release();
-   tile_iv.release(); tile_pd.release(); tile_cnt.release(); match.release(); glen.release(); goff.release(); exitoff.release(); gentry.release();
+   tile_iv.release(); tile_pd.release(); tile_cnt.release(); units.release(); unit_words.release(); unit_cnt.release(); match.release(); glen.release(); goff.release(); exitoff.release(); gentry.release();
    gtokcnt.release(); gtokbase.release(); tokpos.release(); wtok.release(); wtokbase.release(); wintbase.release(); ph.release();
    gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
    chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();

@@ -278,14 +278,15 @@ void zb_sort_pairs(zb_stream_t st, uint64_t *keys, uint32_t *vals, uint64_t *key
 
 /* --------------------------------------------------------------- tile filter --------------------------------------------------------------- */
 
-__global__ void __launch_bounds__(128) tile_filter_k(const uint32_t *sa_lcp, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt) {
+__global__ void __launch_bounds__(128) tile_filter_k(const uint32_t *srcw, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt) {
    const int wid = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5);
    if (wid >= ntiles) return;
    const int lane = threadIdx.x & 31;
    const ZbTileDesc t = tiles[first_tile + wid];
-   const uint32_t *src = sa_lcp + t.sa_base;
+   const uint32_t *src = srcw + t.src_base;
    uint32_t *dst = out + (size_t)wid * stride;
-   const uint32_t n = t.wlen;
+   const uint32_t n = t.src_cnt_idx >= 0 ? src_cnt[t.src_cnt_idx] : t.src_n;
+   const uint32_t lo = t.lo - t.src_lo, hi = t.hi - t.src_lo;
    const uint32_t lt = (1u << lane) - 1u;
    uint32_t carry = 0x1ffu, count = 0;
    for (uint32_t r0 = 0; r0 < n; r0 += 32) {
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(128) tile_filter_k(const uint32_t *sa_lcp, con
       const uint32_t w = valid ? __ldg(src + r) : 0u;
       const uint32_t pos = w & ZB_POS_MASK;
       uint32_t v = valid ? ((w >> ZB_POS_BITS) & 0x1ffu) : 0x1ffu;
-      const bool keep = valid && pos >= t.lo && pos < t.hi;
+      const bool keep = valid && pos >= lo && pos < hi;
       const uint32_t kmask = __ballot_sync(0xffffffffu, keep);
       const uint32_t below = kmask & lt;
       const int start = below ? (32 - __clz((int)below)) : 0;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(128) tile_filter_k(const uint32_t *sa_lcp, con
          if (lane >= start + d) v = min(v, o);
       }
       if (start == 0) v = min(v, carry);
-      if (keep) dst[count + __popc(below)] = (pos - t.lo) | (v << ZB_POS_BITS);
+      if (keep) dst[count + __popc(below)] = (pos - lo) | (v << ZB_POS_BITS);
       const uint32_t v31 = __shfl_sync(0xffffffffu, v, 31);
       carry = (kmask >> 31) ? 0x1ffu : v31;
       count += __popc(kmask);
@@ -312,11 +313,11 @@ __global__ void __launch_bounds__(128) tile_filter_k(const uint32_t *sa_lcp, con
    if (lane == 0) cnt[wid] = count;
 }
 
-void zb_tile_filter(zb_stream_t st, const uint32_t *sa_lcp, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt) {
+void zb_tile_filter(zb_stream_t st, const uint32_t *src, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt) {
    if (ntiles <= 0) return;
    const int wpb = 4;
    PROF_K("mf_tile_filter", st);
-   tile_filter_k<<<(ntiles + wpb - 1) / wpb, wpb * 32, 0, st>>>(sa_lcp, tiles, ntiles, first_tile, out, stride, cnt);
+   tile_filter_k<<<(ntiles + wpb - 1) / wpb, wpb * 32, 0, st>>>(src, src_cnt, tiles, ntiles, first_tile, out, stride, cnt);
    PROF_E(st);
    g_zb_launches++;
    ZB_CUDA_CHECK(cudaGetLastError());

@@ -87,11 +87,12 @@ void zb_inclusive_max(zb_stream_t st, const uint32_t *in, uint32_t *out, long n,
 size_t zb_scan_scratch_words(long n);
 
 /*
- * Tile filter: for each tile t, stream the packed SA|LCP words of its window (rank order), keep the suffixes
- * whose position lies in [lo, hi), min-reduce the LCP over skipped ranks, and write (pos-lo)|lcp<<22 words
- * to out + t*stride (count to cnt[t]).
+ * Tile filter: for each tile t, stream a list of packed pos|lcp<<22 words in suffix-array order (src + src_base,
+ * src_n words, or src_cnt[src_cnt_idx] words when src_cnt_idx >= 0; positions in the list are relative to src_lo),
+ * keep the suffixes whose window position lies in [lo, hi), min-reduce the LCP over skipped entries, and write
+ * (pos-lo)|lcp<<22 words to out + t*stride (count to cnt[t]).  Used twice: window -> 64 Ki-position units -> tiles.
  */
-struct ZbTileDesc { uint32_t win; uint32_t lo, m0, hi; uint64_t sa_base; uint32_t wlen; uint32_t pad; };
-void zb_tile_filter(zb_stream_t st, const uint32_t *sa_lcp, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt);
+struct ZbTileDesc { uint32_t win; uint32_t lo, m0, hi; uint64_t src_base; uint32_t src_n; uint32_t src_lo; int32_t src_cnt_idx; uint32_t wlen; };
+void zb_tile_filter(zb_stream_t st, const uint32_t *src, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt);
 
 #endif
