@@ -468,6 +468,52 @@ ZB_HD int zb_mf_walk(uint32_t *iv, uint32_t *pd, uint32_t i, zb_match_t *out) {
    return n;
 }
 
+/*
+ * Match list of one main position by direct scan of the tile's suffix array - no interval tree, no mutation, so every
+ * position of a tile is independent (one GPU thread each, the tile's list held in shared memory).
+ *
+ * words[0..n): the tile's suffixes in suffix-array order, pos | lcp<<22 (lcp with the previous entry, already clamped to
+ * {0,3..258}).  r = index of the suffix starting at tile position i.  Walk outwards from r, always taking the side whose
+ * running LCP with i is larger, so candidates arrive by non-increasing LCP.  best = nearest earlier position (within
+ * 32768) seen so far; whenever the LCP level drops and best moved during the level just finished, (level, i - best) is
+ * the next entry of the reference's list: exactly the positions that zultra_find_matches_at (matchfinder.c:171-234)
+ * reports, longest first - for each length the nearest earlier occurrence, each position once, with its own length
+ * (SURVEY 8(a)-M1).  The reference stops storing after 8 entries (matchfinder.c:217); nothing nearer than offset 1 exists.
+ */
+ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, zb_match_t *out) {
+   int L = r - 1, R = r + 1;
+   uint32_t lL = r > 0 ? (words[r] >> ZB_POS_BITS) : 0u;
+   uint32_t lR = R < n ? (words[R] >> ZB_POS_BITS) : 0u;
+   const int minpos = i > ZB_MAX_OFFSET ? (int)(i - ZB_MAX_OFFSET) : 0;
+   int nm = 0, best = -1;
+   uint32_t lvl = 0;
+   bool moved = false;
+   for (;;) {
+      const uint32_t l = lL > lR ? lL : lR;
+      if (l < lvl && moved) {
+         out[nm].length = (uint16_t)lvl; out[nm].offset = (uint16_t)(i - (uint32_t)best); nm++;
+         moved = false;
+         if (nm == ZB_NMATCH || best == (int)i - 1) return nm;
+      }
+      if (l < ZB_MIN_MATCH) break;
+      lvl = l;
+      int p;
+      if (lL >= lR) {
+         const uint32_t w = words[L];
+         p = (int)(w & ZB_POS_MASK);
+         const uint32_t wl = w >> ZB_POS_BITS;
+         lL = L > 0 ? (wl < lL ? wl : lL) : 0u;
+         L--;
+      } else {
+         p = (int)(words[R] & ZB_POS_MASK);
+         R++;
+         if (R < n) { const uint32_t wl = words[R] >> ZB_POS_BITS; lR = wl < lR ? wl : lR; } else lR = 0u;
+      }
+      if (p < (int)i && p >= minpos && p > best) { best = p; moved = true; }
+   }
+   return nm;
+}
+
 /* ---- optimal parse (blockdeflate.c:254-323) ---- */
 
 /* per sub-block bit costs fed to the parse: lit[b], len[length-3] (symbol + extra bits), off[dist symbol] (+extra) */

@@ -31,10 +31,12 @@ struct ZbRunOpts {
    float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* h2d, sa, match, greedy+split, parse, emit, d2h, total */
 };
 
+/* main positions per match-finder tile: as large as shared memory allows (amortises the 32768 look-back entries every
+   tile loads) while still giving every SM several tiles */
 static inline uint32_t zb_pick_tile(size_t total) {
-   if (total <= ((size_t)8 << 20)) return 1024;
-   if (total <= ((size_t)64 << 20)) return 2048;
-   return 4096;
+   uint32_t t = 8192;
+   while (t > 512 && total / t < 600) t >>= 1;
+   return t;
 }
 
 struct ZbTimer {

@@ -262,6 +262,49 @@ inline void ZbPipe::stage_sa() {
 }
 
 /* ============================================================ match finder ============================================================ */
+#ifndef ZB_EMU
+/* CTA per tile: the tile's suffix list (<= 32768 + T words) and the rank of every main position live in shared memory;
+   each thread scans the lists of its main positions (zb_mf_scan) and writes the 32-byte match record. */
+__global__ void __launch_bounds__(512) zb_mf_scan_k(const ZbTileDesc *td, int first, const uint32_t *lists, size_t stride, const uint32_t *cnts,
+                                                    zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs) {
+   extern __shared__ uint32_t zb_smw[];
+   const int k = blockIdx.x;
+   const ZbTileDesc t = td[first + k];
+   const int n = (int)cnts[k];
+   const uint32_t nlook = t.m0 - t.lo, nmain = t.hi - t.m0;
+   uint32_t *words = zb_smw;
+   uint16_t *rom = (uint16_t *)(zb_smw + stride);
+   const uint32_t *src = lists + (size_t)k * stride;
+   for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const uint32_t w = src[e];
+      words[e] = w;
+      const uint32_t p = w & ZB_POS_MASK;
+      if (p >= nlook) rom[p - nlook] = (uint16_t)e;
+   }
+   __syncthreads();
+   const uint32_t gbase = wbs[t.win];
+   for (uint32_t m = threadIdx.x; m < nmain; m += blockDim.x) {
+      zb_match_t o[ZB_NMATCH];
+      const uint32_t p = t.m0 + m;
+      const int nm = zb_mf_scan(words, n, (int)rom[m], nlook + m, o);
+      const uint32_t maxlen = t.wlen - p;   /* matchfinder.c:276-280 (LAST_LITERALS = 0) */
+      uint32_t rec[ZB_NMATCH];
+#pragma unroll
+      for (int q = 0; q < ZB_NMATCH; q++) {
+         uint32_t len = 0, off = 0;
+         if (q < nm) { len = o[q].length; off = o[q].offset; if (len > maxlen) len = maxlen; }
+         rec[q] = len | (off << 16);
+      }
+      uint4 *dst = (uint4 *)(mt + ((size_t)(gbase + p) << 3));
+      dst[0] = make_uint4(rec[0], rec[1], rec[2], rec[3]);
+      dst[1] = make_uint4(rec[4], rec[5], rec[6], rec[7]);
+      const uint32_t l0 = rec[0] & 0xffffu;
+      gl[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)l0 : (uint16_t)1;
+      go[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)(rec[0] >> 16) : (uint16_t)0;
+   }
+}
+#endif
+
 inline void ZbPipe::stage_match(uint32_t tile_main) {
    /* Two filter levels.  Units: per window, 32768 main positions + the 32768 before them, filtered from the window's
       packed words.  Tiles: tile_main main positions (a divisor of 32768) + look-back, filtered from their unit. */
@@ -295,40 +338,54 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    const size_t stride = ZB_MAX_OFFSET + tile_main;
    const int wave = 16384;
    const int nw_tiles = std::min(ntile, wave);
-   tile_iv.need((size_t)nw_tiles * stride); tile_pd.need((size_t)nw_tiles * stride); tile_cnt.need(nw_tiles);
-   const ZbTileDesc *td = tiles.p; uint32_t *ivb = tile_iv.p, *pdb = tile_pd.p, *tc = tile_cnt.p;
+   tile_iv.need((size_t)nw_tiles * stride); tile_cnt.need(nw_tiles);
+   const ZbTileDesc *td = tiles.p; uint32_t *ivb = tile_iv.p, *tc = tile_cnt.p;
    zb_match_t *mt = match.p; uint16_t *gl = glen.p, *go = goff.p; const uint32_t *wbs = wbase.p;
-   /* one tile per warp, lane 0 walks: the walk is a chain of dependent loads and 32 tiles in one warp would serialise */
-   const int lanes = 32;
    stat_tiles = ntile;
+#ifndef ZB_EMU
+   const size_t smem = stride * 4 + (size_t)tile_main * 2;
+   ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_mf_scan_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#else
+   tile_pd.need((size_t)nw_tiles * tile_main);
+   uint32_t *pdb = tile_pd.p;
+#endif
    for (int first = 0; first < ntile; first += wave) {
       const int cnt = std::min(wave, ntile - first);
       zb_tile_filter(st, unit_words.p, unit_cnt.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p);
-      zb_tag("mf_build_walk");
-      zb_launch(st, (long)cnt * lanes, ZB_LAMBDA(long x) {
-         if (x % lanes) return;
-         const int k = (int)(x / lanes);
+#ifndef ZB_EMU
+      if (g_zb_prof_on) { zb_tag("mf_scan"); zb_prof_begin(0, st); }
+      zb_mf_scan_k<<<cnt, 512, smem, st>>>(td, first, ivb, stride, tc, mt, gl, go, wbs);
+      if (g_zb_prof_on) zb_prof_end(st);
+      g_zb_launches++;
+      ZB_CUDA_CHECK(cudaGetLastError());
+#else
+      /* host build: same per-position scan, lists in ordinary memory */
+      zb_launch(st, cnt, ZB_LAMBDA(long k) {
          const ZbTileDesc t = td[first + k];
-         uint32_t *iv = ivb + (size_t)k * stride, *pd = pdb + (size_t)k * stride;
-         const int n = (int)tc[k];
-         ZbMfStack stk;
-         zb_mf_build(iv, pd, n, t.m0 - t.lo, stk);
-         const uint32_t gbase = wbs[t.win];
-         for (uint32_t p = t.m0; p < t.hi; p++) {
-            zb_match_t m[ZB_NMATCH];
-            int nm = zb_mf_walk(iv, pd, p - t.lo, m);
-            const uint32_t maxlen = t.wlen - p;   /* matchfinder.c:276-280 (LAST_LITERALS = 0) */
-            zb_match_t *dst = mt + ((size_t)(gbase + p) << 3);
-            for (int q = 0; q < ZB_NMATCH; q++) {
-               zb_match_t v; v.length = 0; v.offset = 0;
-               if (q < nm) { v = m[q]; if (v.length > maxlen) v.length = (uint16_t)maxlen; }
-               dst[q] = v;
-            }
-            uint16_t l0 = nm > 0 ? (m[0].length > maxlen ? (uint16_t)maxlen : m[0].length) : 0;
-            gl[gbase + p] = l0 >= ZB_MIN_MATCH ? l0 : (uint16_t)1;
-            go[gbase + p] = l0 >= ZB_MIN_MATCH ? m[0].offset : (uint16_t)0;
+         const uint32_t *words = ivb + (size_t)k * stride; uint32_t *rom = pdb + (size_t)k * tile_main;
+         const uint32_t nlook = t.m0 - t.lo;
+         for (uint32_t e = 0; e < tc[k]; e++) { uint32_t p = words[e] & ZB_POS_MASK; if (p >= nlook) rom[p - nlook] = e; }
+      });
+      zb_launch(st, (long)cnt * tile_main, ZB_LAMBDA(long x) {
+         const int k = (int)(x / tile_main); const uint32_t m = (uint32_t)(x % tile_main);
+         const ZbTileDesc t = td[first + k];
+         if (m >= t.hi - t.m0) return;
+         const uint32_t *words = ivb + (size_t)k * stride; const uint32_t *rom = pdb + (size_t)k * tile_main;
+         const uint32_t nlook = t.m0 - t.lo, p = t.m0 + m, gbase = wbs[t.win];
+         zb_match_t o[ZB_NMATCH];
+         const int nm = zb_mf_scan(words, (int)tc[k], (int)rom[m], nlook + m, o);
+         const uint32_t maxlen = t.wlen - p;
+         zb_match_t *dst = mt + ((size_t)(gbase + p) << 3);
+         for (int q = 0; q < ZB_NMATCH; q++) {
+            zb_match_t v; v.length = 0; v.offset = 0;
+            if (q < nm) { v = o[q]; if (v.length > maxlen) v.length = (uint16_t)maxlen; }
+            dst[q] = v;
          }
-      }, 128);
+         const uint16_t l0 = dst[0].length;
+         gl[gbase + p] = l0 >= ZB_MIN_MATCH ? l0 : (uint16_t)1;
+         go[gbase + p] = l0 >= ZB_MIN_MATCH ? dst[0].offset : (uint16_t)0;
+      });
+#endif
    }
 }
 
@@ -661,65 +718,79 @@ ZB_HD void zb_walk_best(const zb_match_t *best, uint32_t entry, uint32_t hi, F &
  * each round is one redux.min on (cost << 5 | lane), which keeps the reference's order on ties (literal, then matches
  * longest first, lengths descending, strict >, blockdeflate.c:272-312). */
 __device__ __forceinline__ void zb_parse_range_warp(const uint8_t *t, const uint32_t *mtw, const uint8_t *tlit, const uint8_t *tlen, const uint8_t *toff,
-                                                    int lo, int from, int end, int keep_hi, zb_match_t *best, uint16_t *ring, int &slot, int lane) {
-   int i = from - 1;
-   uint32_t mm = 0, tb_ = 0;
-   if (i >= lo) { mm = lane < 8 ? __ldg(mtw + ((size_t)i << 3) + lane) : 0u; tb_ = t[i]; }
-   for (; i >= lo; i--) {
-      const uint32_t cur = mm, lit = tb_;
-      if (i - 1 >= lo) { mm = lane < 8 ? __ldg(mtw + ((size_t)(i - 1) << 3) + lane) : 0u; tb_ = t[i - 1]; }
-      const int s1 = slot;
-      slot = s1 + 1; if (slot >= ZB_RING) slot -= ZB_RING;
-      const uint16_t base = ring[s1];
-      int bestc = tlit[lit], bestlen = 0, bestoff = 0;
-      const int len0 = (int)(cur & 0xffffu), moff = (int)(cur >> 16);
-      const bool valid = lane < 8 && len0 >= ZB_MIN_MATCH;
-      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-      if (vmask) {
-         int ml = len0; if (i + ml > end) ml = end - i;
-         const int offc = valid ? (int)toff[zb_off_sym((uint32_t)moff)] : 0;
-         const bool leave = valid && len0 >= ZB_LEAVE_ALONE;
-         const unsigned lmask = __ballot_sync(0xffffffffu, leave);
-         if (lmask) {
-            unsigned key = 0xffffffffu;
-            if (leave) {
-               int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING;
-               int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
-               const int cnd = (int)tlen[lidx] + offc + (int)(int16_t)(uint16_t)(ring[sl] - base);
-               key = ((unsigned)(cnd + 8192) << 5) | (unsigned)lane;
-            }
-            const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
-            const int cnd = (int)(kmin >> 5) - 8192;
-            const int wl = (int)(kmin & 31u);
-            const int wml = __shfl_sync(0xffffffffu, ml, wl), wof = __shfl_sync(0xffffffffu, moff, wl);
-            if (cnd < bestc) { bestc = cnd; bestlen = wml; bestoff = wof; }
-         }
-         unsigned smask = vmask & ~lmask;
-         while (smask) {
-            const int m = __ffs((int)smask) - 1;
-            smask &= smask - 1;
-            const int mlm = __shfl_sync(0xffffffffu, ml, m), offm = __shfl_sync(0xffffffffu, offc, m), moffm = __shfl_sync(0xffffffffu, moff, m);
-            const int cntm = mlm - 2;
-            for (int r0 = 0; r0 < cntm; r0 += 32) {
-               const int idx = r0 + lane;
+                                                    int lo, int from, int end, int keep_hi, zb_match_t *best, uint16_t *ring, int &slot, int lane,
+                                                    uint32_t *mbuf /* [32][8] */, uint8_t *tbuf /* [32] */) {
+   /* positions are taken in groups of 32, top down; while a group is processed out of shared memory the records of the
+      next group (32 x 32 B, one record per lane) are already in flight into registers */
+   int ghi = from - 1;
+   uint4 ra = make_uint4(0, 0, 0, 0), rb = ra; uint32_t rt = 0;
+   if (ghi - lane >= lo) { const uint4 *q = (const uint4 *)(mtw + ((size_t)(ghi - lane) << 3)); ra = __ldg(q); rb = __ldg(q + 1); rt = t[ghi - lane]; }
+   for (; ghi >= lo; ghi -= 32) {
+      {
+         uint4 *mb = (uint4 *)(mbuf + lane * 8);
+         mb[0] = ra; mb[1] = rb; tbuf[lane] = (uint8_t)rt;
+      }
+      __syncwarp();
+      const int nh = ghi - 32;
+      if (nh - lane >= lo) { const uint4 *q = (const uint4 *)(mtw + ((size_t)(nh - lane) << 3)); ra = __ldg(q); rb = __ldg(q + 1); rt = t[nh - lane]; }
+      const int cntg = ghi - lo + 1 < 32 ? ghi - lo + 1 : 32;
+      for (int j = 0; j < cntg; j++) {
+         const int i = ghi - j;
+         const uint32_t cur = lane < 8 ? mbuf[j * 8 + lane] : 0u;
+         const uint32_t lit = tbuf[j];
+         const int s1 = slot;
+         slot = s1 + 1; if (slot >= ZB_RING) slot -= ZB_RING;
+         const uint16_t base = ring[s1];
+         int bestc = tlit[lit], bestlen = 0, bestoff = 0;
+         const int len0 = (int)(cur & 0xffffu), moff = (int)(cur >> 16);
+         const bool valid = lane < 8 && len0 >= ZB_MIN_MATCH;
+         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+         if (vmask) {
+            int ml = len0; if (i + ml > end) ml = end - i;
+            const int offc = valid ? (int)toff[zb_off_sym((uint32_t)moff)] : 0;
+            const bool leave = valid && len0 >= ZB_LEAVE_ALONE;
+            const unsigned lmask = __ballot_sync(0xffffffffu, leave);
+            if (lmask) {
                unsigned key = 0xffffffffu;
-               if (idx < cntm) {
-                  const int k = mlm - idx;
-                  int sl = s1 - (k - 1); if (sl < 0) sl += ZB_RING;
-                  const int cnd = (int)tlen[k - ZB_MIN_MATCH] + offm + (int)(int16_t)(uint16_t)(ring[sl] - base);
+               if (leave) {
+                  int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING;
+                  int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
+                  const int cnd = (int)tlen[lidx] + offc + (int)(int16_t)(uint16_t)(ring[sl] - base);
                   key = ((unsigned)(cnd + 8192) << 5) | (unsigned)lane;
                }
                const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
                const int cnd = (int)(kmin >> 5) - 8192;
-               if (cnd < bestc) { bestc = cnd; bestlen = mlm - (r0 + (int)(kmin & 31u)); bestoff = moffm; }
+               const int wl = (int)(kmin & 31u);
+               const int wml = __shfl_sync(0xffffffffu, ml, wl), wof = __shfl_sync(0xffffffffu, moff, wl);
+               if (cnd < bestc) { bestc = cnd; bestlen = wml; bestoff = wof; }
+            }
+            unsigned smask = vmask & ~lmask;
+            while (smask) {
+               const int m = __ffs((int)smask) - 1;
+               smask &= smask - 1;
+               const int mlm = __shfl_sync(0xffffffffu, ml, m), offm = __shfl_sync(0xffffffffu, offc, m), moffm = __shfl_sync(0xffffffffu, moff, m);
+               const int cntm = mlm - 2;
+               for (int r0 = 0; r0 < cntm; r0 += 32) {
+                  const int idx = r0 + lane;
+                  unsigned key = 0xffffffffu;
+                  if (idx < cntm) {
+                     const int k = mlm - idx;
+                     int sl = s1 - (k - 1); if (sl < 0) sl += ZB_RING;
+                     const int cnd = (int)tlen[k - ZB_MIN_MATCH] + offm + (int)(int16_t)(uint16_t)(ring[sl] - base);
+                     key = ((unsigned)(cnd + 8192) << 5) | (unsigned)lane;
+                  }
+                  const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+                  const int cnd = (int)(kmin >> 5) - 8192;
+                  if (cnd < bestc) { bestc = cnd; bestlen = mlm - (r0 + (int)(kmin & 31u)); bestoff = moffm; }
+               }
             }
          }
+         if (lane == 0) {
+            ring[slot] = (uint16_t)(base + (uint16_t)bestc);
+            if (i < keep_hi) { zb_match_t b; b.length = (uint16_t)bestlen; b.offset = (uint16_t)bestoff; best[i] = b; }
+         }
+         __syncwarp();
       }
-      if (lane == 0) {
-         ring[slot] = (uint16_t)(base + (uint16_t)bestc);
-         if (i < keep_hi) { zb_match_t b; b.length = (uint16_t)bestlen; b.offset = (uint16_t)bestoff; best[i] = b; }
-      }
-      __syncwarp();
    }
 }
 
@@ -727,6 +798,8 @@ __global__ void __launch_bounds__(128) zb_parse_dp_k(const ZbSub *sb, const ZbSu
                                                      const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw) {
    __shared__ uint16_t ring_s[4][ZB_RING + 4];
    __shared__ uint32_t tab_s[4][(sizeof(ZbCostTab) + 3) / 4];
+   __shared__ __align__(16) uint32_t mbuf_s[4][32 * 8];
+   __shared__ uint8_t tbuf_s[4][32];
    const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
    const long c = (long)blockIdx.x * 4 + wl;
    if (c >= ndch) return;
@@ -748,7 +821,7 @@ __global__ void __launch_bounds__(128) zb_parse_dp_k(const ZbSub *sb, const ZbSu
    const uint8_t *tlit = (const uint8_t *)tab_s[wl], *tlen = tlit + 256, *toff = tlit + 512;
    const uint32_t *mtw = (const uint32_t *)(mt + ((size_t)gb << 3));
    int slot = 0;
-   if (from > hi) zb_parse_range_warp(t, mtw, tlit, tlen, toff, hi, from, end, hi, bm + gb, ring, slot, lane);
+   if (from > hi) zb_parse_range_warp(t, mtw, tlit, tlen, toff, hi, from, end, hi, bm + gb, ring, slot, lane, mbuf_s[wl], tbuf_s[wl]);
    {
       int16_t *sw = sgw + (size_t)c * 260;
       const uint16_t b = ring[slot];
@@ -758,7 +831,7 @@ __global__ void __launch_bounds__(128) zb_parse_dp_k(const ZbSub *sb, const ZbSu
       }
    }
    __syncwarp();
-   zb_parse_range_warp(t, mtw, tlit, tlen, toff, lo, hi, end, hi, bm + gb, ring, slot, lane);
+   zb_parse_range_warp(t, mtw, tlit, tlen, toff, lo, hi, end, hi, bm + gb, ring, slot, lane, mbuf_s[wl], tbuf_s[wl]);
    {
       int16_t *sg = sgt + (size_t)c * 260;
       const uint16_t b = ring[slot];
