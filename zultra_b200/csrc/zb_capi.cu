@@ -10,6 +10,7 @@ extern int g_zb_cuda_error;
 
 struct zultra_cuda_ctx_s {
    int device;
+   unsigned tile = 0;
    ZbPipe pipe;
    float ms[8];
    long long counters[8];
@@ -59,6 +60,12 @@ int zultra_cuda_ctx_create(zultra_cuda_ctx_t **pp, int device) {
    c->device = device;
    memset(c->ms, 0, sizeof(c->ms)); memset(c->counters, 0, sizeof(c->counters));
    if (cudaStreamCreateWithFlags(&c->pipe.st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ZULTRA_CUDA_ERR_CUDA; }
+   {  /* tuning knobs (never change the output) */
+      const char *e;
+      if ((e = getenv("ZULTRA_CUDA_PARSE_CD")) && atoi(e) >= 512) c->pipe.parse_cd = atoi(e);
+      if ((e = getenv("ZULTRA_CUDA_PARSE_WU")) && atoi(e) >= 258) c->pipe.parse_wu = atoi(e);
+      if ((e = getenv("ZULTRA_CUDA_TILE")) && atoi(e) >= 256) c->tile = (unsigned)atoi(e);
+   }
    *pp = c;
    return 0;
 }
@@ -79,6 +86,7 @@ static int run_one(zultra_cuda_ctx_t *c, const ZbStreamIn &s, unsigned block, Zb
    cudaEvent_t e0, e1;
    cudaEventCreate(&e0); cudaEventCreate(&e1);
    cudaEventRecord(e0, c->pipe.st);
+   if (!o.tile_main) o.tile_main = c->tile;
    int rc = zb_run_batch(c->pipe, &s, 1, block, c->out, res, o);
    cudaEventRecord(e1, c->pipe.st);
    cudaEventSynchronize(e1);

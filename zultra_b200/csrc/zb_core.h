@@ -536,21 +536,41 @@ ZB_HD void zb_make_costtab(const int *llen, const int *olen, ZbCostTab &t) {
  * Writes best[i] for i in [lo, keep_hi).  If sig != 0, stores cost[lo+k]-cost[lo] for k=0..258 (0 beyond end).
  * RING: accessor with get(slot)/set(slot,v).
  */
+struct ZbMatchRec { uint32_t w[8]; };   /* the 8 candidates of one position: length | offset << 16 */
+ZB_HD ZbMatchRec zb_load_rec(const zb_match_t *match, int i) {
+   ZbMatchRec r;
+#ifdef __CUDA_ARCH__
+   const uint4 *q = (const uint4 *)(match + ((size_t)i << 3));
+   const uint4 a = __ldg(q), b = __ldg(q + 1);
+   r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w; r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+#else
+   const zb_match_t *pm = match + ((size_t)i << 3);
+   for (int m = 0; m < 8; m++) r.w[m] = (uint32_t)pm[m].length | ((uint32_t)pm[m].offset << 16);
+#endif
+   return r;
+}
+
 template <class RING>
 ZB_HD void zb_parse_range(const uint8_t *T, const zb_match_t *match, const ZbCostTab &tab, int lo, int from, int end,
                           int keep_hi, zb_match_t *best, RING &ring, int &slot /* in: slot of `from`; out: slot of lo */) {
    int s = slot;
+   if (from - 1 < lo) return;
+   ZbMatchRec nxt = zb_load_rec(match, from - 1);
+   uint32_t nlit = T[from - 1];
    for (int i = from - 1; i >= lo; i--) {
+      const ZbMatchRec rec = nxt;
+      const uint32_t lit = nlit;
+      if (i - 1 >= lo) { nxt = zb_load_rec(match, i - 1); nlit = T[i - 1]; }   /* independent of the recurrence: overlaps with it */
       int s1 = s;                 /* slot of i+1 */
       s = s1 + 1; if (s >= ZB_RING) s -= ZB_RING; /* slot of i: going down in position = going up in slot */
       const uint16_t base = ring.get(s1);
-      int bestc = tab.lit[T[i]];
+      int bestc = tab.lit[lit];
       int bestlen = 0, bestoff = 0;
-      const zb_match_t *pm = match + ((size_t)i << 3);
+#pragma unroll
       for (int m = 0; m < ZB_NMATCH; m++) {
-         const int mlen0 = pm[m].length;
+         const int mlen0 = (int)(rec.w[m] & 0xffffu);
          if (mlen0 < ZB_MIN_MATCH) break;
-         const int moff = pm[m].offset;
+         const int moff = (int)(rec.w[m] >> 16);
          const int offc = tab.off[zb_off_sym((uint32_t)moff)];
          int ml = mlen0;
          if (i + ml > end) ml = end - i;
@@ -578,6 +598,12 @@ struct ZbRingLocal {
    uint16_t v[ZB_RING];
    ZB_HD uint16_t get(int s) const { return v[s]; }
    ZB_HD void set(int s, uint16_t x) { v[s] = x; }
+};
+/* ring of one thread inside a shared-memory array laid out [slot][thread] */
+struct ZbRingStrided {
+   uint16_t *base; int stride;
+   ZB_HD uint16_t get(int s) const { return base[s * stride]; }
+   ZB_HD void set(int s, uint16_t x) { base[s * stride] = x; }
 };
 
 #endif /* ZB_CORE_H */

@@ -124,6 +124,7 @@ struct ZbPipe {
    std::vector<ZbStreamOut> h_sout;
    int nsub = 0;
    /* stats */
+   int parse_cd = ZB_CD, parse_wu = ZB_WU;   /* parse chunk / warm-up positions */
    int stat_sa_rounds = 0, stat_redo = 0, stat_ub = 0, stat_tiles = 0;
    double t_stage[8];
 
@@ -263,11 +264,15 @@ inline void ZbPipe::stage_sa() {
 
 /* ============================================================ match finder ============================================================ */
 #ifndef ZB_EMU
-/* CTA per tile: the tile's suffix list (<= 32768 + T words) and the rank of every main position live in shared memory;
-   each thread scans the lists of its main positions (zb_mf_scan) and writes the 32-byte match record. */
-__global__ void __launch_bounds__(512) zb_mf_scan_k(const ZbTileDesc *td, int first, const uint32_t *lists, size_t stride, const uint32_t *cnts,
-                                                    zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs) {
+/* CTA per tile: the tile's suffix list (<= 32768 + T words) and the rank of every main position live in shared memory.
+   Scan lengths are heavy-tailed (a common trigram means hundreds of neighbours), so lanes do not own fixed positions:
+   a lane that finishes fetches the next main position from a shared counter and all 32 lanes keep stepping
+   (same arithmetic as zb_mf_scan, kept as a resumable state). */
+#define ZB_MF_THREADS 1024
+__global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *td, int first, const uint32_t *lists, size_t stride, const uint32_t *cnts,
+                                                              zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs) {
    extern __shared__ uint32_t zb_smw[];
+   __shared__ uint32_t next_m;
    const int k = blockIdx.x;
    const ZbTileDesc t = td[first + k];
    const int n = (int)cnts[k];
@@ -275,6 +280,7 @@ __global__ void __launch_bounds__(512) zb_mf_scan_k(const ZbTileDesc *td, int fi
    uint32_t *words = zb_smw;
    uint16_t *rom = (uint16_t *)(zb_smw + stride);
    const uint32_t *src = lists + (size_t)k * stride;
+   if (threadIdx.x == 0) next_m = 0;
    for (int e = threadIdx.x; e < n; e += blockDim.x) {
       const uint32_t w = src[e];
       words[e] = w;
@@ -283,24 +289,72 @@ __global__ void __launch_bounds__(512) zb_mf_scan_k(const ZbTileDesc *td, int fi
    }
    __syncthreads();
    const uint32_t gbase = wbs[t.win];
-   for (uint32_t m = threadIdx.x; m < nmain; m += blockDim.x) {
-      zb_match_t o[ZB_NMATCH];
-      const uint32_t p = t.m0 + m;
-      const int nm = zb_mf_scan(words, n, (int)rom[m], nlook + m, o);
-      const uint32_t maxlen = t.wlen - p;   /* matchfinder.c:276-280 (LAST_LITERALS = 0) */
-      uint32_t rec[ZB_NMATCH];
+   /* per-lane scan state */
+   bool busy = false, drained = false;
+   uint32_t m = 0, i = 0, lL = 0, lR = 0, lvl = 0, rec[ZB_NMATCH];
+   int L = 0, R = 0, best = -1, minpos = 0, nm = 0;
+   bool moved = false;
+   for (;;) {
+      if (!busy && !drained) {
+         m = atomicAdd(&next_m, 1u);
+         if (m >= nmain) drained = true;
+         else {
+            busy = true;
+            const int r = (int)rom[m];
+            i = nlook + m;
+            L = r - 1; R = r + 1;
+            lL = r > 0 ? (words[r] >> ZB_POS_BITS) : 0u;
+            lR = R < n ? (words[R] >> ZB_POS_BITS) : 0u;
+            minpos = i > ZB_MAX_OFFSET ? (int)(i - ZB_MAX_OFFSET) : 0;
+            nm = 0; best = -1; lvl = 0; moved = false;
 #pragma unroll
-      for (int q = 0; q < ZB_NMATCH; q++) {
-         uint32_t len = 0, off = 0;
-         if (q < nm) { len = o[q].length; off = o[q].offset; if (len > maxlen) len = maxlen; }
-         rec[q] = len | (off << 16);
+            for (int q = 0; q < ZB_NMATCH; q++) rec[q] = 0;
+         }
       }
-      uint4 *dst = (uint4 *)(mt + ((size_t)(gbase + p) << 3));
-      dst[0] = make_uint4(rec[0], rec[1], rec[2], rec[3]);
-      dst[1] = make_uint4(rec[4], rec[5], rec[6], rec[7]);
-      const uint32_t l0 = rec[0] & 0xffffu;
-      gl[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)l0 : (uint16_t)1;
-      go[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)(rec[0] >> 16) : (uint16_t)0;
+      if (__all_sync(0xffffffffu, drained && !busy)) break;
+      if (busy) {
+#pragma unroll 1
+         for (int step = 0; step < 8; step++) {
+            const uint32_t l = lL > lR ? lL : lR;
+            bool fin = false;
+            if (l < lvl && moved) {
+               const uint32_t v = lvl | ((i - (uint32_t)best) << 16);
+#pragma unroll
+               for (int q = 0; q < ZB_NMATCH; q++) if (q == nm) rec[q] = v;
+               nm++; moved = false;
+               if (nm == ZB_NMATCH || best == (int)i - 1) fin = true;
+            }
+            if (!fin && l < ZB_MIN_MATCH) fin = true;
+            if (fin) {
+               const uint32_t p = t.m0 + m;
+               const uint32_t maxlen = t.wlen - p;   /* matchfinder.c:276-280 (LAST_LITERALS = 0) */
+#pragma unroll
+               for (int q = 0; q < ZB_NMATCH; q++) { uint32_t len = rec[q] & 0xffffu; if (len > maxlen) rec[q] = (rec[q] & 0xffff0000u) | maxlen; }
+               uint4 *dst = (uint4 *)(mt + ((size_t)(gbase + p) << 3));
+               dst[0] = make_uint4(rec[0], rec[1], rec[2], rec[3]);
+               dst[1] = make_uint4(rec[4], rec[5], rec[6], rec[7]);
+               const uint32_t l0 = rec[0] & 0xffffu;
+               gl[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)l0 : (uint16_t)1;
+               go[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)(rec[0] >> 16) : (uint16_t)0;
+               busy = false;
+               break;
+            }
+            lvl = l;
+            int p;
+            if (lL >= lR) {
+               const uint32_t w = words[L];
+               p = (int)(w & ZB_POS_MASK);
+               const uint32_t wl = w >> ZB_POS_BITS;
+               lL = L > 0 ? (wl < lL ? wl : lL) : 0u;
+               L--;
+            } else {
+               p = (int)(words[R] & ZB_POS_MASK);
+               R++;
+               if (R < n) { const uint32_t wl = words[R] >> ZB_POS_BITS; lR = wl < lR ? wl : lR; } else lR = 0u;
+            }
+            if (p < (int)i && p >= minpos && p > best) { best = p; moved = true; }
+         }
+      }
    }
 }
 #endif
@@ -354,7 +408,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
       zb_tile_filter(st, unit_words.p, unit_cnt.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p);
 #ifndef ZB_EMU
       if (g_zb_prof_on) { zb_tag("mf_scan"); zb_prof_begin(0, st); }
-      zb_mf_scan_k<<<cnt, 512, smem, st>>>(td, first, ivb, stride, tc, mt, gl, go, wbs);
+      zb_mf_scan_k<<<cnt, ZB_MF_THREADS, smem, st>>>(td, first, ivb, stride, tc, mt, gl, go, wbs);
       if (g_zb_prof_on) zb_prof_end(st);
       g_zb_launches++;
       ZB_CUDA_CHECK(cudaGetLastError());
@@ -711,97 +765,15 @@ ZB_HD void zb_walk_best(const zb_match_t *best, uint32_t entry, uint32_t hi, F &
 }
 
 #ifndef ZB_EMU
-/* ---- warp-cooperative form of the chunked backward recurrence (same arithmetic as zb_parse_range) ----
- * One warp per parse chunk.  The 260-entry cost ring and the sub-block's cost table live in shared memory; per position
- * lanes 0..7 hold the 8 match candidates (one coalesced 32-byte load, prefetched one position ahead), the >= 40
- * "leave alone" matches are priced in one round (one lane each) and every shorter match in rounds of 32 lengths;
- * each round is one redux.min on (cost << 5 | lane), which keeps the reference's order on ties (literal, then matches
- * longest first, lengths descending, strict >, blockdeflate.c:272-312). */
-__device__ __forceinline__ void zb_parse_range_warp(const uint8_t *t, const uint32_t *mtw, const uint8_t *tlit, const uint8_t *tlen, const uint8_t *toff,
-                                                    int lo, int from, int end, int keep_hi, zb_match_t *best, uint16_t *ring, int &slot, int lane,
-                                                    uint32_t *mbuf /* [32][8] */, uint8_t *tbuf /* [32] */) {
-   /* positions are taken in groups of 32, top down; while a group is processed out of shared memory the records of the
-      next group (32 x 32 B, one record per lane) are already in flight into registers */
-   int ghi = from - 1;
-   uint4 ra = make_uint4(0, 0, 0, 0), rb = ra; uint32_t rt = 0;
-   if (ghi - lane >= lo) { const uint4 *q = (const uint4 *)(mtw + ((size_t)(ghi - lane) << 3)); ra = __ldg(q); rb = __ldg(q + 1); rt = t[ghi - lane]; }
-   for (; ghi >= lo; ghi -= 32) {
-      {
-         uint4 *mb = (uint4 *)(mbuf + lane * 8);
-         mb[0] = ra; mb[1] = rb; tbuf[lane] = (uint8_t)rt;
-      }
-      __syncwarp();
-      const int nh = ghi - 32;
-      if (nh - lane >= lo) { const uint4 *q = (const uint4 *)(mtw + ((size_t)(nh - lane) << 3)); ra = __ldg(q); rb = __ldg(q + 1); rt = t[nh - lane]; }
-      const int cntg = ghi - lo + 1 < 32 ? ghi - lo + 1 : 32;
-      for (int j = 0; j < cntg; j++) {
-         const int i = ghi - j;
-         const uint32_t cur = lane < 8 ? mbuf[j * 8 + lane] : 0u;
-         const uint32_t lit = tbuf[j];
-         const int s1 = slot;
-         slot = s1 + 1; if (slot >= ZB_RING) slot -= ZB_RING;
-         const uint16_t base = ring[s1];
-         int bestc = tlit[lit], bestlen = 0, bestoff = 0;
-         const int len0 = (int)(cur & 0xffffu), moff = (int)(cur >> 16);
-         const bool valid = lane < 8 && len0 >= ZB_MIN_MATCH;
-         const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-         if (vmask) {
-            int ml = len0; if (i + ml > end) ml = end - i;
-            const int offc = valid ? (int)toff[zb_off_sym((uint32_t)moff)] : 0;
-            const bool leave = valid && len0 >= ZB_LEAVE_ALONE;
-            const unsigned lmask = __ballot_sync(0xffffffffu, leave);
-            if (lmask) {
-               unsigned key = 0xffffffffu;
-               if (leave) {
-                  int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING;
-                  int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
-                  const int cnd = (int)tlen[lidx] + offc + (int)(int16_t)(uint16_t)(ring[sl] - base);
-                  key = ((unsigned)(cnd + 8192) << 5) | (unsigned)lane;
-               }
-               const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
-               const int cnd = (int)(kmin >> 5) - 8192;
-               const int wl = (int)(kmin & 31u);
-               const int wml = __shfl_sync(0xffffffffu, ml, wl), wof = __shfl_sync(0xffffffffu, moff, wl);
-               if (cnd < bestc) { bestc = cnd; bestlen = wml; bestoff = wof; }
-            }
-            unsigned smask = vmask & ~lmask;
-            while (smask) {
-               const int m = __ffs((int)smask) - 1;
-               smask &= smask - 1;
-               const int mlm = __shfl_sync(0xffffffffu, ml, m), offm = __shfl_sync(0xffffffffu, offc, m), moffm = __shfl_sync(0xffffffffu, moff, m);
-               const int cntm = mlm - 2;
-               for (int r0 = 0; r0 < cntm; r0 += 32) {
-                  const int idx = r0 + lane;
-                  unsigned key = 0xffffffffu;
-                  if (idx < cntm) {
-                     const int k = mlm - idx;
-                     int sl = s1 - (k - 1); if (sl < 0) sl += ZB_RING;
-                     const int cnd = (int)tlen[k - ZB_MIN_MATCH] + offm + (int)(int16_t)(uint16_t)(ring[sl] - base);
-                     key = ((unsigned)(cnd + 8192) << 5) | (unsigned)lane;
-                  }
-                  const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
-                  const int cnd = (int)(kmin >> 5) - 8192;
-                  if (cnd < bestc) { bestc = cnd; bestlen = mlm - (r0 + (int)(kmin & 31u)); bestoff = moffm; }
-               }
-            }
-         }
-         if (lane == 0) {
-            ring[slot] = (uint16_t)(base + (uint16_t)bestc);
-            if (i < keep_hi) { zb_match_t b; b.length = (uint16_t)bestlen; b.offset = (uint16_t)bestoff; best[i] = b; }
-         }
-         __syncwarp();
-      }
-   }
-}
-
-__global__ void __launch_bounds__(128) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
-                                                     const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw) {
-   __shared__ uint16_t ring_s[4][ZB_RING + 4];
-   __shared__ uint32_t tab_s[4][(sizeof(ZbCostTab) + 3) / 4];
-   __shared__ __align__(16) uint32_t mbuf_s[4][32 * 8];
-   __shared__ uint8_t tbuf_s[4][32];
-   const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
-   const long c = (long)blockIdx.x * 4 + wl;
+/* ---- chunked backward recurrence, one thread per parse chunk (32 independent chunks per warp) ----
+ * The 260-entry cost ring of every thread lives in shared memory ([slot][thread], so a warp's accesses fall into
+ * distinct banks up to the 2-way u16 pairing); match records are fetched one position ahead (zb_parse_range). */
+#define ZB_DP_THREADS 64
+__global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
+                                                               const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw,
+                                                               int CD, int WU) {
+   __shared__ uint16_t ring_s[ZB_RING * ZB_DP_THREADS];
+   const long c = (long)blockIdx.x * ZB_DP_THREADS + threadIdx.x;
    if (c >= ndch) return;
    const uint32_t x = dcs[c];
    const ZbSub s = sb[x];
@@ -809,41 +781,37 @@ __global__ void __launch_bounds__(128) zb_parse_dp_k(const ZbSub *sb, const ZbSu
    const uint32_t k = (uint32_t)c - s.dchunk_base;
    const uint32_t gb = wbs[s.win];
    const uint8_t *t = T + wd[s.win].in_off;
-   const int lo = (int)(s.ps + k * ZB_CD);
-   const int hi = (int)(lo + ZB_CD < (int)s.pe ? lo + ZB_CD : (int)s.pe);
+   const int lo = (int)(s.ps + k * CD);
+   const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
    const int end = (int)s.pe;
-   int from = hi + ZB_WU; if (from > end) from = end;
-   const uint32_t *tsrc = (const uint32_t *)&tb[x].cost;
-   for (int j = lane; j < (int)(sizeof(ZbCostTab) / 4); j += 32) tab_s[wl][j] = tsrc[j];
-   uint16_t *ring = ring_s[wl];
-   for (int j = lane; j < ZB_RING; j += 32) ring[j] = 0;
-   __syncwarp();
-   const uint8_t *tlit = (const uint8_t *)tab_s[wl], *tlen = tlit + 256, *toff = tlit + 512;
-   const uint32_t *mtw = (const uint32_t *)(mt + ((size_t)gb << 3));
+   int from = hi + WU; if (from > end) from = end;
+   ZbRingStrided ring = {ring_s + threadIdx.x, ZB_DP_THREADS};
+   for (int i = 0; i < ZB_RING; i++) ring.set(i, 0);
    int slot = 0;
-   if (from > hi) zb_parse_range_warp(t, mtw, tlit, tlen, toff, hi, from, end, hi, bm + gb, ring, slot, lane, mbuf_s[wl], tbuf_s[wl]);
+   const ZbCostTab &ct = tb[x].cost;
+   if (from > hi) zb_parse_range(t, mt + ((size_t)gb << 3), ct, hi, from, end, hi, bm + gb, ring, slot);
    {
       int16_t *sw = sgw + (size_t)c * 260;
-      const uint16_t b = ring[slot];
-      for (int q = lane; q <= ZB_MAX_MATCH; q += 32) {
+      const uint16_t b = ring.get(slot);
+      for (int q = 0; q <= ZB_MAX_MATCH; q++) {
          int sl = slot - q; if (sl < 0) sl += ZB_RING;
-         sw[q] = (hi + q <= end && hi + q <= from) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
+         sw[q] = (hi + q <= end && hi + q <= from) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
       }
    }
-   __syncwarp();
-   zb_parse_range_warp(t, mtw, tlit, tlen, toff, lo, hi, end, hi, bm + gb, ring, slot, lane, mbuf_s[wl], tbuf_s[wl]);
+   zb_parse_range(t, mt + ((size_t)gb << 3), ct, lo, hi, end, hi, bm + gb, ring, slot);
    {
       int16_t *sg = sgt + (size_t)c * 260;
-      const uint16_t b = ring[slot];
-      for (int q = lane; q <= ZB_MAX_MATCH; q += 32) {
+      const uint16_t b = ring.get(slot);
+      for (int q = 0; q <= ZB_MAX_MATCH; q++) {
          int sl = slot - q; if (sl < 0) sl += ZB_RING;
-         sg[q] = (lo + q <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
+         sg[q] = (lo + q <= end) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
       }
    }
 }
 #endif
 
 inline void ZbPipe::stage_parse() {
+   const int CD = parse_cd, WU = parse_wu;
    const int ns = nsub;
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
    ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in_ptr, win.p};
@@ -881,7 +849,7 @@ inline void ZbPipe::stage_parse() {
       uint32_t d = 0, p = 0;
       for (int x = 0; x < ns; x++) {
          uint32_t size = sb[x].pe - sb[x].ps;
-         sb[x].dchunk_base = d; sb[x].ndchunk = (size + ZB_CD - 1) / ZB_CD; d += sb[x].ndchunk;
+         sb[x].dchunk_base = d; sb[x].ndchunk = (size + CD - 1) / CD; d += sb[x].ndchunk;
          sb[x].pchunk_base = p; sb[x].npchunk = (size + ZB_CP - 1) / ZB_CP; p += sb[x].npchunk;
       }
       cn[4] = d; cn[5] = p;
@@ -904,12 +872,12 @@ inline void ZbPipe::stage_parse() {
 
    for (int pass = 0; pass < 4; pass++) {
       /* D2: chunked backward recurrence.  Chunk k of a sub-block covers [ps + k*CD, ..).  Every chunk but the last
-         starts ZB_WU positions past its end from an all-zero cost guess; the relative costs it sees at its own end
+         starts WU positions past its end from an all-zero cost guess; the relative costs it sees at its own end
          (sig_warm) are later compared with what the next chunk really computed there (sig_true). */
 #ifndef ZB_EMU
       if (ndch > 0) {
          if (g_zb_prof_on) { zb_tag("parse_dp"); zb_prof_begin(0, st); }
-         zb_parse_dp_k<<<(unsigned)((ndch + 3) / 4), 128, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw);
+         zb_parse_dp_k<<<(unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS), ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, CD, WU);
          if (g_zb_prof_on) zb_prof_end(st);
          g_zb_launches++;
          ZB_CUDA_CHECK(cudaGetLastError());
@@ -922,10 +890,10 @@ inline void ZbPipe::stage_parse() {
          const uint32_t k = (uint32_t)c - s.dchunk_base;
          const uint32_t gb = wbs[s.win];
          const uint8_t *t = T + wd[s.win].in_off;
-         const int lo = (int)(s.ps + k * ZB_CD);
-         const int hi = (int)(lo + ZB_CD < (int)s.pe ? lo + ZB_CD : (int)s.pe);
+         const int lo = (int)(s.ps + k * CD);
+         const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
          const int end = (int)s.pe;
-         int from = hi + ZB_WU; if (from > end) from = end;
+         int from = hi + WU; if (from > end) from = end;
          ZbRingLocal ring;
          for (int i = 0; i < ZB_RING; i++) ring.v[i] = 0;
          int slot = 0;
@@ -957,8 +925,8 @@ inline void ZbPipe::stage_parse() {
          const uint32_t k = (uint32_t)c - s.dchunk_base;
          uint8_t good = 1;
          if (k + 1 < s.ndchunk) {
-            const int hi = (int)(s.ps + (k + 1) * ZB_CD), end = (int)s.pe;
-            int from = hi + ZB_WU; if (from > end) from = end;
+            const int hi = (int)(s.ps + (k + 1) * CD), end = (int)s.pe;
+            int from = hi + WU; if (from > end) from = end;
             const int16_t *a = sgw + (size_t)c * 260, *b = sgt + (size_t)(c + 1) * 260;
             int lim = from - hi; if (lim > ZB_MAX_MATCH) lim = ZB_MAX_MATCH;
             /* the warm-up must have covered the whole horizon, else it started from the true end state anyway */
@@ -979,12 +947,12 @@ inline void ZbPipe::stage_parse() {
          const ZbCostTab &ct = tb[x].cost;
          for (int k = (int)s.ndchunk - 2; k >= 0; k--) {
             const size_t c = s.dchunk_base + k;
-            const int lo = (int)(s.ps + k * ZB_CD), hi = lo + ZB_CD;
+            const int lo = (int)(s.ps + k * CD), hi = lo + CD;
             bool good = ok[c];
             if (good) continue;
             /* re-check against the (possibly repaired) neighbour before redoing */
             {
-               int from = hi + ZB_WU; if (from > end) from = end;
+               int from = hi + WU; if (from > end) from = end;
                int lim = from - hi; if (lim > ZB_MAX_MATCH) lim = ZB_MAX_MATCH;
                good = !(from < end && from - hi < ZB_MAX_MATCH);
                const int16_t *a = sgw + c * 260, *b = sgt + (c + 1) * 260;
