@@ -480,7 +480,12 @@ ZB_HD int zb_mf_walk(uint32_t *iv, uint32_t *pd, uint32_t i, zb_match_t *out) {
  * reports, longest first - for each length the nearest earlier occurrence, each position once, with its own length
  * (SURVEY 8(a)-M1).  The reference stops storing after 8 entries (matchfinder.c:217); nothing nearer than offset 1 exists.
  */
-ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, zb_match_t *out) {
+#define ZB_CHAIN_LO 3      /* levels ZB_CHAIN_LO .. ZB_CHAIN_HI-1 come from the nearest-previous tables (zb_mf_chain_*) */
+#define ZB_CHAIN_HI 6      /* the suffix-array scan only covers LCP levels >= ZB_CHAIN_HI */
+#define ZB_NCHAIN (ZB_CHAIN_HI - ZB_CHAIN_LO)
+
+/* chain[q] = offset from i to the nearest earlier position sharing >= ZB_CHAIN_LO+q bytes (0 = none within 32768) */
+ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, const uint16_t *chain, zb_match_t *out) {
    int L = r - 1, R = r + 1;
    uint32_t lL = r > 0 ? (words[r] >> ZB_POS_BITS) : 0u;
    uint32_t lR = R < n ? (words[R] >> ZB_POS_BITS) : 0u;
@@ -495,7 +500,7 @@ ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, zb_match_t
          moved = false;
          if (nm == ZB_NMATCH || best == (int)i - 1) return nm;
       }
-      if (l < ZB_MIN_MATCH) break;
+      if (l < ZB_CHAIN_HI) break;
       lvl = l;
       int p;
       if (lL >= lR) {
@@ -511,7 +516,43 @@ ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, zb_match_t
       }
       if (p < (int)i && p >= minpos && p > best) { best = p; moved = true; }
    }
+   /* levels below ZB_CHAIN_HI: the nearest earlier occurrence per level is known; it is new iff nearer than best */
+   for (int q = ZB_NCHAIN - 1; q >= 0 && nm < ZB_NMATCH; q--) {
+      const uint32_t off = chain[q];
+      if (off && (int)(i - off) > best) {
+         best = (int)(i - off);
+         out[nm].length = (uint16_t)(ZB_CHAIN_LO + q); out[nm].offset = (uint16_t)off; nm++;
+         if (off == 1) break;
+      }
+   }
    return nm;
+}
+
+/*
+ * Nearest earlier occurrence per position for one LCP level, over one unit (64 Ki positions: 32768 main + look-back).
+ * words: the unit's suffixes in suffix-array order.  Two suffixes share >= level bytes iff no LCP below `level` lies
+ * between them, so a group id is the index of the last entry whose LCP is < level.  Pass 1 gives every position its
+ * group id; pass 2 walks the positions in increasing order and links each to the previous position of its group.
+ * This is the sequential statement; the GPU runs the same two passes 32 positions at a time (zb_mf_chain_k).
+ * out[p - nlook] (main positions only) = offset, 0 if none or farther than 32768.
+ */
+ZB_HD void zb_mf_chain_unit(const uint32_t *words, int n, uint32_t level, uint32_t nlook, uint16_t *gidpos, uint32_t *last, uint16_t *out) {
+   uint32_t gid = 0;
+   for (int e = 0; e < n; e++) {
+      const uint32_t w = words[e];
+      if ((w >> ZB_POS_BITS) < level) { gid = (uint32_t)e; last[gid] = 0xffffffffu; }
+      gidpos[w & ZB_POS_MASK] = (uint16_t)gid;
+   }
+   for (uint32_t p = 0; p < (uint32_t)n; p++) {
+      const uint32_t g = gidpos[p];
+      const uint32_t prev = last[g];
+      last[g] = p;
+      if (p >= nlook) {
+         uint32_t off = prev != 0xffffffffu ? p - prev : 0u;
+         if (off > ZB_MAX_OFFSET) off = 0;
+         out[p - nlook] = (uint16_t)off;
+      }
+   }
 }
 
 /* ---- optimal parse (blockdeflate.c:254-323) ---- */
@@ -566,27 +607,44 @@ ZB_HD void zb_parse_range(const uint8_t *T, const zb_match_t *match, const ZbCos
       const uint16_t base = ring.get(s1);
       int bestc = tab.lit[lit];
       int bestlen = 0, bestoff = 0;
+      /* Candidates in the reference's order are: literal; then for m = 0..7, lengths ml..3 (only ml for a >= 40 match),
+         replaced on strictly lower cost (blockdeflate.c:272-312).  lencost(k) + cost[i+k] does not depend on the match,
+         so the best length of a short match is a prefix minimum over k (largest k on ties = first met going down), and
+         the matches are combined shortest first with "<=" so that the earlier (longer) match keeps ties.  Same choice,
+         at most 37 + 8 evaluations instead of 8 x 37. */
+      int M = 0;
 #pragma unroll
-      for (int m = 0; m < ZB_NMATCH; m++) {
-         const int mlen0 = (int)(rec.w[m] & 0xffffu);
-         if (mlen0 < ZB_MIN_MATCH) break;
-         const int moff = (int)(rec.w[m] >> 16);
-         const int offc = tab.off[zb_off_sym((uint32_t)moff)];
-         int ml = mlen0;
-         if (i + ml > end) ml = end - i;
-         if (mlen0 >= ZB_LEAVE_ALONE) {
-            int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING; /* slot of i+ml */
-            int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
-            int c = tab.len[lidx] + offc + (int16_t)(uint16_t)(ring.get(sl) - base);
-            if (bestc > c) { bestc = c; bestlen = ml; bestoff = moff; }
-         } else {
-            int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING;
-            for (int k = ml; k >= ZB_MIN_MATCH; k--) {
-               int c = tab.len[k - ZB_MIN_MATCH] + offc + (int16_t)(uint16_t)(ring.get(sl) - base);
-               if (bestc > c) { bestc = c; bestlen = k; bestoff = moff; }
-               sl++; if (sl >= ZB_RING) sl -= ZB_RING;
+      for (int m = 0; m < ZB_NMATCH; m++) if (M == m && (rec.w[m] & 0xffffu) >= ZB_MIN_MATCH) M = m + 1;
+      if (M) {
+         int bt = 0x7fffffff, bl = 0, bo = 0;
+         int k = ZB_MIN_MATCH, curmin = 0x7fffffff, curk = 0;
+         int sk = s1 - (ZB_MIN_MATCH - 1); if (sk < 0) sk += ZB_RING;   /* slot of i+3 */
+#pragma unroll
+         for (int m = ZB_NMATCH - 1; m >= 0; m--) {
+            if (m < M) {
+               const int mlen0 = (int)(rec.w[m] & 0xffffu), moff = (int)(rec.w[m] >> 16);
+               const int offc = tab.off[zb_off_sym((uint32_t)moff)];
+               int ml = mlen0;
+               if (i + ml > end) ml = end - i;
+               int total, kk;
+               if (mlen0 >= ZB_LEAVE_ALONE) {
+                  int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING;
+                  int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
+                  total = tab.len[lidx] + offc + (int16_t)(uint16_t)(ring.get(sl) - base);
+                  kk = ml;
+               } else {
+                  while (k <= ml) {
+                     const int c = tab.len[k - ZB_MIN_MATCH] + (int16_t)(uint16_t)(ring.get(sk) - base);
+                     if (c <= curmin) { curmin = c; curk = k; }
+                     k++; sk--; if (sk < 0) sk += ZB_RING;
+                  }
+                  total = curk ? curmin + offc : 0x7fffffff;
+                  kk = curk;
+               }
+               if (total <= bt && total != 0x7fffffff) { bt = total; bl = kk; bo = moff; }
             }
          }
+         if (bt < bestc) { bestc = bt; bestlen = bl; bestoff = bo; }
       }
       ring.set(s, (uint16_t)(base + (uint16_t)bestc));
       if (i < keep_hi) { best[i].length = (uint16_t)bestlen; best[i].offset = (uint16_t)bestoff; }
