@@ -176,9 +176,9 @@ def main():
     block = 1 << 20
     nblocks = (n + block - 1) // block
     # shard by contiguous max-block ranges; every rank keeps the 32 KiB before its first block as history
-    per = (nblocks + world - 1) // world
-    b0, b1 = min(nblocks, rank * per), min(nblocks, (rank + 1) * per)
-    lo, hi = b0 * block, min(n, b1 * block)
+    from zultra_b200 import shard
+    lo, hi = shard.plan_shards(n, block, world)[rank]
+    b0, b1 = lo // block, (hi + block - 1) // block
     L = z.load()
     L.zultra_cuda_profile.argtypes = [C.c_int]
     L.zultra_cuda_profile_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -199,7 +199,18 @@ def main():
 
     for _ in range(args.warmup):
         step(False)
-    L.zultra_cuda_profile_collect(None, None, None, 0) if False else None
+    # parity gate before any timing counts: the stream must inflate back to the input (and equal the 1-GPU stream)
+    if rank == 0:
+        import hashlib
+        import zlib
+        stream = runner.final_stream()
+        raw = data.tobytes()
+        assert zlib.decompress(stream, {0: -15, 1: 15, 2: 31}[w["flags"]]) == raw, "output does not inflate to the input"
+        stream_sha = hashlib.sha256(stream).hexdigest()
+        if world > 1 and len(data) <= (256 << 20):
+            one = z.memory_compress(data, w["flags"], block)
+            assert one == stream, "sharded stream differs from the single-GPU stream"
+        del raw
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -211,6 +222,8 @@ def main():
     names = C.create_string_buffer(32 * 256); kms = (C.c_float * 256)(); kcnt = (C.c_int * 256)()
     nk = L.zultra_cuda_profile_collect(names, kms, kcnt, 256)
     ktab = sorted([(names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), kms[i], kcnt[i]) for i in range(nk)], key=lambda r: -r[1])
+    if world > 1:
+        ktab = [r for r in ktab]
     t = torch.tensor([sum(times)], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -253,7 +266,7 @@ def main():
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s"},
                "stages_ms": {k: round(v, 3) for k, v in stages.items()},
                "kernels_ms_per_step": {r[0]: round(r[1] / args.steps, 3) for r in ktab[:12]},
-               "compressed_bytes": runner.last_out_bytes}
+               "compressed_bytes": runner.last_out_bytes, "stream_sha256": stream_sha, "verified": "inflate(stream) == input" + (" and == 1-GPU stream" if world > 1 else "")}
         if not args.no_cpu_baseline and world == 1:
             v, dt, sample = cpu_reference_timing(data, w["flags"], 1, 24 << 20)
             if v is not None:

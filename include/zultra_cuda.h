@@ -53,6 +53,20 @@ int zultra_cuda_compress_blocks_device(zultra_cuda_ctx_t *pCtx, const void *pDev
                                        int nDoFinalize, unsigned int nFlags, unsigned int *pnChecksum,
                                        void *pDevOutData, size_t nMaxOutDataSize, unsigned long long *pnOutBitCount);
 
+/*
+ * Sharded operation (multi-GPU): a shard = a contiguous range of max-blocks of one stream on one device, its input
+ * resident as [nHistorySize bytes preceding the shard | shard bytes].  Everything except the final placement of bits is
+ * independent of the entering bit phase, so shard_prepare runs the pipeline and reports the shard's total size in bits
+ * for each of the 8 possible entering phases (the stored-block decision of libzultra.c:345-347 depends on the phase);
+ * once the phases of the preceding shards are known, shard_emit writes the shard's bitstream for its true phase.
+ * *pnChecksum (shard_prepare) receives the checksum of the shard's own bytes started from the initial value given;
+ * zultra_cuda_checksum_combine folds shard checksums in order.
+ */
+int zultra_cuda_shard_prepare(zultra_cuda_ctx_t *pCtx, const void *pDevInData, int nHistorySize, size_t nInDataSize, unsigned int nMaxBlockSize,
+                              int nDoFinalize, unsigned int nFlags, unsigned int *pnChecksum, unsigned long long *pnPhaseBits8);
+int zultra_cuda_shard_emit(zultra_cuda_ctx_t *pCtx, unsigned int nInBitCount, void *pDevOutData, size_t nMaxOutDataSize, unsigned long long *pnOutBitCount);
+unsigned int zultra_cuda_checksum_combine(unsigned int nFlags, unsigned int nChecksum1, unsigned int nChecksum2, unsigned long long nLength2);
+
 /* Batch of independent streams, each equal to zultra_memory_compress(p, n, .., nFlags, nMaxBlockSize) (config 5 of
    BASELINE.json; an extension, not in the reference).  pnOutSizes[i] = (size_t)-1 on per-stream failure. */
 int zultra_cuda_memory_compress_batch(zultra_cuda_ctx_t *pCtx, const unsigned char *const *ppInData, const size_t *pnInSizes,

@@ -1,7 +1,23 @@
 /* Host build of the pipeline (tests only): C entry points for ctypes. */
 #include "zb_engine.h"
 
+static ZbPipe g_shard_pipe;
 extern "C" {
+/* sharded operation, host build: same two calls as zultra_cuda_shard_prepare / _emit */
+int emu_shard_prepare(const uint8_t *buf /* [hist|data] */, int hist_len, long n, unsigned block_size, int finalize, unsigned long long *bits8) {
+   g_shard_pipe.st = 0;
+   ZbStreamIn s = {0, (size_t)n, 0, (uint32_t)hist_len, finalize, 0, 0};
+   std::vector<uint8_t> o; std::vector<ZbStreamRes> r;
+   ZbRunOpts opt; opt.dev_in = buf; opt.phase = 1;
+   if (zb_run_batch(g_shard_pipe, &s, 1, block_size, o, r, opt)) return -1;
+   memcpy(bits8, opt.phase_bits, sizeof(opt.phase_bits));
+   return 0;
+}
+long emu_shard_emit(int in_bits, uint8_t *out, long cap, unsigned long long *bits) {
+   if (zb_finish_shard(g_shard_pipe, (uint32_t)in_bits, out, (size_t)cap, bits)) return -1;
+   return (long)((*bits + 7) / 8);
+}
+
 /* single stream, one call; returns bytes written (ceil(bits/8)), *bits = total bits */
 long emu_compress(const uint8_t *data, long n, const uint8_t *hist, int hist_len, unsigned block_size, int finalize, int in_bits,
                   uint8_t *out, long out_cap, unsigned long long *bits, unsigned tile_main,

@@ -87,3 +87,19 @@ class Emu:
             k = d["nsub"].value
             d["nsub"] = k; d["sub"] = d["sub"][:k]; d["ll"] = d["ll"][:k]; d["ol"] = d["ol"][:k]
         return out[:n].tobytes(), bits.value, d
+
+    def shard_prepare(self, buf, hist, n, block=1 << 20, finalize=0):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self._keep = buf
+        bits = (C.c_ulonglong * 8)()
+        rc = self.lib.emu_shard_prepare(_p(buf), hist, C.c_long(n), C.c_uint(block), finalize, bits)
+        assert rc == 0
+        return [int(b) for b in bits]
+
+    def shard_emit(self, in_bits, cap):
+        out = np.zeros(cap, dtype=np.uint8)
+        bits = C.c_ulonglong(0)
+        self.lib.emu_shard_emit.restype = C.c_long
+        n = self.lib.emu_shard_emit(in_bits, _p(out), C.c_long(cap), C.byref(bits))
+        assert n >= 0
+        return out[:n].tobytes(), bits.value

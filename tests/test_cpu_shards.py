@@ -1,0 +1,72 @@
+"""world_size-2 gloo test of the multi-GPU host logic (block-range shards, 8-phase maps, bit-offset stitching) with the
+host-emulated pipeline standing in for the GPUs; the stitched stream must equal the reference's one-shot stream."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def _worker(rank, world, port, block, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import refharness
+    from zultra_b200 import shard, synth
+    data = np.concatenate([synth.mozilla(150000, seed=51), np.random.default_rng(5).integers(0, 256, size=70000).astype(np.uint8), synth.enwik(130000, seed=52)])
+    emu = refharness.Emu()
+    lo, hi = shard.plan_shards(len(data), block, world)[rank]
+    hist = min(lo, 32768)
+    maps = emu.shard_prepare(data[lo - hist:hi], hist, hi - lo, block=block, finalize=1 if hi >= len(data) else 0) if hi > lo else list(range(8))
+    mine = torch.tensor(maps, dtype=torch.int64)
+    allm = [torch.zeros(8, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allm, mine)
+    offs, nbits, total = shard.compose([m.tolist() for m in allm])
+    buf, bits = emu.shard_emit(offs[rank] & 7, (hi - lo) + 70000) if hi > lo else (b"", offs[rank] & 7)
+    assert bits - (offs[rank] & 7) == nbits[rank]
+    pad = torch.zeros(len(data) + 70000, dtype=torch.uint8)
+    pad[: len(buf)] = torch.from_numpy(np.frombuffer(buf, dtype=np.uint8).copy())
+    gl = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, gl, dst=0)
+    if rank == 0:
+        stream = shard.merge([g.numpy().tobytes() for g in gl], offs, nbits, total)
+        ref = refharness.Ref().compress(data, flags=0, block=block) if os.path.exists(refharness.REF_SO) else None
+        import oracle_py
+        q.put((stream == oracle_py.compress(data, 0, block), ref is None or stream == ref))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("block", [32768, 65536])
+def test_two_rank_sharding_stitches_to_the_reference_stream(block):
+    import refharness
+    if not os.path.exists(refharness.EMU_SO):
+        import subprocess
+        subprocess.check_call(["make", "-C", ROOT, "emu"])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 300) + (1 if block == 65536 else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, block, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    ok_oracle, ok_ref = q.get(timeout=5)
+    assert ok_oracle and ok_ref
+
+
+def test_compose_and_plan():
+    from zultra_b200 import shard
+    assert shard.plan_shards(10 * 1048576 + 5, 1048576, 4) == [(0, 3145728), (3145728, 6291456), (6291456, 9437184), (9437184, 10485765)]
+    assert shard.plan_shards(100, 1048576, 2) == [(0, 100), (100, 100)]
+    maps = [[10 + p for p in range(8)], [21 + p for p in range(8)]]
+    offs, nb, tot = shard.compose(maps)
+    assert offs == [0, 10] and nb == [10, 21] and tot == 31

@@ -56,6 +56,10 @@ def load():
                                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.zultra_cuda_compress_blocks_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_int, C.c_uint, C.c_void_p,
                                                          C.c_void_p, C.c_size_t, C.c_void_p]
+        L.zultra_cuda_shard_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_uint, C.c_int, C.c_uint, C.c_void_p, C.c_void_p]
+        L.zultra_cuda_shard_emit.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.zultra_cuda_checksum_combine.restype = C.c_uint
+        L.zultra_cuda_checksum_combine.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_ulonglong]
         L.zultra_cuda_memory_compress_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_uint]
         L.zultra_cuda_window_sa_lcp.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.zultra_cuda_window_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint]
@@ -160,6 +164,22 @@ class CudaCtx:
         if rc != 0:
             raise RuntimeError("zultra_cuda_compress_blocks_device failed: %d" % rc)
         return bits.value, ck.value
+
+    def shard_prepare(self, dev_in_ptr, hist, n, block=0, finalize=0, flags=0):
+        """Phase-independent part of a shard; returns (bits for entering phases 0..7, checksum of the shard bytes)."""
+        bits = (C.c_ulonglong * 8)()
+        ck = C.c_uint(1 if flags == 1 else 0)
+        rc = self.L.zultra_cuda_shard_prepare(self.p, dev_in_ptr, hist, n, block, finalize, flags, C.byref(ck), bits)
+        if rc != 0:
+            raise RuntimeError("zultra_cuda_shard_prepare failed: %d" % rc)
+        return [int(b) for b in bits], ck.value
+
+    def shard_emit(self, in_bits, dev_out_ptr, out_cap):
+        bits = C.c_ulonglong(0)
+        rc = self.L.zultra_cuda_shard_emit(self.p, in_bits, dev_out_ptr, out_cap, C.byref(bits))
+        if rc != 0:
+            raise RuntimeError("zultra_cuda_shard_emit failed: %d" % rc)
+        return bits.value
 
     def window_sa_lcp(self, win):
         w = _u8(win)

@@ -122,6 +122,47 @@ int zultra_cuda_compress_blocks(zultra_cuda_ctx_t *c, const unsigned char *hist,
    return ctx_leave(c, rc);
 }
 
+int zultra_cuda_shard_prepare(zultra_cuda_ctx_t *c, const void *dev_in, int hist_size, size_t n, unsigned int block, int finalize, unsigned int flags,
+                              unsigned int *checksum, unsigned long long *phase_bits8) {
+   int rc = ctx_enter(c);
+   if (rc) return rc;
+   if (!dev_in || !phase_bits8 || hist_size < 0 || hist_size > ZB_HISTORY) return ZULTRA_CUDA_ERR_ARG;
+   ZbStreamIn s = {0, n, 0, (uint32_t)hist_size, finalize, 0, checksum ? *checksum : 0};
+   ZbRunOpts o;
+   o.dev_in = (const uint8_t *)dev_in; o.phase = 1;
+   o.checksum_kind = (flags & 2) ? 2 : ((flags & 1) ? 1 : 0);
+   std::vector<ZbStreamRes> res;
+   rc = run_one(c, s, clamp_block(block), o, res);
+   if (rc == 0) { memcpy(phase_bits8, o.phase_bits, sizeof(o.phase_bits)); if (checksum) *checksum = res[0].checksum; }
+   return ctx_leave(c, rc ? ZULTRA_CUDA_ERR_CUDA : 0);
+}
+
+int zultra_cuda_shard_emit(zultra_cuda_ctx_t *c, unsigned int in_bits, void *dev_out, size_t out_cap, unsigned long long *out_bits) {
+   int rc = ctx_enter(c);
+   if (rc) return rc;
+   if (!dev_out || !out_bits || in_bits > 7) return ZULTRA_CUDA_ERR_ARG;
+   long long l0 = g_zb_launches;
+   rc = zb_finish_shard(c->pipe, in_bits, (uint8_t *)dev_out, out_cap, out_bits);
+   c->counters[4] += g_zb_launches - l0;
+   return ctx_leave(c, rc == -2 ? ZULTRA_CUDA_ERR_DST : (rc ? ZULTRA_CUDA_ERR_CUDA : 0));
+}
+
+unsigned int zultra_cuda_checksum_combine(unsigned int flags, unsigned int ck1, unsigned int ck2, unsigned long long len2) {
+   if (flags & 2) return zb_crc32_combine(ck1, ck2, len2);
+   if (flags & 1) {   /* adler32 of A||B from adler(A), adler(B) (B started from 1), len(B) */
+      const unsigned long long BASE = 65521;
+      unsigned long long rem = len2 % BASE, sum1 = ck1 & 0xffff, sum2 = (rem * sum1) % BASE;
+      sum1 += (ck2 & 0xffff) + BASE - 1;
+      sum2 += ((ck1 >> 16) & 0xffff) + ((ck2 >> 16) & 0xffff) + BASE - rem;
+      if (sum1 >= BASE) sum1 -= BASE;
+      if (sum1 >= BASE) sum1 -= BASE;
+      if (sum2 >= (BASE << 1)) sum2 -= (BASE << 1);
+      if (sum2 >= BASE) sum2 -= BASE;
+      return (unsigned int)(sum1 | (sum2 << 16));
+   }
+   return 0;
+}
+
 int zultra_cuda_compress_blocks_device(zultra_cuda_ctx_t *c, const void *dev_in, size_t n, unsigned int block, int finalize,
                                        unsigned int flags, unsigned int *checksum, void *dev_out, size_t out_cap, unsigned long long *out_bits) {
    int rc = ctx_enter(c);

@@ -481,7 +481,8 @@ ZB_HD int zb_mf_walk(uint32_t *iv, uint32_t *pd, uint32_t i, zb_match_t *out) {
  * (SURVEY 8(a)-M1).  The reference stops storing after 8 entries (matchfinder.c:217); nothing nearer than offset 1 exists.
  */
 #define ZB_CHAIN_LO 3      /* levels ZB_CHAIN_LO .. ZB_CHAIN_HI-1 come from the nearest-previous tables (zb_mf_chain_*) */
-#define ZB_CHAIN_HI 6      /* the suffix-array scan only covers LCP levels >= ZB_CHAIN_HI */
+#define ZB_CHAIN_HI 3      /* the suffix-array scan only covers LCP levels >= ZB_CHAIN_HI (3 = chain tables off: the
+                              unit-level table kernel is DRAM-random-access bound and costs more than it saves) */
 #define ZB_NCHAIN (ZB_CHAIN_HI - ZB_CHAIN_LO)
 
 /* chain[q] = offset from i to the nearest earlier position sharing >= ZB_CHAIN_LO+q bytes (0 = none within 32768) */
@@ -518,7 +519,7 @@ ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, const uint
    }
    /* levels below ZB_CHAIN_HI: the nearest earlier occurrence per level is known; it is new iff nearer than best */
    for (int q = ZB_NCHAIN - 1; q >= 0 && nm < ZB_NMATCH; q--) {
-      const uint32_t off = chain[q];
+      const uint32_t off = chain ? chain[q] : 0u;
       if (off && (int)(i - off) > best) {
          best = (int)(i - off);
          out[nm].length = (uint16_t)(ZB_CHAIN_LO + q); out[nm].offset = (uint16_t)off; nm++;

@@ -24,7 +24,9 @@ struct ZbDump {   /* optional stage dumps for tests (host copies) */
 struct ZbRunOpts {
    uint32_t tile_main = 0;
    int checksum_kind = 0;          /* 0 none, 1 Adler-32, 2 CRC-32 (frame.c:473) */
-   const uint8_t *dev_in = 0;      /* single stream whose data is already in device memory (hist_len must be 0) */
+   const uint8_t *dev_in = 0;      /* single stream already in device memory: [hist_len history bytes | data] */
+   int phase = 3;                  /* 1 = stop after the phase-independent part (shards), 2 = only finish, 3 = both */
+   unsigned long long phase_bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
    uint8_t *dev_out = 0; size_t dev_out_cap = 0;   /* leave the bitstream of stream 0 in device memory instead of copying back */
    ZbDump *dump = 0;
    int stop_after = 99;            /* 1 = SA, 2 = match (stage dumps) */
@@ -102,7 +104,14 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
       zb_sync(p.st); o.ms[3] = tm.lap();
       p.stage_parse();
       zb_sync(p.st); o.ms[4] = tm.lap();
-      p.stage_emit(so);
+      p.stage_emit_prepare();
+      if (o.phase == 1) {   /* shard: report the size for every entering phase and wait for zb_finish_shard */
+         if (o.checksum_kind) { std::vector<uint32_t> sums; p.stage_checksum(o.checksum_kind, ck_off, ck_len, sums, s[0].checksum); res[0].checksum = sums[0]; }
+         p.phase_map(0, (uint32_t)wins.size(), o.phase_bits);
+         zb_sync(p.st); o.ms[5] = tm.lap(); o.ms[7] = tot.lap();
+         return 0;
+      }
+      p.stage_emit_finish(so);
       if (o.checksum_kind) {
          std::vector<uint32_t> sums;
          if (ns == 1) { p.stage_checksum(o.checksum_kind, ck_off, ck_len, sums, s[0].checksum); res[0].checksum = sums[0]; }
@@ -149,6 +158,19 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
       }
       zb_sync(p.st);
    }
+   return 0;
+}
+/* second half of a sharded call: the entering bit phase is now known */
+static inline int zb_finish_shard(ZbPipe &p, uint32_t in_bits, uint8_t *dev_out, size_t dev_out_cap, unsigned long long *total_bits) {
+   std::vector<ZbStreamOut> so(1);
+   memset(&so[0], 0, sizeof(ZbStreamOut));
+   so[0].first_win = 0; so[0].nwin = (uint32_t)p.nwin; so[0].in_bits = in_bits;
+   p.stage_emit_finish(so);
+   const size_t nb = (size_t)((p.h_sout[0].total_bits + 7) / 8);
+   if (nb > dev_out_cap) return -2;
+   zb_d2d(p.st, dev_out, p.out.p + p.h_sout[0].out_word_off, nb);
+   zb_sync(p.st);
+   *total_bits = p.h_sout[0].total_bits;
    return 0;
 }
 #endif

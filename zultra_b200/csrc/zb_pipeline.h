@@ -136,7 +136,10 @@ struct ZbPipe {
    void stage_greedy();
    void stage_split();
    void stage_parse();
-   void stage_emit(const std::vector<ZbStreamOut> &streams);
+   void stage_emit(const std::vector<ZbStreamOut> &streams) { stage_emit_prepare(); stage_emit_finish(streams); }
+   void stage_emit_prepare();                                   /* path, token bits, sub-block sizes: independent of the bit phase */
+   void stage_emit_finish(const std::vector<ZbStreamOut> &streams);   /* stitch scan for the entering phase, then emission */
+   void phase_map(uint32_t first_win, uint32_t nwin, unsigned long long bits_out[8]);   /* total bits for each entering phase 0..7 */
    /* checksum partials of byte ranges of the device input: kind 1 = Adler-32, 2 = CRC-32 */
    ZbBuf<uint32_t> ck_tab, ck_part; ZbBuf<uint64_t> ck_rng; bool ck_tab_ready = false;
    void stage_checksum(int kind, const std::vector<uint64_t> &range_off, const std::vector<uint64_t> &range_len, std::vector<uint32_t> &sums, uint32_t init_first);
@@ -269,9 +272,10 @@ inline void ZbPipe::stage_sa() {
 __global__ void __launch_bounds__(128) zb_mf_chain_k(const ZbTileDesc *units, int nunit, const uint32_t *unit_words, const uint32_t *unit_cnt,
                                                      uint16_t *gidpos_all, uint32_t *last_all, uint16_t *chain, const uint32_t *wbs, uint32_t P) {
    const int wid = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5);
+   const int nch = ZB_NCHAIN > 0 ? ZB_NCHAIN : 1;
    if (wid >= nunit * ZB_NCHAIN) return;
    const int lane = threadIdx.x & 31;
-   const int u = wid / ZB_NCHAIN, q = wid % ZB_NCHAIN;
+   const int u = wid / nch, q = wid % nch;
    const uint32_t level = ZB_CHAIN_LO + q;
    const ZbTileDesc t = units[u];
    const uint32_t *words = unit_words + (size_t)u * (2 * ZB_MAX_OFFSET);
@@ -444,20 +448,15 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    unit_words.need((size_t)nunit * (2 * ZB_MAX_OFFSET)); unit_cnt.need(nunit);
    zb_tile_filter(st, sa_lcp.p, 0, units.p, nunit, 0, unit_words.p, 2 * ZB_MAX_OFFSET, unit_cnt.p);
    /* nearest earlier occurrence for the low LCP levels, per unit */
-   chain.need((size_t)ZB_NCHAIN * P);
-   {
+   chain.need((size_t)ZB_NCHAIN * P + 16);
+   if (ZB_NCHAIN > 0) {
       const ZbTileDesc *ud = units.p; const uint32_t *uw = unit_words.p, *uc = unit_cnt.p; uint16_t *ch = chain.p; const uint32_t *wbs0 = wbase.p; const uint32_t PP = P;
       const int cwave = 4096;   /* (unit, level) tasks per launch: bounds the scratch */
       chain_gid.need((size_t)std::min(nunit * ZB_NCHAIN, cwave) * (2 * ZB_MAX_OFFSET)); chain_last.need((size_t)std::min(nunit * ZB_NCHAIN, cwave) * (2 * ZB_MAX_OFFSET));
       uint16_t *cg = chain_gid.p; uint32_t *cl = chain_last.p;
 #ifndef ZB_EMU
-      for (int f = 0; f < nunit * ZB_NCHAIN; f += cwave) {
-         /* tasks are (unit, level) pairs in order; a wave must start on a unit boundary */
-         const int u0 = f / ZB_NCHAIN, u1 = std::min(nunit, (f + cwave) / ZB_NCHAIN);
-         (void)u0; (void)u1;
-      }
       {
-         const int per = cwave / ZB_NCHAIN;
+         const int per = cwave / (ZB_NCHAIN > 0 ? ZB_NCHAIN : 1);
          for (int u0 = 0; u0 < nunit; u0 += per) {
             const int nu = std::min(per, nunit - u0);
             if (g_zb_prof_on) { zb_tag("mf_chain"); zb_prof_begin(0, st); }
@@ -515,7 +514,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
          const uint32_t *words = ivb + (size_t)k * stride; const uint32_t *rom = pdb + (size_t)k * tile_main;
          const uint32_t nlook = t.m0 - t.lo, p = t.m0 + m, gbase = wbs[t.win];
          zb_match_t o[ZB_NMATCH];
-         uint16_t chv[ZB_NCHAIN];
+         uint16_t chv[ZB_NCHAIN + 1];
          for (int q = 0; q < ZB_NCHAIN; q++) chv[q] = chq[(size_t)q * PPe + gbase + p];
          const int nm = zb_mf_scan(words, (int)tc[k], (int)rom[m], nlook + m, chv, o);
          const uint32_t maxlen = t.wlen - p;
@@ -1248,7 +1247,7 @@ inline void ZbPipe::stage_parse() {
  * writer's arithmetic of libzultra.c:327-398 (entering bit phase, stored-block fallback on BYTE deltas), then
  * every chunk writes its tokens at its absolute bit offset.
  */
-inline void ZbPipe::stage_emit(const std::vector<ZbStreamOut> &streams) {
+inline void ZbPipe::stage_emit_prepare() {
    const int ns = nsub;
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
@@ -1302,6 +1301,38 @@ inline void ZbPipe::stage_emit(const std::vector<ZbStreamOut> &streams) {
       s.body_bits = s.hdr_bits < 0 ? -1 : (int32_t)(s.hdr_bits + acc + tb[x].llen[ZB_EOB]);
       sb[x] = s;
    });
+}
+
+/* The stitch arithmetic of libzultra.c:327-398 on the host, for all 8 entering bit phases (multi-GPU: a shard learns its
+   phase from the shards before it; everything up to here is phase independent). */
+inline void ZbPipe::phase_map(uint32_t first_win, uint32_t nw, unsigned long long bits_out[8]) {
+   std::vector<ZbSub> hs(nsub);
+   zb_d2h(st, hs.data(), sub.p, sizeof(ZbSub) * nsub); zb_sync(st);
+   for (int ph = 0; ph < 8; ph++) {
+      unsigned long long bit = (unsigned long long)ph;
+      for (int x = 0; x < nsub; x++) {
+         const ZbSub &s = hs[x];
+         if (s.win < first_win || s.win >= first_win + nw) continue;
+         const uint32_t size = s.pe - s.ps;
+         bool stored = s.body_bits < 0;
+         if (!stored) { const unsigned long long a = (bit + 3) >> 3, b = (bit + 3 + (unsigned long long)s.body_bits) >> 3; if (b - a > size) stored = true; }
+         if (!stored) bit += 3 + (unsigned long long)s.body_bits;
+         else { uint32_t rem = size; while (rem) { uint32_t n = rem > 65535 ? 65535 : rem; bit += 3; bit = (bit + 7) & ~7ull; bit += 32 + 8ull * n; rem -= n; } }
+      }
+      bits_out[ph] = bit;
+   }
+}
+
+inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams) {
+   const int ns = nsub;
+   ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
+   const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
+   zb_match_t *bm = best.p; uint32_t *pen = pentry.p, *pb = pbits.p, *pcs = pchunk_sub.p;
+   long npch = 0;
+   {
+      uint32_t v; zb_d2h(st, &v, cn + 5, 4); zb_sync(st); npch = v;
+   }
+   (void)tb; (void)T; (void)bm; (void)pen; (void)pb; (void)pcs; (void)wbs;
    /* E3: stitch scan, one task per stream */
    const int nstr = (int)streams.size();
    h_sout = streams; nstream = nstr;
