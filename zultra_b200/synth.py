@@ -158,7 +158,10 @@ def mozilla(n, seed=SEED_MOZ):
             b = rng.integers(0, 256, size=seg).astype(np.uint8)
         out.append(b[:seg])
         have += seg
-    return np.concatenate(out)[:n].copy()
+    res = np.concatenate(out)[:n]
+    if len(res) < n:   # some segment kinds come out a little short of their nominal size: top up with further segments
+        res = np.concatenate([res, mozilla(n - len(res), seed=seed + 7919)])
+    return res.copy()
 
 
 def js48k(n=48944, seed=SEED_JS):
