@@ -266,7 +266,7 @@ def main():
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s"},
                "stages_ms": {k: round(v, 3) for k, v in stages.items()},
                "kernels_ms_per_step": {r[0]: round(r[1] / args.steps, 3) for r in ktab[:12]},
-               "compressed_bytes": runner.last_out_bytes, "stream_sha256": stream_sha, "verified": "inflate(stream) == input" + (" and == 1-GPU stream" if world > 1 else "")}
+               "counters": ctx.counters(), "compressed_bytes": runner.last_out_bytes, "stream_sha256": stream_sha, "verified": "inflate(stream) == input" + (" and == 1-GPU stream" if world > 1 else "")}
         if not args.no_cpu_baseline and world == 1:
             v, dt, sample = cpu_reference_timing(data, w["flags"], 1, 24 << 20)
             if v is not None:

@@ -34,9 +34,7 @@ static void fill_counters(zultra_cuda_ctx_t *c, long long launches0) {
    ZbPipe &p = c->pipe;
    c->counters[0] = p.nwin; c->counters[1] = p.nsub; c->counters[2] = p.stat_sa_rounds;
    c->counters[4] = g_zb_launches - launches0;
-   uint32_t redo = 0;
-   if (p.counters.p) { cudaMemcpy(&redo, p.counters.p + 6, 4, cudaMemcpyDeviceToHost); }
-   c->counters[3] = redo;
+   c->counters[3] = p.stat_redo; c->counters[7] = p.stat_tiles;
 }
 
 extern "C" {
@@ -87,6 +85,7 @@ static int run_one(zultra_cuda_ctx_t *c, const ZbStreamIn &s, unsigned block, Zb
    cudaEventCreate(&e0); cudaEventCreate(&e1);
    cudaEventRecord(e0, c->pipe.st);
    if (!o.tile_main) o.tile_main = c->tile;
+   c->pipe.stat_redo = 0;
    int rc = zb_run_batch(c->pipe, &s, 1, block, c->out, res, o);
    cudaEventRecord(e1, c->pipe.st);
    cudaEventSynchronize(e1);

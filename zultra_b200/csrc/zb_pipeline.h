@@ -117,7 +117,7 @@ struct ZbPipe {
    ZbBuf<uint32_t> wsplit; ZbBuf<uint32_t> wnsplit;
    /* sub-blocks */
    ZbBuf<ZbSub> sub; ZbBuf<ZbSubTabs> tabs; ZbBuf<uint32_t> dchunk_sub, pchunk_sub;
-   ZbBuf<zb_match_t> best; ZbBuf<int16_t> sig_true, sig_warm; ZbBuf<uint8_t> dok;
+   ZbBuf<zb_match_t> best; ZbBuf<int16_t> sig_true, sig_warm, sig_new; ZbBuf<uint8_t> dok;
    ZbBuf<uint32_t> pentry, pbits;
    /* output */
    ZbBuf<uint32_t> out; ZbBuf<ZbStreamOut> sout;
@@ -947,7 +947,7 @@ inline void ZbPipe::stage_parse() {
    zb_d2h(st, hc, cn + 4, 8); zb_sync(st);
    const long ndch = hc[0], npch = hc[1];
    dchunk_sub.need(ndch + 1); pchunk_sub.need(npch + 1); best.need(P);
-   sig_true.need((size_t)(ndch + 1) * 260); sig_warm.need((size_t)(ndch + 1) * 260); dok.need(ndch + 1);
+   sig_true.need((size_t)(ndch + 1) * 260); sig_warm.need((size_t)(ndch + 1) * 260); sig_new.need((size_t)(ndch + 1) * 260); dok.need(ndch + 1);
    pentry.need(npch + 1); pbits.need(npch + 1);
    uint32_t *dcs = dchunk_sub.p, *pcs = pchunk_sub.p;
    zb_launch(st, ns, ZB_LAMBDA(long x) {
@@ -956,7 +956,7 @@ inline void ZbPipe::stage_parse() {
    });
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
    const zb_match_t *mt = match.p; zb_match_t *bm = best.p;
-   int16_t *sgt = sig_true.p, *sgw = sig_warm.p; uint8_t *ok = dok.p;
+   int16_t *sgt = sig_true.p, *sgw = sig_warm.p, *sgn = sig_new.p; uint8_t *ok = dok.p;
    uint16_t *ex = exitoff.p; uint32_t *pen = pentry.p;
 
    for (int pass = 0; pass < 4; pass++) {
@@ -1008,63 +1008,61 @@ inline void ZbPipe::stage_parse() {
          }
       }, 64);
 #endif
-      /* D3: does each chunk's warm-up agree with its right neighbour's true costs? */
-      zb_launch(st, ndch, ZB_LAMBDA(long c) {
-         const ZbSub s = sb[dcs[c]];
-         const uint32_t k = (uint32_t)c - s.dchunk_base;
-         uint8_t good = 1;
-         if (k + 1 < s.ndchunk) {
-            const int hi = (int)(s.ps + (k + 1) * CD), end = (int)s.pe;
-            int from = hi + WU; if (from > end) from = end;
-            const int16_t *a = sgw + (size_t)c * 260, *b = sgt + (size_t)(c + 1) * 260;
-            int lim = from - hi; if (lim > ZB_MAX_MATCH) lim = ZB_MAX_MATCH;
-            /* the warm-up must have covered the whole horizon, else it started from the true end state anyway */
-            if (from < end && from - hi < ZB_MAX_MATCH) good = 0;
-            for (int q = 0; q <= lim && good; q++) if (a[q] != b[q]) good = 0;
-         }
-         ok[c] = good;
-      });
-      /* D4: repair, right to left: a chunk whose warm-up disagreed is recomputed from its neighbour's true costs */
-      zb_tag("parse_repair");
-      zb_launch(st, ns, ZB_LAMBDA(long x) {
-         const ZbSub s = sb[x];
-         if (pass > 0 && !s.is_dyn) return;
-         if (s.ndchunk < 2) return;
-         const uint32_t gb = wbs[s.win];
-         const uint8_t *t = T + wd[s.win].in_off;
-         const int end = (int)s.pe;
-         const ZbCostTab &ct = tb[x].cost;
-         for (int k = (int)s.ndchunk - 2; k >= 0; k--) {
-            const size_t c = s.dchunk_base + k;
-            const int lo = (int)(s.ps + k * CD), hi = lo + CD;
-            bool good = ok[c];
-            if (good) continue;
-            /* re-check against the (possibly repaired) neighbour before redoing */
-            {
-               int from = hi + WU; if (from > end) from = end;
-               int lim = from - hi; if (lim > ZB_MAX_MATCH) lim = ZB_MAX_MATCH;
-               good = !(from < end && from - hi < ZB_MAX_MATCH);
-               const int16_t *a = sgw + c * 260, *b = sgt + (c + 1) * 260;
-               for (int q = 0; q <= lim && good; q++) if (a[q] != b[q]) good = false;
+      /* D3/D4: verify and repair.  A chunk is right iff the relative costs its warm-up saw over the 259-position horizon
+         at its end equal what its right neighbour really computed there, and the neighbour is right.  Rounds: every chunk
+         is compared with its neighbour's current costs; every chunk that disagrees is recomputed IN PARALLEL from the
+         neighbour's costs; repeat until nothing disagrees.  By induction from the (exact) last chunk of each sub-block the
+         fixed point is the sequential result; the number of rounds is the longest run of consecutive wrong chunks
+         (non-resynchronising data such as long byte runs), independent chains repair concurrently. */
+      for (int round = 0;; round++) {
+         zb_memset(st, cn + 7, 0, 4);
+         zb_tag("parse_verify");
+         zb_launch(st, ndch, ZB_LAMBDA(long c) {
+            const ZbSub s = sb[dcs[c]];
+            uint8_t good = 1;
+            const uint32_t k = (uint32_t)c - s.dchunk_base;
+            if (!(pass > 0 && !s.is_dyn) && k + 1 < s.ndchunk) {
+               const int16_t *a = sgw + (size_t)c * 260, *b = sgt + (size_t)(c + 1) * 260;
+               for (int q = 0; q <= ZB_MAX_MATCH && good; q++) if (a[q] != b[q]) good = 0;
             }
-            if (good) { ok[c] = 1; continue; }
+            ok[c] = good;
+            if (!good) zb_atomic_add((int *)cn + 7, 1);
+         });
+         uint32_t nbad = 0;
+         zb_d2h(st, &nbad, cn + 7, 4); zb_sync(st);
+         if (!nbad) break;
+         stat_redo += (int)nbad;
+         zb_tag("parse_repair");
+         zb_launch(st, ndch, ZB_LAMBDA(long c) {
+            if (ok[c]) return;
+            const uint32_t x = dcs[c];
+            const ZbSub s = sb[x];
+            const uint32_t k = (uint32_t)c - s.dchunk_base;
+            const uint32_t gb = wbs[s.win];
+            const uint8_t *t = T + wd[s.win].in_off;
+            const int end = (int)s.pe;
+            const ZbCostTab &ct = tb[x].cost;
+            const int lo = (int)(s.ps + k * CD), hi = lo + CD;
             ZbRingLocal ring;
-            const int16_t *b = sgt + (c + 1) * 260;
+            const int16_t *b = sgt + (size_t)(c + 1) * 260;
+            int16_t *sw = sgw + (size_t)c * 260;
             int slot = 0;
-            for (int q = 0; q <= ZB_MAX_MATCH; q++) { int sl = slot - q; if (sl < 0) sl += ZB_RING; ring.v[sl] = (uint16_t)b[q]; }
+            for (int q = 0; q <= ZB_MAX_MATCH; q++) { int sl = slot - q; if (sl < 0) sl += ZB_RING; ring.v[sl] = (uint16_t)b[q]; sw[q] = b[q]; }
             zb_parse_range(t, mt + ((size_t)gb << 3), ct, lo, hi, end, hi, bm + gb, ring, slot);
-            int16_t *sg = sgt + c * 260;
+            /* the new costs at this chunk's start go to a staging row: neighbours still read the old row this round */
+            int16_t *sg = sgn + (size_t)c * 260;
             const uint16_t b0 = ring.get(slot);
             for (int q = 0; q <= ZB_MAX_MATCH; q++) {
                int sl = slot - q; if (sl < 0) sl += ZB_RING;
                sg[q] = (lo + q <= end) ? (int16_t)(uint16_t)(ring.get(sl) - b0) : (int16_t)0;
             }
-            ok[c] = 2;
-            zb_atomic_add((int *)cn + 6, 1);
-            /* the left neighbour was judged against the old values: force its re-check */
-            if (k > 0) ok[c - 1] = 0;
-         }
-      });
+         }, 32);
+         zb_launch(st, ndch, ZB_LAMBDA(long c) {
+            if (ok[c]) return;
+            int16_t *sg = sgt + (size_t)c * 260; const int16_t *sn = sgn + (size_t)c * 260;
+            for (int q = 0; q <= ZB_MAX_MATCH; q++) sg[q] = sn[q];
+         });
+      }
       /* D5: chosen path: exit offsets per path-chunk, serial hop per sub-block */
       zb_launch(st, npch, ZB_LAMBDA(long c) {
          const ZbSub s = sb[pcs[c]];
@@ -1449,27 +1447,23 @@ inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams) {
          (void)bytes;
       }
    });
-   /* E6: stored payload bytes, one task per 256 bytes of a stored sub-block */
-   {
-      /* count tasks on the host side from nothing: launch over all positions/256 and filter by sub-block (stored is rare) */
-      zb_launch(st, ns, ZB_LAMBDA(long x) {
-         const ZbSub s = sb[x];
-         if (!s.stored) return;
-         uint8_t *bytes = (uint8_t *)(ow + so[wd[s.win].stream].out_word_off);
-         const uint8_t *t = T + wd[s.win].in_off;
-         uint64_t bit = s.bit_off;
-         uint32_t rem = s.pe - s.ps, src = s.ps;
-         while (rem) {
-            const uint32_t n = rem > 65535 ? 65535 : rem;
-            bit += 3; bit = (bit + 7) & ~7ull; bit += 32;
-            /* payload bytes are byte aligned; first/last bytes may share a 32-bit word with bit-packed neighbours,
-               which write with atomicOr into zeroed memory - byte stores to distinct bytes do not conflict */
-            uint8_t *d = bytes + (bit >> 3);
-            for (uint32_t i = 0; i < n; i++) d[i] = t[src + i];
-            bit += 8ull * n; src += n; rem -= n;
-         }
-      });
-   }
+   /* E6: stored payload bytes (libzultra.c:385-390), one task per path chunk of a stored sub-block.  Payload of stored
+      chunk j (65535 bytes each) starts 5 bytes later than the previous one; the first starts after the padded header. */
+   zb_tag("emit_stored");
+   zb_launch(st, npch, ZB_LAMBDA(long c) {
+      const uint32_t x = pcs[c];
+      const ZbSub s = sb[x];
+      if (!s.stored) return;
+      const uint32_t k = (uint32_t)c - s.pchunk_base;
+      const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      uint8_t *bytes = (uint8_t *)(ow + so[wd[s.win].stream].out_word_off);
+      const uint8_t *t = T + wd[s.win].in_off;
+      const uint64_t first_payload = ((s.bit_off + 3 + 7) >> 3) + 4;
+      for (uint32_t p = lo; p < hi; p++) {
+         const uint32_t q = p - s.ps;
+         bytes[first_payload + q + 5ull * (q / 65535u)] = t[p];
+      }
+   });
 }
 
 inline void ZbPipe::release_all() {
@@ -1479,7 +1473,7 @@ inline void ZbPipe::release_all() {
    gtokcnt.release(); gtokbase.release(); tokpos.release(); wtok.release(); wtokbase.release(); wintbase.release(); ph.release();
    gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
    chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();
-   best.release(); sig_true.release(); sig_warm.release(); dok.release(); pentry.release(); pbits.release(); out.release(); sout.release();
+   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); pentry.release(); pbits.release(); out.release(); sout.release();
 }
 
 
