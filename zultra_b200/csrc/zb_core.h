@@ -479,19 +479,33 @@ ZB_HD int zb_mf_walk(uint32_t *iv, uint32_t *pd, uint32_t i, zb_match_t *out) {
  * the next entry of the reference's list: exactly the positions that zultra_find_matches_at (matchfinder.c:171-234)
  * reports, longest first - for each length the nearest earlier occurrence, each position once, with its own length
  * (SURVEY 8(a)-M1).  The reference stops storing after 8 entries (matchfinder.c:217); nothing nearer than offset 1 exists.
+ *
+ * Rank walk + text walk.  The rank walk costs one step per member of the enclosing LCP >= 3 group, which is heavy-tailed
+ * (common trigrams, byte runs).  Every suffix the walk has seen lies outside the position interval (best, i) - otherwise
+ * it would have become `best` - so what the remaining walk could still add is exactly the Pareto frontier of the positions
+ * j in (best, i), all with lcp(i, j) <= bound = the LCP level the walk has reached.  Once that interval is short compared
+ * with the steps already spent, it is cheaper to read it directly: j = i-1 .. best+1, byte-compare up to `bound`, keep
+ * every j that is strictly longer than all nearer ones, stop as soon as one reaches `bound`.  Same list, and the cost of
+ * a position becomes O(min(group size, distance to the nearest long match)).
  */
-#define ZB_CHAIN_LO 3      /* levels ZB_CHAIN_LO .. ZB_CHAIN_HI-1 come from the nearest-previous tables (zb_mf_chain_*) */
-#define ZB_CHAIN_HI 3      /* the suffix-array scan only covers LCP levels >= ZB_CHAIN_HI (3 = chain tables off: the
-                              unit-level table kernel is DRAM-random-access bound and costs more than it saves) */
-#define ZB_NCHAIN (ZB_CHAIN_HI - ZB_CHAIN_LO)
+#ifndef ZB_TS_MIN
+#define ZB_TS_MIN 12      /* rank-walk steps before the text walk is considered */
+#define ZB_TS_MUL 6       /* switch when (i - best - 1) <= ZB_TS_MUL * steps */
+#endif
+#ifdef ZB_SCAN_STATS
+extern long g_zb_rank_steps, g_zb_text_steps, g_zb_cmp_bytes;
+#define ZB_STAT(x) (x)
+#else
+#define ZB_STAT(x) ((void)0)
+#endif
 
-/* chain[q] = offset from i to the nearest earlier position sharing >= ZB_CHAIN_LO+q bytes (0 = none within 32768) */
-ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, const uint16_t *chain, zb_match_t *out) {
+/* T[p] = byte at tile position p (readable up to the window end) */
+ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, const uint8_t *T, zb_match_t *out) {
    int L = r - 1, R = r + 1;
    uint32_t lL = r > 0 ? (words[r] >> ZB_POS_BITS) : 0u;
    uint32_t lR = R < n ? (words[R] >> ZB_POS_BITS) : 0u;
-   const int minpos = i > ZB_MAX_OFFSET ? (int)(i - ZB_MAX_OFFSET) : 0;
-   int nm = 0, best = -1;
+   int best = (i > ZB_MAX_OFFSET ? (int)(i - ZB_MAX_OFFSET) : 0) - 1;   /* p > best also enforces the 32768 limit */
+   int nm = 0, steps = 0;
    uint32_t lvl = 0;
    bool moved = false;
    for (;;) {
@@ -499,10 +513,34 @@ ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, const uint
       if (l < lvl && moved) {
          out[nm].length = (uint16_t)lvl; out[nm].offset = (uint16_t)(i - (uint32_t)best); nm++;
          moved = false;
-         if (nm == ZB_NMATCH || best == (int)i - 1) return nm;
+         if (nm == ZB_NMATCH) return nm;
       }
-      if (l < ZB_CHAIN_HI) break;
-      lvl = l;
+      if (l < ZB_MIN_MATCH) return nm;
+      if (steps >= ZB_TS_MIN && (int)i - 1 - best <= ZB_TS_MUL * steps) {
+         /* text walk over (best, i): records arrive nearest first = shortest first; tr[0] is the longest so far */
+         uint32_t tr[ZB_NMATCH]; int nt = 0; uint32_t curmax = 0;
+         const uint8_t c0 = T[i], c1 = T[i + 1], c2 = T[i + 2];
+         for (int j = (int)i - 1; j > best; j--) {
+            ZB_STAT(g_zb_text_steps++);
+            if (T[j] != c0 || T[j + 1] != c1 || T[j + 2] != c2) continue;
+            uint32_t len = ZB_MIN_MATCH;
+            while (len < l && T[j + len] == T[i + len]) len++;
+            ZB_STAT(g_zb_cmp_bytes += len);
+            if (len > curmax) {
+               for (int z = ZB_NMATCH - 1; z > 0; z--) tr[z] = tr[z - 1];
+               tr[0] = len | ((i - (uint32_t)j) << 16);
+               if (nt < ZB_NMATCH) nt++;
+               curmax = len;
+               if (len == l) break;
+            }
+         }
+         /* the pending record of the rank walk stands unless a nearer position reached the same level */
+         if (moved && !(nt && curmax == lvl)) { out[nm].length = (uint16_t)lvl; out[nm].offset = (uint16_t)(i - (uint32_t)best); nm++; }
+         for (int z = 0; z < nt && nm < ZB_NMATCH; z++) { out[nm].length = (uint16_t)(tr[z] & 0xffffu); out[nm].offset = (uint16_t)(tr[z] >> 16); nm++; }
+         return nm;
+      }
+      lvl = l; steps++;
+      ZB_STAT(g_zb_rank_steps++);
       int p;
       if (lL >= lR) {
          const uint32_t w = words[L];
@@ -515,43 +553,12 @@ ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, const uint
          R++;
          if (R < n) { const uint32_t wl = words[R] >> ZB_POS_BITS; lR = wl < lR ? wl : lR; } else lR = 0u;
       }
-      if (p < (int)i && p >= minpos && p > best) { best = p; moved = true; }
-   }
-   /* levels below ZB_CHAIN_HI: the nearest earlier occurrence per level is known; it is new iff nearer than best */
-   for (int q = ZB_NCHAIN - 1; q >= 0 && nm < ZB_NMATCH; q--) {
-      const uint32_t off = chain ? chain[q] : 0u;
-      if (off && (int)(i - off) > best) {
-         best = (int)(i - off);
-         out[nm].length = (uint16_t)(ZB_CHAIN_LO + q); out[nm].offset = (uint16_t)off; nm++;
-         if (off == 1) break;
-      }
-   }
-   return nm;
-}
-
-/*
- * Nearest earlier occurrence per position for one LCP level, over one unit (64 Ki positions: 32768 main + look-back).
- * words: the unit's suffixes in suffix-array order.  Two suffixes share >= level bytes iff no LCP below `level` lies
- * between them, so a group id is the index of the last entry whose LCP is < level.  Pass 1 gives every position its
- * group id; pass 2 walks the positions in increasing order and links each to the previous position of its group.
- * This is the sequential statement; the GPU runs the same two passes 32 positions at a time (zb_mf_chain_k).
- * out[p - nlook] (main positions only) = offset, 0 if none or farther than 32768.
- */
-ZB_HD void zb_mf_chain_unit(const uint32_t *words, int n, uint32_t level, uint32_t nlook, uint16_t *gidpos, uint32_t *last, uint16_t *out) {
-   uint32_t gid = 0;
-   for (int e = 0; e < n; e++) {
-      const uint32_t w = words[e];
-      if ((w >> ZB_POS_BITS) < level) { gid = (uint32_t)e; last[gid] = 0xffffffffu; }
-      gidpos[w & ZB_POS_MASK] = (uint16_t)gid;
-   }
-   for (uint32_t p = 0; p < (uint32_t)n; p++) {
-      const uint32_t g = gidpos[p];
-      const uint32_t prev = last[g];
-      last[g] = p;
-      if (p >= nlook) {
-         uint32_t off = prev != 0xffffffffu ? p - prev : 0u;
-         if (off > ZB_MAX_OFFSET) off = 0;
-         out[p - nlook] = (uint16_t)off;
+      if (p < (int)i && p > best) {
+         best = p; moved = true;
+         if (best == (int)i - 1) {   /* nothing nearer exists and the level of this record is fixed: done */
+            out[nm].length = (uint16_t)lvl; out[nm].offset = 1; nm++;
+            return nm;
+         }
       }
    }
 }

@@ -106,7 +106,7 @@ struct ZbPipe {
    ZbBuf<uint32_t> sa_lcp;      /* packed SA|LCP words, rank order, per window at wbase[w] */
    ZbBuf<uint32_t> counters;    /* misc device counters */
    /* match finder */
-   ZbBuf<ZbTileDesc> tiles, units; ZbBuf<uint32_t> tile_iv, tile_pd, tile_cnt, unit_words, unit_cnt, chain_last; ZbBuf<uint16_t> chain, chain_gid;
+   ZbBuf<ZbTileDesc> tiles, units; ZbBuf<uint32_t> tile_iv, tile_pd, tile_cnt, unit_words, unit_cnt;
    ZbBuf<zb_match_t> match; ZbBuf<uint16_t> glen, goff;
    /* greedy path */
    ZbBuf<uint16_t> exitoff; ZbBuf<uint32_t> gentry, gtokcnt, gtokbase, tokpos, wtok; /* wtok[w] = tokens of window w; base in wtokbase */
@@ -267,71 +267,24 @@ inline void ZbPipe::stage_sa() {
 
 /* ============================================================ match finder ============================================================ */
 #ifndef ZB_EMU
-/* One warp per (unit, level): zb_mf_chain_unit, 32 entries / 32 positions per step.  Group ids and the per-group "latest
-   position" table live in global scratch (L2); inside a step the predecessor within the warp comes from match.any. */
-__global__ void __launch_bounds__(128) zb_mf_chain_k(const ZbTileDesc *units, int nunit, const uint32_t *unit_words, const uint32_t *unit_cnt,
-                                                     uint16_t *gidpos_all, uint32_t *last_all, uint16_t *chain, const uint32_t *wbs, uint32_t P) {
-   const int wid = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5);
-   const int nch = ZB_NCHAIN > 0 ? ZB_NCHAIN : 1;
-   if (wid >= nunit * ZB_NCHAIN) return;
-   const int lane = threadIdx.x & 31;
-   const int u = wid / nch, q = wid % nch;
-   const uint32_t level = ZB_CHAIN_LO + q;
-   const ZbTileDesc t = units[u];
-   const uint32_t *words = unit_words + (size_t)u * (2 * ZB_MAX_OFFSET);
-   const uint32_t n = unit_cnt[u];
-   uint16_t *gidpos = gidpos_all + (size_t)wid * (2 * ZB_MAX_OFFSET);
-   uint32_t *last = last_all + (size_t)wid * (2 * ZB_MAX_OFFSET);
-   const uint32_t lt = (1u << lane) - 1u;
-   uint32_t carry = 0;
-   for (uint32_t r0 = 0; r0 < n; r0 += 32) {
-      const uint32_t e = r0 + lane;
-      const bool valid = e < n;
-      const uint32_t w = valid ? __ldg(words + e) : 0u;
-      const bool head = valid && (w >> ZB_POS_BITS) < level;
-      const uint32_t hm = __ballot_sync(0xffffffffu, head);
-      const uint32_t le = hm & (lt | (1u << lane));
-      const uint32_t gid = le ? r0 + (31 - __clz((int)le)) : carry;
-      if (head) last[e] = 0xffffffffu;
-      if (valid) gidpos[w & ZB_POS_MASK] = (uint16_t)gid;
-      if (hm) carry = r0 + (31 - __clz((int)hm));
-   }
-   __syncwarp();
-   const uint32_t nlook = t.m0 - t.lo;
-   uint16_t *out = chain + (size_t)q * P + wbs[t.win] + t.m0;
-   for (uint32_t p0 = 0; p0 < n; p0 += 32) {
-      const uint32_t p = p0 + lane;
-      const bool valid = p < n;
-      const uint32_t g = valid ? gidpos[p] : 0xffffffffu - lane;
-      const uint32_t peers = __match_any_sync(0xffffffffu, g);
-      const uint32_t below = peers & lt;
-      uint32_t prev = 0xffffffffu;
-      if (valid) prev = below ? p0 + (31 - __clz((int)below)) : last[g];
-      __syncwarp();
-      if (valid && (peers >> lane) == 1u) last[g] = p;   /* highest lane of the group records the latest position */
-      if (valid && p >= nlook) {
-         uint32_t off = prev != 0xffffffffu ? p - prev : 0u;
-         if (off > ZB_MAX_OFFSET) off = 0;
-         out[p - nlook] = (uint16_t)off;
-      }
-      __syncwarp();
-   }
-}
-
-/* CTA per tile: the tile's suffix list (<= 32768 + T words) and the rank of every main position live in shared memory.
-   Scan lengths are heavy-tailed, so lanes do not own fixed positions: a lane that finishes fetches the next main position
-   from a shared counter and all 32 lanes keep stepping (same arithmetic as zb_mf_scan, kept as a resumable state). */
+/* CTA per tile: the tile's suffix list (<= 32768 + T words), the rank of every main position and the tile's text live in
+   shared memory.  Walk lengths are heavy-tailed, so lanes do not own fixed positions: a lane that finishes fetches the next
+   main position from a shared counter and all 32 lanes keep stepping (same arithmetic as zb_mf_scan, kept as a resumable
+   state: rank walk, then - once the interval (best, i) is short - the text walk).  Records go straight to global memory as
+   they are found. */
 #define ZB_MF_THREADS 1024
 __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *td, int first, const uint32_t *lists, size_t stride, const uint32_t *cnts,
-                                                              zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, const uint16_t *chain, uint32_t P) {
+                                                              zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, const ZbWinDesc *wd, const uint8_t *T,
+                                                              uint32_t tile_main) {
    extern __shared__ uint32_t zb_smw[];
    __shared__ uint32_t next_m;
    const int k = blockIdx.x;
    const ZbTileDesc t = td[first + k];
    const int n = (int)cnts[k];
    const uint32_t nlook = t.m0 - t.lo, nmain = t.hi - t.m0;
-   uint32_t *words = zb_smw + 1;          /* words[-1] and words[n] are LCP-0 sentinels: no bounds tests in the scan */
+   uint32_t *words = zb_smw + 1;          /* words[-1] and words[n] are LCP-0 sentinels: no bounds tests in the walk */
    uint16_t *rom = (uint16_t *)(zb_smw + stride + 2);
+   uint8_t *txt = (uint8_t *)(rom + tile_main);
    const uint32_t *src = lists + (size_t)k * stride;
    if (threadIdx.x == 0) { next_m = 0; zb_smw[0] = 0; words[n] = 0; }
    for (int e = threadIdx.x; e < n; e += blockDim.x) {
@@ -340,12 +293,19 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
       const uint32_t p = w & ZB_POS_MASK;
       if (p >= nlook) rom[p - nlook] = (uint16_t)e;
    }
+   {
+      const uint8_t *tsrc = T + wd[t.win].in_off + t.lo;
+      uint32_t ntxt = t.hi - t.lo + ZB_MAX_MATCH;
+      if (ntxt > t.wlen - t.lo) ntxt = t.wlen - t.lo;
+      for (uint32_t e = threadIdx.x; e < ntxt; e += blockDim.x) txt[e] = tsrc[e];
+   }
    __syncthreads();
    const uint32_t gbase = wbs[t.win];
-   bool busy = false, drained = false;
-   uint32_t m = 0, lL = 0, lR = 0, lvl = 0, rec[ZB_NMATCH];
-   int i = 0, L = 0, R = 0, best = -1, nm = 0;
-   bool moved = false;
+   bool busy = false, drained = false, moved = false, text = false;
+   uint32_t m = 0, lL = 0, lR = 0, lvl = 0, first_rec = 0, maxlen = 0, k3 = 0, kj = 0, curmax = 0, tr[ZB_NMATCH];
+   int i = 0, L = 0, R = 0, best = -1, nm = 0, steps = 0, j = 0, nt = 0;
+   uint32_t *dst = 0;
+#define ZB_MF_EMIT(v_) do { uint32_t v__ = (v_); if ((v__ & 0xffffu) > maxlen) v__ = (v__ & 0xffff0000u) | maxlen; if (nm == 0) first_rec = v__; dst[nm++] = v__; } while (0)
    for (;;) {
       if (!busy && !drained) {
          m = atomicAdd(&next_m, 1u);
@@ -358,62 +318,79 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
             lL = words[r] >> ZB_POS_BITS;     /* words[0] has LCP 0 */
             lR = words[R] >> ZB_POS_BITS;     /* words[n] = 0 */
             best = (i > ZB_MAX_OFFSET ? i - ZB_MAX_OFFSET : 0) - 1;   /* p > best also enforces the 32768 limit */
-            nm = 0; lvl = 0; moved = false;
-#pragma unroll
-            for (int q = 0; q < ZB_NMATCH; q++) rec[q] = 0;
+            nm = 0; lvl = 0; moved = false; steps = 0; text = false; first_rec = 0;
+            maxlen = t.wlen - (t.m0 + m);     /* matchfinder.c:276-280 (LAST_LITERALS = 0) */
+            dst = (uint32_t *)(mt + ((size_t)(gbase + t.m0 + m) << 3));
          }
       }
       if (__all_sync(0xffffffffu, drained && !busy)) break;
-      if (busy) {
+      bool fin = false;
+      if (busy && !text) {
 #pragma unroll 1
          for (int step = 0; step < 8; step++) {
             const uint32_t l = lL > lR ? lL : lR;
-            bool fin = false;
             if (l < lvl && moved) {
-               const uint32_t v = lvl | ((uint32_t)(i - best) << 16);
-#pragma unroll
-               for (int q = 0; q < ZB_NMATCH; q++) if (q == nm) rec[q] = v;
-               nm++; moved = false;
-               if (nm == ZB_NMATCH || best == i - 1) fin = true;
+               ZB_MF_EMIT(lvl | ((uint32_t)(i - best) << 16));
+               moved = false;
+               if (nm == ZB_NMATCH) { fin = true; break; }
             }
-            if (!fin && l < ZB_CHAIN_HI) {
-               fin = true;
-               const uint32_t p = t.m0 + m;
-#pragma unroll
-               for (int q = ZB_NCHAIN - 1; q >= 0; q--) {
-                  const uint32_t off = chain[(size_t)q * P + gbase + p];
-                  if (nm < ZB_NMATCH && off && i - (int)off > best && best != i - 1) {
-                     best = i - (int)off;
-                     const uint32_t v = (uint32_t)(ZB_CHAIN_LO + q) | (off << 16);
-#pragma unroll
-                     for (int z = 0; z < ZB_NMATCH; z++) if (z == nm) rec[z] = v;
-                     nm++;
-                  }
-               }
-            }
-            if (fin) {
-               const uint32_t p = t.m0 + m;
-               const uint32_t maxlen = t.wlen - p;   /* matchfinder.c:276-280 (LAST_LITERALS = 0) */
-#pragma unroll
-               for (int q = 0; q < ZB_NMATCH; q++) { uint32_t len = rec[q] & 0xffffu; if (len > maxlen) rec[q] = (rec[q] & 0xffff0000u) | maxlen; }
-               uint4 *dst = (uint4 *)(mt + ((size_t)(gbase + p) << 3));
-               dst[0] = make_uint4(rec[0], rec[1], rec[2], rec[3]);
-               dst[1] = make_uint4(rec[4], rec[5], rec[6], rec[7]);
-               const uint32_t l0 = rec[0] & 0xffffu;
-               gl[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)l0 : (uint16_t)1;
-               go[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)(rec[0] >> 16) : (uint16_t)0;
-               busy = false;
+            if (l < ZB_MIN_MATCH) { fin = true; break; }
+            if (steps >= ZB_TS_MIN && i - 1 - best <= ZB_TS_MUL * steps) {
+               text = true; j = i - 1; nt = 0; curmax = 0;
+               k3 = (uint32_t)txt[i] | ((uint32_t)txt[i + 1] << 8) | ((uint32_t)txt[i + 2] << 16);
+               kj = k3;
+               lL = l;   /* lL now holds the bound of the text walk */
                break;
             }
-            lvl = l;
+            lvl = l; steps++;
             uint32_t w;
             if (lL >= lR) { w = words[L]; L--; const uint32_t wl = w >> ZB_POS_BITS; lL = wl < lL ? wl : lL; }
             else { w = words[R]; R++; const uint32_t wl = words[R] >> ZB_POS_BITS; lR = wl < lR ? wl : lR; }
             const int p = (int)(w & ZB_POS_MASK);
-            if (p < i && p > best) { best = p; moved = true; }
+            if (p < i && p > best) {
+               best = p; moved = true;
+               if (best == i - 1) { ZB_MF_EMIT(lvl | (1u << 16)); fin = true; break; }
+            }
          }
       }
+      if (busy && text && !fin) {
+         const uint32_t bound = lL;
+         bool done = false;
+#pragma unroll 1
+         for (int step = 0; step < 16; step++) {
+            if (j <= best) { done = true; break; }
+            kj = ((kj << 8) | (uint32_t)txt[j]) & 0xffffffu;
+            if (kj == k3) {
+               uint32_t len = ZB_MIN_MATCH;
+               while (len < bound && txt[j + len] == txt[i + len]) len++;
+               if (len > curmax) {
+#pragma unroll
+                  for (int z = ZB_NMATCH - 1; z > 0; z--) tr[z] = tr[z - 1];
+                  tr[0] = len | ((uint32_t)(i - j) << 16);
+                  if (nt < ZB_NMATCH) nt++;
+                  curmax = len;
+                  if (len == bound) { done = true; break; }
+               }
+            }
+            j--;
+         }
+         if (done) {
+            if (moved && !(nt && curmax == lvl)) ZB_MF_EMIT(lvl | ((uint32_t)(i - best) << 16));
+#pragma unroll
+            for (int z = 0; z < ZB_NMATCH; z++) if (z < nt && nm < ZB_NMATCH) ZB_MF_EMIT(tr[z]);
+            fin = true;
+         }
+      }
+      if (fin) {
+         for (int z = nm; z < ZB_NMATCH; z++) dst[z] = 0u;
+         const uint32_t p = t.m0 + m;
+         const uint32_t l0 = first_rec & 0xffffu;
+         gl[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)l0 : (uint16_t)1;
+         go[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)(first_rec >> 16) : (uint16_t)0;
+         busy = false;
+      }
    }
+#undef ZB_MF_EMIT
 }
 #endif
 
@@ -447,34 +424,6 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    match.need((size_t)P * ZB_NMATCH); glen.need(P); goff.need(P);
    unit_words.need((size_t)nunit * (2 * ZB_MAX_OFFSET)); unit_cnt.need(nunit);
    zb_tile_filter(st, sa_lcp.p, 0, units.p, nunit, 0, unit_words.p, 2 * ZB_MAX_OFFSET, unit_cnt.p);
-   /* nearest earlier occurrence for the low LCP levels, per unit */
-   chain.need((size_t)ZB_NCHAIN * P + 16);
-   if (ZB_NCHAIN > 0) {
-      const ZbTileDesc *ud = units.p; const uint32_t *uw = unit_words.p, *uc = unit_cnt.p; uint16_t *ch = chain.p; const uint32_t *wbs0 = wbase.p; const uint32_t PP = P;
-      const int cwave = 4096;   /* (unit, level) tasks per launch: bounds the scratch */
-      chain_gid.need((size_t)std::min(nunit * ZB_NCHAIN, cwave) * (2 * ZB_MAX_OFFSET)); chain_last.need((size_t)std::min(nunit * ZB_NCHAIN, cwave) * (2 * ZB_MAX_OFFSET));
-      uint16_t *cg = chain_gid.p; uint32_t *cl = chain_last.p;
-#ifndef ZB_EMU
-      {
-         const int per = cwave / (ZB_NCHAIN > 0 ? ZB_NCHAIN : 1);
-         for (int u0 = 0; u0 < nunit; u0 += per) {
-            const int nu = std::min(per, nunit - u0);
-            if (g_zb_prof_on) { zb_tag("mf_chain"); zb_prof_begin(0, st); }
-            zb_mf_chain_k<<<(nu * ZB_NCHAIN + 3) / 4, 128, 0, st>>>(ud + u0, nu, uw + (size_t)u0 * (2 * ZB_MAX_OFFSET), uc + u0, cg, cl, ch, wbs0, PP);
-            if (g_zb_prof_on) zb_prof_end(st);
-            g_zb_launches++;
-            ZB_CUDA_CHECK(cudaGetLastError());
-         }
-      }
-#else
-      zb_launch(st, (long)nunit * ZB_NCHAIN, ZB_LAMBDA(long x) {
-         const int u = (int)(x / ZB_NCHAIN), q = (int)(x % ZB_NCHAIN);
-         const ZbTileDesc t = ud[u];
-         zb_mf_chain_unit(uw + (size_t)u * (2 * ZB_MAX_OFFSET), (int)uc[u], (uint32_t)(ZB_CHAIN_LO + q), t.m0 - t.lo, cg, cl,
-                          ch + (size_t)q * PP + wbs0[t.win] + t.m0);
-      });
-#endif
-   }
    const size_t stride = ZB_MAX_OFFSET + tile_main;
    const int wave = 16384;
    const int nw_tiles = std::min(ntile, wave);
@@ -483,19 +432,19 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    zb_match_t *mt = match.p; uint16_t *gl = glen.p, *go = goff.p; const uint32_t *wbs = wbase.p;
    stat_tiles = ntile;
 #ifndef ZB_EMU
-   const size_t smem = (stride + 2) * 4 + (size_t)tile_main * 2;
-   const uint16_t *chp = chain.p; const uint32_t PP2 = P;
+   const size_t smem = (stride + 2) * 4 + (size_t)tile_main * 2 + ((stride + ZB_MAX_MATCH + 7) & ~(size_t)3);
+   const ZbWinDesc *wdp = win.p; const uint8_t *Tp = in_ptr;
    ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_mf_scan_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 #else
    tile_pd.need((size_t)nw_tiles * tile_main);
-   uint32_t *pdb = tile_pd.p; const uint16_t *chq = chain.p; const uint32_t PPe = P;
+   uint32_t *pdb = tile_pd.p; const ZbWinDesc *wdp = win.p; const uint8_t *Tp = in_ptr;
 #endif
    for (int first = 0; first < ntile; first += wave) {
       const int cnt = std::min(wave, ntile - first);
       zb_tile_filter(st, unit_words.p, unit_cnt.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p);
 #ifndef ZB_EMU
       if (g_zb_prof_on) { zb_tag("mf_scan"); zb_prof_begin(0, st); }
-      zb_mf_scan_k<<<cnt, ZB_MF_THREADS, smem, st>>>(td, first, ivb, stride, tc, mt, gl, go, wbs, chp, PP2);
+      zb_mf_scan_k<<<cnt, ZB_MF_THREADS, smem, st>>>(td, first, ivb, stride, tc, mt, gl, go, wbs, wdp, Tp, tile_main);
       if (g_zb_prof_on) zb_prof_end(st);
       g_zb_launches++;
       ZB_CUDA_CHECK(cudaGetLastError());
@@ -514,9 +463,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
          const uint32_t *words = ivb + (size_t)k * stride; const uint32_t *rom = pdb + (size_t)k * tile_main;
          const uint32_t nlook = t.m0 - t.lo, p = t.m0 + m, gbase = wbs[t.win];
          zb_match_t o[ZB_NMATCH];
-         uint16_t chv[ZB_NCHAIN + 1];
-         for (int q = 0; q < ZB_NCHAIN; q++) chv[q] = chq[(size_t)q * PPe + gbase + p];
-         const int nm = zb_mf_scan(words, (int)tc[k], (int)rom[m], nlook + m, chv, o);
+         const int nm = zb_mf_scan(words, (int)tc[k], (int)rom[m], nlook + m, Tp + wdp[t.win].in_off + t.lo, o);
          const uint32_t maxlen = t.wlen - p;
          zb_match_t *dst = mt + ((size_t)(gbase + p) << 3);
          for (int q = 0; q < ZB_NMATCH; q++) {
@@ -1469,7 +1416,7 @@ inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams) {
 inline void ZbPipe::release_all() {
    win.release(); wbase.release(); in.release(); keyA.release(); keyB.release(); valA.release(); valB.release(); rank.release(); sa.release();
    actA.release(); actB.release(); tmpA.release(); tmpB.release(); scratch.release(); sa_lcp.release(); counters.release(); tiles.release();
-   tile_iv.release(); tile_pd.release(); tile_cnt.release(); units.release(); unit_words.release(); unit_cnt.release(); chain.release(); chain_gid.release(); chain_last.release(); match.release(); glen.release(); goff.release(); exitoff.release(); gentry.release();
+   tile_iv.release(); tile_pd.release(); tile_cnt.release(); units.release(); unit_words.release(); unit_cnt.release(); match.release(); glen.release(); goff.release(); exitoff.release(); gentry.release();
    gtokcnt.release(); gtokbase.release(); tokpos.release(); wtok.release(); wtokbase.release(); wintbase.release(); ph.release();
    gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
    chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();
