@@ -27,7 +27,7 @@ void zb_inclusive_max(zb_stream_t, const uint32_t *in, uint32_t *out, long n, ui
    uint32_t acc = 0;
    for (long i = 0; i < n; i++) { acc = std::max(acc, in[i]); out[i] = acc; }
 }
-void zb_tile_filter(zb_stream_t, const uint32_t *srcw, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first, uint32_t *out, size_t stride, uint32_t *cnt) {
+void zb_tile_filter(zb_stream_t, const uint32_t *srcw, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first, uint32_t *out, size_t stride, uint32_t *cnt, int, uint32_t *) {
    for (int k = 0; k < ntiles; k++) {
       const ZbTileDesc t = tiles[first + k];
       const uint32_t *src = srcw + t.src_base;

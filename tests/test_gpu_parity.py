@@ -158,6 +158,45 @@ def test_large_vs_compiled_reference(z, ref):
         assert z.memory_compress(data, flags) == ref.compress(data, flags=flags)
 
 
+def test_lanes_vs_compiled_reference(z, ref, monkeypatch):
+    """Block ranges of one call run as concurrent lanes (zb_capi.cu run_lanes); the stitched stream must equal the
+    reference byte for byte, including stored sub-blocks whose size depends on the entering bit phase, a history that
+    is not contiguous with the data, an entering bit count and the running checksum."""
+    rng = np.random.default_rng(5)
+    data = np.concatenate([synth.enwik(700000, seed=31), rng.integers(0, 256, size=300000).astype(np.uint8), synth.mozilla(900000, seed=32),
+                           rng.integers(0, 256, size=150000).astype(np.uint8), synth.enwik(450000, seed=33)])
+    monkeypatch.setenv("ZULTRA_CUDA_LANE_MIN_BLOCKS", "1")
+    for lanes, block in ((3, 262144), (4, 131072), (7, 65536)):
+        monkeypatch.setenv("ZULTRA_CUDA_LANES", str(lanes))
+        c = z.CudaCtx()
+        try:
+            for flags in (0, 1, 2):
+                want = ref.compress(data, flags=flags, block=block)
+                hdr = 0 if flags == 0 else (2 if flags == 1 else 10)
+                ftr = 0 if flags == 0 else (4 if flags == 1 else 8)
+                got, bits, ck = c.compress_blocks(data, block=block, finalize=1, flags=flags)
+                assert c.counters()["r5"] == lanes
+                assert got == want[hdr:len(want) - ftr], (lanes, block, flags)
+                if flags == 1:
+                    assert ck == zlib.adler32(data.tobytes())
+                if flags == 2:
+                    assert ck == zlib.crc32(data.tobytes())
+            # second half of a stream: separate history buffer, 5 pending bits
+            cut = 4 * block
+            a, abits, ack = c.compress_blocks(data[:cut], block=block, finalize=0, flags=2)
+            b, bbits, bck = c.compress_blocks(data[cut:], hist=data[cut - 32768:cut].copy(), block=block, finalize=1, in_bits=abits & 7, flags=2, checksum=ack)
+            want = ref.compress(data, flags=2, block=block)[10:-8]
+            joined = bytearray(a)
+            if abits & 7:
+                joined[-1] |= b[0]
+                joined += b[1:]
+            else:
+                joined += b
+            assert bytes(joined) == want and bck == zlib.crc32(data.tobytes())
+        finally:
+            c.close()
+
+
 def test_cli_drop_in(z, tmp_path):
     cli = os.path.join(ROOT, "zultra_b200", "zultra")
     src = tmp_path / "in.bin"

@@ -5,6 +5,7 @@
 #include "../../include/zultra_cuda.h"
 #include <new>
 #include <mutex>
+#include <thread>
 
 extern int g_zb_cuda_error;
 
@@ -15,6 +16,11 @@ struct zultra_cuda_ctx_s {
    float ms[8];
    long long counters[8];
    std::vector<uint8_t> out;
+   /* lanes: block ranges of one call run concurrently, each on its own stream / pipeline / host thread, so that the
+      latency-bound stages of one range overlap the issue-bound stages of another (see run_lanes) */
+   int nlanes = 1, lane_min_blocks = 4;   /* measured on B200: lanes do not pay (the big kernels are shared-memory / issue limited), kept for H2D overlap experiments */
+   std::vector<zultra_cuda_ctx_s *> lanes;
+   ZbBuf<uint32_t> lane_out;
 };
 
 static int ctx_enter(zultra_cuda_ctx_t *c) {
@@ -63,6 +69,8 @@ int zultra_cuda_ctx_create(zultra_cuda_ctx_t **pp, int device) {
       if ((e = getenv("ZULTRA_CUDA_PARSE_CD")) && atoi(e) >= 512) c->pipe.parse_cd = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_PARSE_WU")) && atoi(e) >= 258) c->pipe.parse_wu = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_TILE")) && atoi(e) >= 256) c->tile = (unsigned)atoi(e);
+      if ((e = getenv("ZULTRA_CUDA_LANES")) && atoi(e) >= 1 && atoi(e) <= 16) c->nlanes = atoi(e);
+      if ((e = getenv("ZULTRA_CUDA_LANE_MIN_BLOCKS")) && atoi(e) >= 1) c->lane_min_blocks = atoi(e);
    }
    *pp = c;
    return 0;
@@ -71,6 +79,8 @@ int zultra_cuda_ctx_create(zultra_cuda_ctx_t **pp, int device) {
 void zultra_cuda_ctx_destroy(zultra_cuda_ctx_t *c) {
    if (!c) return;
    cudaSetDevice(c->device);
+   for (size_t i = 0; i < c->lanes.size(); i++) zultra_cuda_ctx_destroy(c->lanes[i]);
+   c->lane_out.release();
    c->pipe.release_all();
    cudaStreamDestroy(c->pipe.st);
    delete c;
@@ -96,6 +106,118 @@ static int run_one(zultra_cuda_ctx_t *c, const ZbStreamIn &s, unsigned block, Zb
    return rc;
 }
 
+/*
+ * One call = consecutive max-blocks of one stream.  With enough blocks the range is cut into `nl` lanes of whole blocks;
+ * each lane is a shard in the sense of zultra_cuda_shard_prepare (its own 32 KiB of preceding input as history) driven by
+ * its own host thread on its own stream.  Everything up to the sub-block sizes is independent of the bit phase; the 8-entry
+ * phase maps compose left to right into every lane's absolute bit offset (the same algebra as the multi-GPU stitch),
+ * then all lanes emit into ONE zeroed word buffer, edge words merged with atomicOr.
+ *   host_in != 0: [host_hist (hist_size) | host_in (n)] in host memory;  dev_in != 0: the same layout in device memory.
+ */
+static int lanes_wanted(zultra_cuda_ctx_t *c, size_t n, unsigned block) {
+   const size_t nblocks = (n + block - 1) / block;
+   int nl = c->nlanes;
+   while (nl > 1 && nblocks < (size_t)nl * c->lane_min_blocks) nl--;
+   return nl;
+}
+
+static int run_lanes(zultra_cuda_ctx_t *c, int nl, const uint8_t *host_hist, int hist_size, const uint8_t *host_in, const uint8_t *dev_in, size_t n,
+                     unsigned block, int finalize, unsigned in_bits, unsigned flags, unsigned *checksum, uint8_t *host_out, uint8_t *dev_out, size_t out_cap,
+                     unsigned long long *out_bits) {
+   const long long l0 = g_zb_launches;
+   const size_t nblocks = (n + block - 1) / block, per = (nblocks + nl - 1) / nl;
+   while ((int)c->lanes.size() < nl) {
+      zultra_cuda_ctx_t *q = 0;
+      if (zultra_cuda_ctx_create(&q, c->device)) return ZULTRA_CUDA_ERR_CUDA;
+      c->lanes.push_back(q);
+   }
+   const int kind = (flags & 2) ? 2 : ((flags & 1) ? 1 : 0);
+   struct Lane { size_t lo, hi; int rc; ZbRunOpts o; unsigned ck; unsigned long long abs_bits, end_bits; };
+   std::vector<Lane> L(nl);
+   ZbTimer tot;
+   for (int k = 0; k < nl; k++) {
+      L[k].lo = std::min(n, (size_t)k * per * block); L[k].hi = std::min(n, (size_t)(k + 1) * per * block); L[k].rc = 0;
+      L[k].ck = k == 0 ? (checksum ? *checksum : 0) : (kind == 1 ? 1u : 0u);
+   }
+   auto prepare = [&](int k) {
+      zultra_cuda_ctx_t *q = k == 0 ? c : c->lanes[k];
+      Lane &l = L[k];
+      if (l.hi <= l.lo) return;
+      cudaSetDevice(c->device);
+      const uint32_t h = k == 0 ? (uint32_t)hist_size : (uint32_t)ZB_HISTORY;
+      ZbStreamIn s;
+      if (dev_in) { ZbStreamIn t = {0, l.hi - l.lo, 0, h, (finalize && l.hi == n) ? 1 : 0, 0, l.ck}; s = t; l.o.dev_in = dev_in + hist_size + l.lo - h; }
+      else { ZbStreamIn t = {host_in + l.lo, l.hi - l.lo, k == 0 ? host_hist : host_in + l.lo - h, h, (finalize && l.hi == n) ? 1 : 0, 0, l.ck}; s = t; }
+      l.o.phase = 1; l.o.checksum_kind = kind; l.o.tile_main = c->tile;
+      q->pipe.parse_cd = c->pipe.parse_cd; q->pipe.parse_wu = c->pipe.parse_wu;
+      q->pipe.counters.need(64);
+      zb_memset(q->pipe.st, q->pipe.counters.p, 0, 64 * 4);
+      q->pipe.stat_redo = 0;
+      std::vector<ZbStreamRes> res;
+      l.rc = zb_run_batch(q->pipe, &s, 1, block, q->out, res, l.o);
+      if (l.rc == 0) l.ck = res[0].checksum;
+   };
+   {
+      std::vector<std::thread> th;
+      for (int k = 1; k < nl; k++) th.emplace_back(prepare, k);
+      prepare(0);
+      for (size_t i = 0; i < th.size(); i++) th[i].join();
+   }
+   if (getenv("ZULTRA_CUDA_LANE_TRACE")) {
+      double t0 = 1e300; for (int k = 0; k < nl; k++) t0 = std::min(t0, L[k].o.t_abs[0]);
+      for (int k = 0; k < nl; k++) fprintf(stderr, "lane %d: setup %.1f sa %.1f match %.1f split %.1f parse %.1f prep %.1f\n", k, L[k].o.t_abs[0] - t0, L[k].o.t_abs[1] - t0, L[k].o.t_abs[2] - t0, L[k].o.t_abs[3] - t0, L[k].o.t_abs[4] - t0, L[k].o.t_abs[5] - t0);
+   }
+   for (int k = 0; k < nl; k++) if (L[k].rc) return ZULTRA_CUDA_ERR_CUDA;
+   /* phase maps -> absolute bit offsets (tests/test_cpu_shards.py checks this algebra against the reference) */
+   unsigned long long pos = in_bits;
+   for (int k = 0; k < nl; k++) {
+      L[k].abs_bits = pos;
+      if (L[k].hi > L[k].lo) pos += L[k].o.phase_bits[pos & 7] - (pos & 7);
+   }
+   const size_t nb = (size_t)((pos + 7) / 8);
+   if (nb > out_cap) return ZULTRA_CUDA_ERR_DST;
+   const size_t nwords = (size_t)((pos + 31) / 32) + 4;
+   c->lane_out.need(nwords);
+   if (!c->lane_out.p) return ZULTRA_CUDA_ERR_CUDA;
+   zb_memset(c->pipe.st, c->lane_out.p, 0, nwords * 4);
+   zb_sync(c->pipe.st);
+   float t_prep = tot.lap();
+   auto emit = [&](int k) {
+      zultra_cuda_ctx_t *q = k == 0 ? c : c->lanes[k];
+      if (L[k].hi <= L[k].lo) return;
+      cudaSetDevice(c->device);
+      L[k].rc = zb_finish_lane(q->pipe, L[k].abs_bits, c->lane_out.p, &L[k].end_bits);
+   };
+   {
+      std::vector<std::thread> th;
+      for (int k = 1; k < nl; k++) th.emplace_back(emit, k);
+      emit(0);
+      for (size_t i = 0; i < th.size(); i++) th[i].join();
+   }
+   for (int k = 0; k < nl; k++) if (L[k].rc) return ZULTRA_CUDA_ERR_CUDA;
+   if (dev_out) zb_d2d(c->pipe.st, dev_out, c->lane_out.p, nb);
+   else zb_d2h(c->pipe.st, host_out, c->lane_out.p, nb);
+   zb_sync(c->pipe.st);
+   *out_bits = pos;
+   if (checksum) {
+      unsigned ck = L[0].ck;
+      for (int k = 1; k < nl; k++) if (L[k].hi > L[k].lo) ck = zultra_cuda_checksum_combine(flags, ck, L[k].ck, L[k].hi - L[k].lo);
+      *checksum = ck;
+   }
+   /* stage times: the slowest lane per stage (they run side by side); counters: sums */
+   memset(c->ms, 0, sizeof(c->ms)); memset(c->counters, 0, sizeof(c->counters));
+   for (int k = 0; k < nl; k++) {
+      if (L[k].hi <= L[k].lo) continue;
+      ZbPipe &p = (k == 0 ? c : c->lanes[k])->pipe;
+      for (int i = 0; i < 7; i++) c->ms[i] = std::max(c->ms[i], L[k].o.ms[i]);
+      c->counters[0] += p.nwin; c->counters[1] += p.nsub; c->counters[2] = std::max<long long>(c->counters[2], p.stat_sa_rounds);
+      c->counters[3] += p.stat_redo; c->counters[7] += p.stat_tiles;
+   }
+   c->ms[5] += tot.lap(); c->ms[7] = t_prep + c->ms[5];
+   c->counters[4] = g_zb_launches - l0; c->counters[5] = nl;
+   return 0;
+}
+
 static unsigned clamp_block(unsigned b) {
    if (!b) b = 1048576;
    if (b < 32768) b = 32768;
@@ -109,6 +231,10 @@ int zultra_cuda_compress_blocks(zultra_cuda_ctx_t *c, const unsigned char *hist,
    int rc = ctx_enter(c);
    if (rc) return rc;
    if (!in || !out || !out_bits || in_bits > 7 || hist_size < 0 || hist_size > ZB_HISTORY) return ZULTRA_CUDA_ERR_ARG;
+   {
+      const int nl = lanes_wanted(c, n, clamp_block(block));
+      if (nl > 1) return ctx_leave(c, run_lanes(c, nl, hist, hist_size, in, 0, n, clamp_block(block), finalize, in_bits, flags, checksum, out, 0, out_cap, out_bits));
+   }
    ZbStreamIn s = {in, n, hist, (uint32_t)hist_size, finalize, in_bits, checksum ? *checksum : 0};
    ZbRunOpts o;
    o.checksum_kind = (flags & 2) ? 2 : ((flags & 1) ? 1 : 0);
@@ -167,6 +293,10 @@ int zultra_cuda_compress_blocks_device(zultra_cuda_ctx_t *c, const void *dev_in,
    int rc = ctx_enter(c);
    if (rc) return rc;
    if (!dev_in || !dev_out || !out_bits) return ZULTRA_CUDA_ERR_ARG;
+   {
+      const int nl = lanes_wanted(c, n, clamp_block(block));
+      if (nl > 1) return ctx_leave(c, run_lanes(c, nl, 0, 0, 0, (const uint8_t *)dev_in, n, clamp_block(block), finalize, 0, flags, checksum, 0, (uint8_t *)dev_out, out_cap, out_bits));
+   }
    ZbStreamIn s = {0, n, 0, 0, finalize, 0, checksum ? *checksum : 0};
    ZbRunOpts o;
    o.dev_in = (const uint8_t *)dev_in; o.dev_out = (uint8_t *)dev_out; o.dev_out_cap = out_cap;

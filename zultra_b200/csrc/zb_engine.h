@@ -31,6 +31,7 @@ struct ZbRunOpts {
    ZbDump *dump = 0;
    int stop_after = 99;            /* 1 = SA, 2 = match (stage dumps) */
    float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* h2d, sa, match, greedy+split, parse, emit, d2h, total */
+   double t_abs[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* host clock (ms since an arbitrary origin) at the end of each stage: lane timelines */
 };
 
 /* main positions per match-finder tile: as large as shared memory allows (amortises the 32768 look-back entries every
@@ -41,6 +42,7 @@ static inline uint32_t zb_pick_tile(size_t total) {
    return t;
 }
 
+static inline double zb_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 struct ZbTimer {
    std::chrono::steady_clock::time_point t0;
    ZbTimer() : t0(std::chrono::steady_clock::now()) {}
@@ -59,7 +61,8 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
    if (in_bytes >= ((size_t)1 << 31)) return -1;
    ZbTimer tm, tot;
    std::vector<uint8_t> stage;
-   const bool single_direct = (ns == 1 && s[0].hist_len == 0 && !o.dev_in);   /* copy straight from the caller's buffer */
+   /* copy straight from the caller's buffer when [history | data] is contiguous there */
+   const bool single_direct = (ns == 1 && !o.dev_in && (s[0].hist_len == 0 || s[0].hist + s[0].hist_len == s[0].data));
    if (!o.dev_in && !single_direct) stage.resize(in_bytes);
    size_t off = 0, total_block = 0;
    for (int i = 0; i < ns; i++) {
@@ -90,25 +93,25 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
    res.assign(ns, ZbStreamRes());
    for (int i = 0; i < ns; i++) res[i].checksum = s[i].checksum;
    if (wins.empty()) { out.clear(); return 0; }
-   p.setup(wins, o.dev_in ? o.dev_in : (single_direct ? s[0].data : stage.data()), in_bytes, o.dev_in != 0);
-   zb_sync(p.st); o.ms[0] = tm.lap();
+   p.setup(wins, o.dev_in ? o.dev_in : (single_direct ? s[0].data - s[0].hist_len : stage.data()), in_bytes, o.dev_in != 0);
+   zb_sync(p.st); o.ms[0] = tm.lap(); o.t_abs[0] = zb_now_ms();
    p.stage_sa();
-   zb_sync(p.st); o.ms[1] = tm.lap();
+   zb_sync(p.st); o.ms[1] = tm.lap(); o.t_abs[1] = zb_now_ms();
    if (o.stop_after >= 2) {
       p.stage_match(o.tile_main ? o.tile_main : zb_pick_tile(total_block));
-      zb_sync(p.st); o.ms[2] = tm.lap();
+      zb_sync(p.st); o.ms[2] = tm.lap(); o.t_abs[2] = zb_now_ms();
    }
    if (o.stop_after >= 3) {
       p.stage_greedy();
       p.stage_split();
-      zb_sync(p.st); o.ms[3] = tm.lap();
+      zb_sync(p.st); o.ms[3] = tm.lap(); o.t_abs[3] = zb_now_ms();
       p.stage_parse();
-      zb_sync(p.st); o.ms[4] = tm.lap();
+      zb_sync(p.st); o.ms[4] = tm.lap(); o.t_abs[4] = zb_now_ms();
       p.stage_emit_prepare();
       if (o.phase == 1) {   /* shard: report the size for every entering phase and wait for zb_finish_shard */
          if (o.checksum_kind) { std::vector<uint32_t> sums; p.stage_checksum(o.checksum_kind, ck_off, ck_len, sums, s[0].checksum); res[0].checksum = sums[0]; }
          p.phase_map(0, (uint32_t)wins.size(), o.phase_bits);
-         zb_sync(p.st); o.ms[5] = tm.lap(); o.ms[7] = tot.lap();
+         zb_sync(p.st); o.ms[5] = tm.lap(); o.ms[7] = tot.lap(); o.t_abs[5] = zb_now_ms();
          return 0;
       }
       p.stage_emit_finish(so);
@@ -171,6 +174,17 @@ static inline int zb_finish_shard(ZbPipe &p, uint32_t in_bits, uint8_t *dev_out,
    zb_d2d(p.st, dev_out, p.out.p + p.h_sout[0].out_word_off, nb);
    zb_sync(p.st);
    *total_bits = p.h_sout[0].total_bits;
+   return 0;
+}
+/* lane of a stream that shares one output buffer with the other lanes: abs_bits = absolute bit offset of the lane's first
+   bit in ext_words (zeroed by the caller); edge words are merged with atomicOr by the emitters */
+static inline int zb_finish_lane(ZbPipe &p, unsigned long long abs_bits, uint32_t *ext_words, unsigned long long *end_bits) {
+   std::vector<ZbStreamOut> so(1);
+   memset(&so[0], 0, sizeof(ZbStreamOut));
+   so[0].first_win = 0; so[0].nwin = (uint32_t)p.nwin; so[0].in_bits = abs_bits;
+   p.stage_emit_finish(so, ext_words);
+   zb_sync(p.st);
+   *end_bits = p.h_sout[0].total_bits;
    return 0;
 }
 #endif

@@ -18,11 +18,12 @@
 #define ZB_CG 1024        /* positions per greedy-path chunk */
 #define ZB_CP 1024        /* positions per parsed-path chunk */
 #define ZB_CD 2048        /* positions per parse (DP) chunk */
-#define ZB_WU 1024        /* parse warm-up positions past the chunk end */
+#define ZB_WU 384         /* parse warm-up positions past the chunk end (>= 258; text re-synchronises well within it, the rest is repaired) */
 #define ZB_TOKI 256       /* tokens per prefix-histogram interval */
 #define ZB_NH 320         /* 288 lit/len + 32 distance counters */
 #define ZB_MAXSB 64       /* sub-blocks per window */
 #define ZB_MAXNODES 64    /* splitter nodes per window per level (<= 32 used) */
+#define ZB_MF_TILE_MAX 8192   /* main positions per match-finder tile: words + ranks + text of 32768 + 8192 positions fill the 227 KB of shared memory */
 
 struct ZbWinDesc {
    uint32_t in_off;   /* offset of the window's first byte (history start) in the device input */
@@ -106,7 +107,7 @@ struct ZbPipe {
    ZbBuf<uint32_t> sa_lcp;      /* packed SA|LCP words, rank order, per window at wbase[w] */
    ZbBuf<uint32_t> counters;    /* misc device counters */
    /* match finder */
-   ZbBuf<ZbTileDesc> tiles, units; ZbBuf<uint32_t> tile_iv, tile_pd, tile_cnt, unit_words, unit_cnt;
+   ZbBuf<ZbTileDesc> tiles, units, groups; ZbBuf<uint32_t> tile_iv, tile_pd, tile_cnt, tile_q, unit_words, unit_cnt, group_words, group_cnt, filt_seg;
    ZbBuf<zb_match_t> match; ZbBuf<uint16_t> glen, goff;
    /* greedy path */
    ZbBuf<uint16_t> exitoff; ZbBuf<uint32_t> gentry, gtokcnt, gtokbase, tokpos, wtok; /* wtok[w] = tokens of window w; base in wtokbase */
@@ -117,7 +118,7 @@ struct ZbPipe {
    ZbBuf<uint32_t> wsplit; ZbBuf<uint32_t> wnsplit;
    /* sub-blocks */
    ZbBuf<ZbSub> sub; ZbBuf<ZbSubTabs> tabs; ZbBuf<uint32_t> dchunk_sub, pchunk_sub;
-   ZbBuf<zb_match_t> best; ZbBuf<int16_t> sig_true, sig_warm, sig_new; ZbBuf<uint8_t> dok;
+   ZbBuf<zb_match_t> best; ZbBuf<int16_t> sig_true, sig_warm, sig_new; ZbBuf<uint8_t> dok; ZbBuf<uint32_t> dbad;
    ZbBuf<uint32_t> pentry, pbits;
    /* output */
    ZbBuf<uint32_t> out; ZbBuf<ZbStreamOut> sout;
@@ -138,7 +139,9 @@ struct ZbPipe {
    void stage_parse();
    void stage_emit(const std::vector<ZbStreamOut> &streams) { stage_emit_prepare(); stage_emit_finish(streams); }
    void stage_emit_prepare();                                   /* path, token bits, sub-block sizes: independent of the bit phase */
-   void stage_emit_finish(const std::vector<ZbStreamOut> &streams);   /* stitch scan for the entering phase, then emission */
+   /* stitch scan for the entering phase, then emission.  ext_words != 0: write into that zeroed word buffer, every stream's
+      in_bits being its ABSOLUTE bit offset there (lanes of one stream sharing one output, zb_capi.cu) */
+   void stage_emit_finish(const std::vector<ZbStreamOut> &streams, uint32_t *ext_words = 0);
    void phase_map(uint32_t first_win, uint32_t nwin, unsigned long long bits_out[8]);   /* total bits for each entering phase 0..7 */
    /* checksum partials of byte ranges of the device input: kind 1 = Adler-32, 2 = CRC-32 */
    ZbBuf<uint32_t> ck_tab, ck_part; ZbBuf<uint64_t> ck_rng; bool ck_tab_ready = false;
@@ -267,43 +270,36 @@ inline void ZbPipe::stage_sa() {
 
 /* ============================================================ match finder ============================================================ */
 #ifndef ZB_EMU
-/* CTA per tile: the tile's suffix list (<= 32768 + T words), the rank of every main position and the tile's text live in
-   shared memory.  Walk lengths are heavy-tailed, so lanes do not own fixed positions: a lane that finishes fetches the next
-   main position from a shared counter and all 32 lanes keep stepping (same arithmetic as zb_mf_scan, kept as a resumable
-   state: rank walk, then - once the interval (best, i) is short - the text walk).  Records go straight to global memory as
-   they are found. */
+/* Match lists, kernel A.  CTA per tile: the tile's suffix list (<= 32768 + T words) and the rank of every main position live
+   in shared memory.  Walk lengths are heavy-tailed, so lanes do not own fixed positions: a lane that finishes fetches the next
+   main position from a shared counter and all 32 lanes keep stepping (same arithmetic as the rank walk of zb_mf_scan, kept
+   as a resumable state).  Records go straight to global memory as they are found.  A position whose walk reaches the
+   text-walk condition is handed to kernel B through a queue that reuses the tile's (now dead) global list: two words
+   {m | nm << 13 | moved << 17 | lvl << 18, bound | (i - 1 - best) << 9}. */
 #define ZB_MF_THREADS 1024
-__global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *td, int first, const uint32_t *lists, size_t stride, const uint32_t *cnts,
-                                                              zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, const ZbWinDesc *wd, const uint8_t *T,
-                                                              uint32_t tile_main) {
+__global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *td, int first, uint32_t *lists, size_t stride, const uint32_t *cnts, uint32_t *qcnt,
+                                                              zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, uint32_t tile_main) {
    extern __shared__ uint32_t zb_smw[];
-   __shared__ uint32_t next_m;
+   __shared__ uint32_t next_m, nq;
    const int k = blockIdx.x;
    const ZbTileDesc t = td[first + k];
    const int n = (int)cnts[k];
    const uint32_t nlook = t.m0 - t.lo, nmain = t.hi - t.m0;
    uint32_t *words = zb_smw + 1;          /* words[-1] and words[n] are LCP-0 sentinels: no bounds tests in the walk */
    uint16_t *rom = (uint16_t *)(zb_smw + stride + 2);
-   uint8_t *txt = (uint8_t *)(rom + tile_main);
-   const uint32_t *src = lists + (size_t)k * stride;
-   if (threadIdx.x == 0) { next_m = 0; zb_smw[0] = 0; words[n] = 0; }
+   uint32_t *queue = lists + (size_t)k * stride;
+   if (threadIdx.x == 0) { next_m = 0; nq = 0; zb_smw[0] = 0; words[n] = 0; }
    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-      const uint32_t w = src[e];
+      const uint32_t w = queue[e];
       words[e] = w;
       const uint32_t p = w & ZB_POS_MASK;
       if (p >= nlook) rom[p - nlook] = (uint16_t)e;
    }
-   {
-      const uint8_t *tsrc = T + wd[t.win].in_off + t.lo;
-      uint32_t ntxt = t.hi - t.lo + ZB_MAX_MATCH;
-      if (ntxt > t.wlen - t.lo) ntxt = t.wlen - t.lo;
-      for (uint32_t e = threadIdx.x; e < ntxt; e += blockDim.x) txt[e] = tsrc[e];
-   }
    __syncthreads();
    const uint32_t gbase = wbs[t.win];
-   bool busy = false, drained = false, moved = false, text = false;
-   uint32_t m = 0, lL = 0, lR = 0, lvl = 0, first_rec = 0, maxlen = 0, k3 = 0, kj = 0, curmax = 0, tr[ZB_NMATCH];
-   int i = 0, L = 0, R = 0, best = -1, nm = 0, steps = 0, j = 0, nt = 0;
+   bool busy = false, drained = false, moved = false;
+   uint32_t m = 0, lL = 0, lR = 0, lvl = 0, first_rec = 0, maxlen = 0;
+   int i = 0, L = 0, R = 0, best = -1, nm = 0, steps = 0;
    uint32_t *dst = 0;
 #define ZB_MF_EMIT(v_) do { uint32_t v__ = (v_); if ((v__ & 0xffffu) > maxlen) v__ = (v__ & 0xffff0000u) | maxlen; if (nm == 0) first_rec = v__; dst[nm++] = v__; } while (0)
    for (;;) {
@@ -318,14 +314,14 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
             lL = words[r] >> ZB_POS_BITS;     /* words[0] has LCP 0 */
             lR = words[R] >> ZB_POS_BITS;     /* words[n] = 0 */
             best = (i > ZB_MAX_OFFSET ? i - ZB_MAX_OFFSET : 0) - 1;   /* p > best also enforces the 32768 limit */
-            nm = 0; lvl = 0; moved = false; steps = 0; text = false; first_rec = 0;
+            nm = 0; lvl = 0; moved = false; steps = 0; first_rec = 0;
             maxlen = t.wlen - (t.m0 + m);     /* matchfinder.c:276-280 (LAST_LITERALS = 0) */
             dst = (uint32_t *)(mt + ((size_t)(gbase + t.m0 + m) << 3));
          }
       }
       if (__all_sync(0xffffffffu, drained && !busy)) break;
       bool fin = false;
-      if (busy && !text) {
+      if (busy) {
 #pragma unroll 1
          for (int step = 0; step < 8; step++) {
             const uint32_t l = lL > lR ? lL : lR;
@@ -335,11 +331,11 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
                if (nm == ZB_NMATCH) { fin = true; break; }
             }
             if (l < ZB_MIN_MATCH) { fin = true; break; }
-            if (steps >= ZB_TS_MIN && i - 1 - best <= ZB_TS_MUL * steps) {
-               text = true; j = i - 1; nt = 0; curmax = 0;
-               k3 = (uint32_t)txt[i] | ((uint32_t)txt[i + 1] << 8) | ((uint32_t)txt[i + 2] << 16);
-               kj = k3;
-               lL = l;   /* lL now holds the bound of the text walk */
+            if (steps >= ZB_TS_MIN && i - 1 - best <= ZB_TS_MUL * steps) {   /* the rest is cheaper read from the text: kernel B */
+               const uint32_t at = atomicAdd(&nq, 1u);
+               queue[2 * at] = m | ((uint32_t)nm << 13) | ((moved ? 1u : 0u) << 17) | (lvl << 18);
+               queue[2 * at + 1] = l | ((uint32_t)(i - 1 - best) << 9);
+               busy = false;
                break;
             }
             lvl = l; steps++;
@@ -353,34 +349,6 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
             }
          }
       }
-      if (busy && text && !fin) {
-         const uint32_t bound = lL;
-         bool done = false;
-#pragma unroll 1
-         for (int step = 0; step < 16; step++) {
-            if (j <= best) { done = true; break; }
-            kj = ((kj << 8) | (uint32_t)txt[j]) & 0xffffffu;
-            if (kj == k3) {
-               uint32_t len = ZB_MIN_MATCH;
-               while (len < bound && txt[j + len] == txt[i + len]) len++;
-               if (len > curmax) {
-#pragma unroll
-                  for (int z = ZB_NMATCH - 1; z > 0; z--) tr[z] = tr[z - 1];
-                  tr[0] = len | ((uint32_t)(i - j) << 16);
-                  if (nt < ZB_NMATCH) nt++;
-                  curmax = len;
-                  if (len == bound) { done = true; break; }
-               }
-            }
-            j--;
-         }
-         if (done) {
-            if (moved && !(nt && curmax == lvl)) ZB_MF_EMIT(lvl | ((uint32_t)(i - best) << 16));
-#pragma unroll
-            for (int z = 0; z < ZB_NMATCH; z++) if (z < nt && nm < ZB_NMATCH) ZB_MF_EMIT(tr[z]);
-            fin = true;
-         }
-      }
       if (fin) {
          for (int z = nm; z < ZB_NMATCH; z++) dst[z] = 0u;
          const uint32_t p = t.m0 + m;
@@ -391,14 +359,121 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
       }
    }
 #undef ZB_MF_EMIT
+   __syncthreads();
+   if (threadIdx.x == 0) qcnt[k] = nq;
+}
+
+/* Match lists, kernel B: the text walk of zb_mf_scan for the positions kernel A queued, one WARP per position.  The tile's
+   text is in shared memory; the 32 lanes test 32 positions j of (best, i) per step for the 3-byte prefix, candidates are
+   compared 32 bytes at a time, nearest first.  Control flow is warp-uniform. */
+#define ZB_MT_THREADS 256
+__global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *td, int first, const uint32_t *lists, size_t stride, const uint32_t *qcnt,
+                                                              zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, const ZbWinDesc *wd, const uint8_t *T) {
+   extern __shared__ uint32_t zb_smw[];
+   __shared__ uint32_t next_q;
+   const int k = blockIdx.x;
+   const uint32_t nq = qcnt[k];
+   if (nq == 0) return;
+   const ZbTileDesc t = td[first + k];
+   const uint32_t nlook = t.m0 - t.lo;
+   uint8_t *txt = (uint8_t *)zb_smw;
+   const uint32_t *queue = lists + (size_t)k * stride;
+   {
+      const uint8_t *tsrc = T + wd[t.win].in_off + t.lo;
+      uint32_t ntxt = t.hi - t.lo + ZB_MAX_MATCH;
+      if (ntxt > t.wlen - t.lo) ntxt = t.wlen - t.lo;
+      /* 4 bytes per thread once the source is aligned */
+      const uint32_t head = (uint32_t)((4u - ((uintptr_t)tsrc & 3u)) & 3u);
+      for (uint32_t e = threadIdx.x; e < head && e < ntxt; e += blockDim.x) txt[e] = tsrc[e];
+      /* shared copy keeps the same byte offsets, so word stores need (e & 3) == head & 3: go bytewise unless head == 0 */
+      if (head == 0) {
+         const uint32_t nw4 = ntxt >> 2;
+         for (uint32_t e = threadIdx.x; e < nw4; e += blockDim.x) zb_smw[e] = ((const uint32_t *)tsrc)[e];
+         for (uint32_t e = (nw4 << 2) + threadIdx.x; e < ntxt; e += blockDim.x) txt[e] = tsrc[e];
+      } else {
+         for (uint32_t e = head + threadIdx.x; e < ntxt; e += blockDim.x) txt[e] = tsrc[e];
+      }
+   }
+   if (threadIdx.x == 0) next_q = 0;
+   __syncthreads();
+   const uint32_t gbase = wbs[t.win];
+   const int lane = threadIdx.x & 31;
+   for (;;) {
+      uint32_t e = 0;
+      if (lane == 0) e = atomicAdd(&next_q, 1u);
+      e = __shfl_sync(0xffffffffu, e, 0);
+      if (e >= nq) break;
+      const uint32_t q0 = queue[2 * e], q1 = queue[2 * e + 1];
+      const uint32_t m = q0 & 0x1fffu, lvl = q0 >> 18, bound = q1 & 0x1ffu;
+      int nm = (int)((q0 >> 13) & 15u);
+      const bool moved = (q0 >> 17) & 1u;
+      const int i = (int)(nlook + m);
+      const int best = i - 1 - (int)(q1 >> 9);
+      const uint32_t k3 = (uint32_t)txt[i] | ((uint32_t)txt[i + 1] << 8) | ((uint32_t)txt[i + 2] << 16);
+      uint32_t tr[ZB_NMATCH], curmax = 0;
+      int nt = 0;
+      bool done = false;
+#pragma unroll
+      for (int z = 0; z < ZB_NMATCH; z++) tr[z] = 0;
+      for (int jb = i - 1; jb > best && !done; jb -= 32) {
+         const int j = jb - lane;
+         bool hit = false;
+         if (j > best) hit = ((uint32_t)txt[j] | ((uint32_t)txt[j + 1] << 8) | ((uint32_t)txt[j + 2] << 16)) == k3;
+         uint32_t hits = __ballot_sync(0xffffffffu, hit);
+         while (hits && !done) {
+            const int h = __ffs((int)hits) - 1;
+            hits &= hits - 1u;
+            const int jh = jb - h;
+            uint32_t len = bound;
+            for (uint32_t o = ZB_MIN_MATCH; o < bound; o += 32) {
+               const uint32_t xo = o + (uint32_t)lane;
+               const bool neq = xo < bound && txt[jh + xo] != txt[i + xo];
+               const uint32_t mm = __ballot_sync(0xffffffffu, neq);
+               if (mm) { len = o + (uint32_t)(__ffs((int)mm) - 1); break; }
+            }
+            if (len > curmax) {
+#pragma unroll
+               for (int z = ZB_NMATCH - 1; z > 0; z--) tr[z] = tr[z - 1];
+               tr[0] = len | ((uint32_t)(i - jh) << 16);
+               if (nt < ZB_NMATCH) nt++;
+               curmax = len;
+               if (len == bound) done = true;
+            }
+         }
+      }
+      if (lane == 0) {
+         const uint32_t p = t.m0 + m;
+         const uint32_t maxlen = t.wlen - p;
+         uint32_t *dst = (uint32_t *)(mt + ((size_t)(gbase + p) << 3));
+         uint32_t first_rec = nm ? dst[0] : 0u;
+#define ZB_MF_EMIT(v_) do { uint32_t v__ = (v_); if ((v__ & 0xffffu) > maxlen) v__ = (v__ & 0xffff0000u) | maxlen; if (nm == 0) first_rec = v__; dst[nm++] = v__; } while (0)
+         /* the pending record of the rank walk stands unless a nearer position reached the same level */
+         if (moved && !(nt && curmax == lvl)) ZB_MF_EMIT(lvl | ((q1 >> 9) + 1u) << 16);
+#pragma unroll
+         for (int z = 0; z < ZB_NMATCH; z++) if (z < nt && nm < ZB_NMATCH) ZB_MF_EMIT(tr[z]);
+#undef ZB_MF_EMIT
+         for (int z = nm; z < ZB_NMATCH; z++) dst[z] = 0u;
+         const uint32_t l0 = first_rec & 0xffffu;
+         gl[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)l0 : (uint16_t)1;
+         go[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)(first_rec >> 16) : (uint16_t)0;
+      }
+   }
 }
 #endif
 
 inline void ZbPipe::stage_match(uint32_t tile_main) {
-   /* Two filter levels.  Units: per window, 32768 main positions + the 32768 before them, filtered from the window's
-      packed words.  Tiles: tile_main main positions (a divisor of 32768) + look-back, filtered from their unit. */
+   /* Filter levels, each cutting the list of the level above down to a position range (rank order kept, LCPs min-reduced):
+      [groups of 8 units, only for windows of more than 4 units ->] units: 32768 main positions + the 32768 before them ->
+      tiles: tile_main main positions (a divisor of 32768) + look-back.  The group level keeps the total streamed volume near
+      7 words per window position instead of 33. */
+   if (tile_main > ZB_MF_TILE_MAX) tile_main = ZB_MF_TILE_MAX;
    while (ZB_MAX_OFFSET % tile_main) tile_main >>= 1;
-   std::vector<ZbTileDesc> hu, ht;
+   const uint32_t GU = 8, gspan = GU * ZB_MAX_OFFSET;
+   uint32_t maxlen = 0;
+   for (int w = 0; w < nwin; w++) maxlen = std::max(maxlen, h_win[w].len);
+   const bool use_groups = maxlen > 4 * ZB_MAX_OFFSET;
+   const size_t gstride = (size_t)(GU + 1) * ZB_MAX_OFFSET;
+   std::vector<ZbTileDesc> hg, hu, ht;
    for (int w = 0; w < nwin; w++) {
       const ZbWinDesc &d = h_win[w];
       for (uint32_t u0 = d.hist; u0 < d.len; u0 += ZB_MAX_OFFSET) {
@@ -406,6 +481,15 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
          u.win = (uint32_t)w; u.m0 = u0; u.hi = std::min(d.len, u0 + ZB_MAX_OFFSET);
          u.lo = u0 > ZB_MAX_OFFSET ? u0 - ZB_MAX_OFFSET : 0;
          u.src_base = h_wbase[w]; u.src_n = d.len; u.src_lo = 0; u.src_cnt_idx = -1; u.wlen = d.len;
+         if (use_groups) {
+            if ((u0 - d.hist) % gspan == 0) {
+               ZbTileDesc g = u;
+               g.hi = std::min(d.len, u0 + gspan);
+               hg.push_back(g);
+            }
+            const int gi = (int)hg.size() - 1;
+            u.src_base = (uint64_t)gi * gstride; u.src_n = 0; u.src_lo = hg[gi].lo; u.src_cnt_idx = gi;
+         }
          const int ui = (int)hu.size();
          hu.push_back(u);
          for (uint32_t m0 = u0; m0 < u.hi; m0 += tile_main) {
@@ -417,13 +501,24 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
          }
       }
    }
-   const int nunit = (int)hu.size(), ntile = (int)ht.size();
+   const int ngroup = (int)hg.size(), nunit = (int)hu.size(), ntile = (int)ht.size();
    units.need(nunit); tiles.need(ntile);
    zb_h2d(st, units.p, hu.data(), sizeof(ZbTileDesc) * nunit);
    zb_h2d(st, tiles.p, ht.data(), sizeof(ZbTileDesc) * ntile);
    match.need((size_t)P * ZB_NMATCH); glen.need(P); goff.need(P);
    unit_words.need((size_t)nunit * (2 * ZB_MAX_OFFSET)); unit_cnt.need(nunit);
-   zb_tile_filter(st, sa_lcp.p, 0, units.p, nunit, 0, unit_words.p, 2 * ZB_MAX_OFFSET, unit_cnt.p);
+   auto segs_for = [](size_t n) { size_t k = (n + 8191) / 8192; return (int)(k < 1 ? 1 : (k > 64 ? 64 : k)); };
+   const int wave_tiles = std::min(ntile, 16384);
+   const int seg_g = segs_for(maxlen), seg_u = segs_for(use_groups ? gstride : maxlen), seg_t = segs_for(2 * ZB_MAX_OFFSET);
+   filt_seg.need(2 * std::max((size_t)ngroup * seg_g, std::max((size_t)nunit * seg_u, (size_t)wave_tiles * seg_t)) + 64);
+   if (use_groups) {
+      groups.need(ngroup); group_words.need((size_t)ngroup * gstride); group_cnt.need(ngroup);
+      zb_h2d(st, groups.p, hg.data(), sizeof(ZbTileDesc) * ngroup);
+      zb_tile_filter(st, sa_lcp.p, 0, groups.p, ngroup, 0, group_words.p, gstride, group_cnt.p, seg_g, filt_seg.p);
+      zb_tile_filter(st, group_words.p, group_cnt.p, units.p, nunit, 0, unit_words.p, 2 * ZB_MAX_OFFSET, unit_cnt.p, seg_u, filt_seg.p);
+   } else {
+      zb_tile_filter(st, sa_lcp.p, 0, units.p, nunit, 0, unit_words.p, 2 * ZB_MAX_OFFSET, unit_cnt.p, seg_u, filt_seg.p);
+   }
    const size_t stride = ZB_MAX_OFFSET + tile_main;
    const int wave = 16384;
    const int nw_tiles = std::min(ntile, wave);
@@ -432,21 +527,30 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    zb_match_t *mt = match.p; uint16_t *gl = glen.p, *go = goff.p; const uint32_t *wbs = wbase.p;
    stat_tiles = ntile;
 #ifndef ZB_EMU
-   const size_t smem = (stride + 2) * 4 + (size_t)tile_main * 2 + ((stride + ZB_MAX_MATCH + 7) & ~(size_t)3);
+   const size_t smem = (stride + 2) * 4 + (size_t)tile_main * 2;
+   const size_t smem_txt = (stride + ZB_MAX_MATCH + 7) & ~(size_t)3;
    const ZbWinDesc *wdp = win.p; const uint8_t *Tp = in_ptr;
-   ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_mf_scan_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+   tile_q.need(nw_tiles);
+   uint32_t *tq = tile_q.p;
+   {  /* the limit is a per-function global: always the largest configuration, so concurrent host threads cannot undercut each other */
+      const size_t smax = ((size_t)ZB_MAX_OFFSET + ZB_MF_TILE_MAX + 2) * 4 + (size_t)ZB_MF_TILE_MAX * 2;
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_mf_scan_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+   }
 #else
    tile_pd.need((size_t)nw_tiles * tile_main);
    uint32_t *pdb = tile_pd.p; const ZbWinDesc *wdp = win.p; const uint8_t *Tp = in_ptr;
 #endif
    for (int first = 0; first < ntile; first += wave) {
       const int cnt = std::min(wave, ntile - first);
-      zb_tile_filter(st, unit_words.p, unit_cnt.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p);
+      zb_tile_filter(st, unit_words.p, unit_cnt.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p, seg_t, filt_seg.p);
 #ifndef ZB_EMU
       if (g_zb_prof_on) { zb_tag("mf_scan"); zb_prof_begin(0, st); }
-      zb_mf_scan_k<<<cnt, ZB_MF_THREADS, smem, st>>>(td, first, ivb, stride, tc, mt, gl, go, wbs, wdp, Tp, tile_main);
+      zb_mf_scan_k<<<cnt, ZB_MF_THREADS, smem, st>>>(td, first, ivb, stride, tc, tq, mt, gl, go, wbs, tile_main);
       if (g_zb_prof_on) zb_prof_end(st);
-      g_zb_launches++;
+      if (g_zb_prof_on) { zb_tag("mf_text"); zb_prof_begin(0, st); }
+      zb_mf_text_k<<<cnt, ZB_MT_THREADS, smem_txt, st>>>(td, first, ivb, stride, tq, mt, gl, go, wbs, wdp, Tp);
+      if (g_zb_prof_on) zb_prof_end(st);
+      zb_count_launch(2);
       ZB_CUDA_CHECK(cudaGetLastError());
 #else
       /* host build: same per-position scan, lists in ordinary memory */
@@ -844,6 +948,179 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
       }
    }
 }
+
+/* ---- repair of wrong chunks: the same recurrence, ONE WARP per chain ----
+ * Chunks whose warm-up did not re-synchronise (byte runs, periodic records: the state never forgets the phase it was
+ * started with) have to be redone from their right neighbour's true costs, one after the other.  That is a serial chain,
+ * so what matters is the latency of one position, not throughput: a warp owns the chain, its 260-entry cost ring lives in
+ * shared memory, lanes 0..7 decode one match of the position each, the candidate lengths k = 3.. of the short matches are
+ * spread over the 32 lanes and reduced with redux.sync (min), one reduction per (step, match).  Key = cost << 6 | (63 - k)
+ * so that the larger k wins ties - the first one met going down from the match length, as the reference's loop does
+ * (blockdeflate.c:292-312); matches are then combined in index order on strictly lower cost, literal first.  Control flow
+ * is uniform across the warp.  ~20x lower latency per position than the thread-per-chunk kernel. */
+#define ZB_DW_THREADS 128
+#define ZB_DW_WARPS (ZB_DW_THREADS / 32)
+#define ZB_DW_INF 0x7fffffffu
+
+struct ZbDwShared {            /* per warp */
+   uint16_t ring[ZB_RING];
+   uint32_t rec[32][ZB_NMATCH + 1];   /* match records of the 32 positions of the current block (+1: bank spread) */
+   uint8_t lit[32];
+   ZbCostTab tab;               /* the sub-block's bit costs */
+};
+
+__device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const zb_match_t *__restrict__ match, int lo, int from, int end,
+                                          zb_match_t *__restrict__ best, ZbDwShared &sh, int &slot, const int lane) {
+   int s = slot;
+   if (from <= lo) return;
+   uint16_t *ring = sh.ring;
+   const ZbCostTab &tab = sh.tab;
+   /* length costs of the candidate lengths this lane evaluates: k = 3 + lane and k = 35 + lane */
+   const int lcA = (int)tab.len[lane];
+   const int lcB = lane < 5 ? (int)tab.len[32 + lane] : 0;
+   /* records are fetched a block of 32 positions ahead (DRAM latency is several positions long): lane x holds position i0 - x */
+   uint4 na = make_uint4(0u, 0u, 0u, 0u), nb = na; uint32_t nl = 0;
+   {
+      const int p = from - 1 - lane;
+      if (p >= lo) { const uint4 *q = (const uint4 *)(match + ((size_t)p << 3)); na = __ldg(q); nb = __ldg(q + 1); nl = t[p]; }
+   }
+   for (int i0 = from - 1; i0 >= lo; i0 -= 32) {
+      __syncwarp();
+      sh.rec[lane][0] = na.x; sh.rec[lane][1] = na.y; sh.rec[lane][2] = na.z; sh.rec[lane][3] = na.w;
+      sh.rec[lane][4] = nb.x; sh.rec[lane][5] = nb.y; sh.rec[lane][6] = nb.z; sh.rec[lane][7] = nb.w;
+      sh.lit[lane] = (uint8_t)nl;
+      {
+         const int p = i0 - 32 - lane;
+         if (p >= lo) { const uint4 *q = (const uint4 *)(match + ((size_t)p << 3)); na = __ldg(q); nb = __ldg(q + 1); nl = t[p]; }
+      }
+      __syncwarp();
+      const int nb_pos = i0 - lo + 1 < 32 ? i0 - lo + 1 : 32;
+      uint32_t outw = 0;      /* lane x keeps the choice of position i0 - x: one coalesced store per block */
+      for (int x = 0; x < nb_pos; x++) {
+         const int i = i0 - x;
+         const uint32_t w = lane < ZB_NMATCH ? sh.rec[x][lane] : 0u;
+         const int len0 = (int)(w & 0xffffu), off0 = (int)(w >> 16);
+         const unsigned vm = __ballot_sync(0xffffffffu, len0 >= ZB_MIN_MATCH) & 0xffu;
+         const int M = __ffs((int)~vm) - 1;          /* leading matches with length >= 3 (blockdeflate.c:281) */
+         const int s1 = s;                           /* slot of i+1 */
+         s = s1 + 1; if (s >= ZB_RING) s -= ZB_RING;
+         const uint16_t base = ring[s1];
+         int bestc = (int)tab.lit[sh.lit[x]], bl = 0, bo = 0;
+         if (M) {
+            const int rem = end - i;
+            const int ml0 = len0 < rem ? len0 : rem;
+            const bool v0 = lane < M, lg0 = len0 >= ZB_LEAVE_ALONE;
+            const uint32_t oc0 = v0 ? (uint32_t)tab.off[zb_off_sym((uint32_t)off0)] : 0u;
+            const int K = (int)__reduce_max_sync(0xffffffffu, (v0 && !lg0) ? (unsigned)ml0 : 0u);   /* candidate lengths 3..K */
+            /* per match: clamped length (9 bits) | leave-alone flag | offset cost (6 bits) | offset (16 bits) */
+            const uint32_t infoA = (uint32_t)ml0 | ((lg0 ? 1u : 0u) << 9) | (oc0 << 10) | ((uint32_t)off0 << 16);
+            uint32_t keyA = ZB_DW_INF, keyB = ZB_DW_INF;
+            {
+               const int k = ZB_MIN_MATCH + lane;
+               if (k <= K) {
+                  int idx = s1 - (k - 1); if (idx < 0) idx += ZB_RING;
+                  keyA = ((uint32_t)((int)(int16_t)(uint16_t)(ring[idx] - base) + lcA + 8192) << 6) | (uint32_t)(63 - k);
+               }
+               const int k2 = k + 32;
+               if (k2 <= K) {
+                  int idx = s1 - (k2 - 1); if (idx < 0) idx += ZB_RING;
+                  keyB = ((uint32_t)((int)(int16_t)(uint16_t)(ring[idx] - base) + lcB + 8192) << 6) | (uint32_t)(63 - k2);
+               }
+            }
+#pragma unroll
+            for (int m = 0; m < ZB_NMATCH; m++) {
+               if (m < M) {
+                  const uint32_t inf = __shfl_sync(0xffffffffu, infoA, m);
+                  const int mlm = (int)(inf & 511u), offc = (int)((inf >> 10) & 63u);
+                  int total = 0x7fffffff, kk = 0;
+                  if ((inf >> 9) & 1u) {   /* >= 40: only the full (clamped) length, even below 3 (SURVEY A-3) */
+                     int lidx = mlm - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
+                     int idx = s1 - (mlm - 1); if (idx < 0) idx += ZB_RING;
+                     total = (int)tab.len[lidx] + offc + (int)(int16_t)(uint16_t)(ring[idx] - base);
+                     kk = mlm;
+                  } else if (mlm >= ZB_MIN_MATCH) {
+                     uint32_t c = (ZB_MIN_MATCH + lane <= mlm) ? keyA : ZB_DW_INF;
+                     if (mlm > 34) { const uint32_t c2 = (ZB_MIN_MATCH + 32 + lane <= mlm) ? keyB : ZB_DW_INF; c = c2 < c ? c2 : c; }
+                     c = __reduce_min_sync(0xffffffffu, c);
+                     total = (int)(c >> 6) - 8192 + offc;
+                     kk = 63 - (int)(c & 63u);
+                  }
+                  if (total < bestc) { bestc = total; bl = kk; bo = (int)(inf >> 16); }
+               }
+            }
+         }
+         if (lane == 0) ring[s] = (uint16_t)(base + (uint16_t)bestc);
+         if (lane == x) outw = (uint32_t)bl | ((uint32_t)bo << 16);
+         __syncwarp();
+      }
+      if (lane < nb_pos) ((uint32_t *)best)[i0 - lane] = outw;
+   }
+   slot = s;
+}
+
+/* One warp per run of wrong chunks.  The warp of the run's rightmost chunk (its right neighbour is right) starts from that
+   neighbour's true costs and walks left chunk after chunk, carrying the ring; past the run it goes on for as long as the
+   chunk it enters had assumed other costs than the ones now known, and stops at a chunk another warp owns.  The caller
+   verifies again afterwards, so a race with a neighbouring run costs a round, never correctness. */
+__global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, const uint32_t *badlist, int nbad, const uint8_t *ok,
+                                                                const ZbWinDesc *wd, const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm,
+                                                                int16_t *sgt, int16_t *sgw, int CD) {
+   __shared__ ZbDwShared sh_all[ZB_DW_WARPS];
+   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+   const long g = (long)blockIdx.x * ZB_DW_WARPS + wi;
+   ZbDwShared &sh = sh_all[wi];
+   uint16_t *ring = sh.ring;
+   if (g >= nbad) return;
+   long c = badlist[g];
+   if (!ok[c + 1]) return;       /* not the head of its run: the head's warp will come through */
+   const uint32_t x = dcs[c];
+   const ZbSub s = sb[x];
+   const uint32_t gb = wbs[s.win];
+   const uint8_t *t = T + wd[s.win].in_off;
+   const zb_match_t *m0 = mt + ((size_t)gb << 3);
+   zb_match_t *b0 = bm + gb;
+   const int end = (int)s.pe;
+   int slot = 0;
+   {
+      const uint32_t *src = (const uint32_t *)&tb[x].cost; uint32_t *dstw = (uint32_t *)&sh.tab;
+      for (int e = lane; e < (int)(sizeof(ZbCostTab) / 4); e += 32) dstw[e] = src[e];
+      const int16_t *b = sgt + (size_t)(c + 1) * 260;
+      int16_t *sw = sgw + (size_t)c * 260;
+      for (int e = lane; e < ZB_RING; e += 32) ring[e] = 0;
+      __syncwarp();
+      for (int e = lane; e <= ZB_MAX_MATCH; e += 32) { int sl = slot - e; if (sl < 0) sl += ZB_RING; const int16_t v = b[e]; ring[sl] = (uint16_t)v; sw[e] = v; }
+   }
+   __syncwarp();
+   for (;;) {
+      const int lo = (int)(s.ps + ((uint32_t)c - s.dchunk_base) * CD), hi = lo + CD;
+      zb_dw_run(t, m0, lo, hi, end, b0, sh, slot, lane);
+      /* this chunk's true costs at its start */
+      const uint16_t b = ring[slot];
+      int16_t *sg = sgt + (size_t)c * 260;
+      for (int e = lane; e <= ZB_MAX_MATCH; e += 32) {
+         int sl = slot - e; if (sl < 0) sl += ZB_RING;
+         sg[e] = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
+      }
+      if ((uint32_t)c == s.dchunk_base) break;
+      const long nx = c - 1;
+      if (!ok[nx] && ok[c]) break;   /* c had been right, so nx heads a run of its own: another warp owns it */
+      int16_t *sw = sgw + (size_t)nx * 260;
+      bool same = true;
+      for (int e = lane; e <= ZB_MAX_MATCH; e += 32) {
+         int sl = slot - e; if (sl < 0) sl += ZB_RING;
+         const int16_t v = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
+         if (sw[e] != v) same = false;
+      }
+      same = __all_sync(0xffffffffu, same);
+      if (ok[nx] && same) break;      /* nx was computed from exactly these costs: the run ends here */
+      for (int e = lane; e <= ZB_MAX_MATCH; e += 32) {   /* what chunk nx is now computed from */
+         int sl = slot - e; if (sl < 0) sl += ZB_RING;
+         sw[e] = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
+      }
+      c = nx;
+      __syncwarp();
+   }
+}
 #endif
 
 inline void ZbPipe::stage_parse() {
@@ -894,7 +1171,7 @@ inline void ZbPipe::stage_parse() {
    zb_d2h(st, hc, cn + 4, 8); zb_sync(st);
    const long ndch = hc[0], npch = hc[1];
    dchunk_sub.need(ndch + 1); pchunk_sub.need(npch + 1); best.need(P);
-   sig_true.need((size_t)(ndch + 1) * 260); sig_warm.need((size_t)(ndch + 1) * 260); sig_new.need((size_t)(ndch + 1) * 260); dok.need(ndch + 1);
+   sig_true.need((size_t)(ndch + 1) * 260); sig_warm.need((size_t)(ndch + 1) * 260); sig_new.need((size_t)(ndch + 1) * 260); dok.need(ndch + 1); dbad.need(ndch + 1);
    pentry.need(npch + 1); pbits.need(npch + 1);
    uint32_t *dcs = dchunk_sub.p, *pcs = pchunk_sub.p;
    zb_launch(st, ns, ZB_LAMBDA(long x) {
@@ -903,7 +1180,7 @@ inline void ZbPipe::stage_parse() {
    });
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
    const zb_match_t *mt = match.p; zb_match_t *bm = best.p;
-   int16_t *sgt = sig_true.p, *sgw = sig_warm.p, *sgn = sig_new.p; uint8_t *ok = dok.p;
+   int16_t *sgt = sig_true.p, *sgw = sig_warm.p, *sgn = sig_new.p; uint8_t *ok = dok.p; uint32_t *bad = dbad.p; (void)sgn;
    uint16_t *ex = exitoff.p; uint32_t *pen = pentry.p;
 
    for (int pass = 0; pass < 4; pass++) {
@@ -915,7 +1192,7 @@ inline void ZbPipe::stage_parse() {
          if (g_zb_prof_on) { zb_tag("parse_dp"); zb_prof_begin(0, st); }
          zb_parse_dp_k<<<(unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS), ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, CD, WU);
          if (g_zb_prof_on) zb_prof_end(st);
-         g_zb_launches++;
+         zb_count_launch(1);
          ZB_CUDA_CHECK(cudaGetLastError());
       }
 #else
@@ -973,12 +1250,19 @@ inline void ZbPipe::stage_parse() {
                for (int q = 0; q <= ZB_MAX_MATCH && good; q++) if (a[q] != b[q]) good = 0;
             }
             ok[c] = good;
-            if (!good) zb_atomic_add((int *)cn + 7, 1);
+            if (!good) { const int at = zb_atomic_add((int *)cn + 7, 1); bad[at] = (uint32_t)c; }
          });
          uint32_t nbad = 0;
          zb_d2h(st, &nbad, cn + 7, 4); zb_sync(st);
          if (!nbad) break;
          stat_redo += (int)nbad;
+#ifndef ZB_EMU
+         if (g_zb_prof_on) { zb_tag("parse_repair"); zb_prof_begin(0, st); }
+         zb_parse_fix_k<<<(unsigned)((nbad + ZB_DW_WARPS - 1) / ZB_DW_WARPS), ZB_DW_THREADS, 0, st>>>(sb, tb, dcs, bad, (int)nbad, ok, wd, wbs, T, mt, bm, sgt, sgw, CD);
+         if (g_zb_prof_on) zb_prof_end(st);
+         zb_count_launch(1);
+         ZB_CUDA_CHECK(cudaGetLastError());
+#else
          zb_tag("parse_repair");
          zb_launch(st, ndch, ZB_LAMBDA(long c) {
             if (ok[c]) return;
@@ -1009,6 +1293,7 @@ inline void ZbPipe::stage_parse() {
             int16_t *sg = sgt + (size_t)c * 260; const int16_t *sn = sgn + (size_t)c * 260;
             for (int q = 0; q <= ZB_MAX_MATCH; q++) sg[q] = sn[q];
          });
+#endif
       }
       /* D5: chosen path: exit offsets per path-chunk, serial hop per sub-block */
       zb_launch(st, npch, ZB_LAMBDA(long c) {
@@ -1268,7 +1553,7 @@ inline void ZbPipe::phase_map(uint32_t first_win, uint32_t nw, unsigned long lon
    }
 }
 
-inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams) {
+inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams, uint32_t *ext_words) {
    const int ns = nsub;
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
@@ -1319,14 +1604,17 @@ inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams) {
    });
    zb_d2h(st, h_sout.data(), so, sizeof(ZbStreamOut) * nstr); zb_sync(st);
    /* output area: every stream gets a zeroed, word-aligned span */
-   {
+   if (ext_words) {
+      for (int q = 0; q < nstr; q++) h_sout[q].out_word_off = 0;
+      zb_h2d(st, so, h_sout.data(), sizeof(ZbStreamOut) * nstr);
+   } else {
       uint64_t w = 0;
       for (int q = 0; q < nstr; q++) { h_sout[q].out_word_off = w; w += (h_sout[q].total_bits + 31) / 32 + 2; }
       out.need(w + 4);
       zb_memset(st, out.p, 0, (w + 4) * 4);
       zb_h2d(st, so, h_sout.data(), sizeof(ZbStreamOut) * nstr);
    }
-   uint32_t *ow = out.p;
+   uint32_t *ow = ext_words ? ext_words : out.p;
    /* E4: tokens */
    zb_tag("emit_tokens");
    zb_launch(st, npch, ZB_LAMBDA(long c) {
@@ -1416,11 +1704,11 @@ inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams) {
 inline void ZbPipe::release_all() {
    win.release(); wbase.release(); in.release(); keyA.release(); keyB.release(); valA.release(); valB.release(); rank.release(); sa.release();
    actA.release(); actB.release(); tmpA.release(); tmpB.release(); scratch.release(); sa_lcp.release(); counters.release(); tiles.release();
-   tile_iv.release(); tile_pd.release(); tile_cnt.release(); units.release(); unit_words.release(); unit_cnt.release(); match.release(); glen.release(); goff.release(); exitoff.release(); gentry.release();
+   tile_iv.release(); tile_pd.release(); tile_cnt.release(); tile_q.release(); groups.release(); group_words.release(); group_cnt.release(); filt_seg.release(); units.release(); unit_words.release(); unit_cnt.release(); match.release(); glen.release(); goff.release(); exitoff.release(); gentry.release();
    gtokcnt.release(); gtokbase.release(); tokpos.release(); wtok.release(); wtokbase.release(); wintbase.release(); ph.release();
    gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
    chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();
-   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); pentry.release(); pbits.release(); out.release(); sout.release();
+   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); dbad.release(); pentry.release(); pbits.release(); out.release(); sout.release();
 }
 
 

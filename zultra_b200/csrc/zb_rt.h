@@ -41,7 +41,8 @@ typedef cudaStream_t zb_stream_t;
 #define ZB_DEV __device__
 #define ZB_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "zultra-b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); zb_cuda_fail(e_); } } while (0)
 void zb_cuda_fail(cudaError_t e);
-extern long long g_zb_launches;   /* kernels launched by this library (bench.py reports it) */
+extern long long g_zb_launches;   /* kernels launched by this library (bench.py reports it); several host threads count */
+static inline void zb_count_launch(int n) { __atomic_fetch_add(&g_zb_launches, (long long)n, __ATOMIC_RELAXED); }
 template <class F> __global__ void zb_task_kernel(long n, F f) {
    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
    if (i < n) f(i);
@@ -56,7 +57,7 @@ template <class F> static inline void zb_launch_(int line, zb_stream_t st, long 
    if (g_zb_prof_on) zb_prof_begin(line, st);
    zb_task_kernel<<<(unsigned)((n + blk - 1) / blk), blk, 0, st>>>(n, f);
    if (g_zb_prof_on) zb_prof_end(st);
-   g_zb_launches++;
+   zb_count_launch(1);
    ZB_CUDA_CHECK(cudaGetLastError());
 }
 void *zb_dev_alloc(size_t n);
@@ -93,6 +94,7 @@ size_t zb_scan_scratch_words(long n);
  * (pos-lo)|lcp<<22 words to out + t*stride (count to cnt[t]).  Used twice: window -> 64 Ki-position units -> tiles.
  */
 struct ZbTileDesc { uint32_t win; uint32_t lo, m0, hi; uint64_t src_base; uint32_t src_n; uint32_t src_lo; int32_t src_cnt_idx; uint32_t wlen; };
-void zb_tile_filter(zb_stream_t st, const uint32_t *src, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt);
+void zb_tile_filter(zb_stream_t st, const uint32_t *src, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt,
+                    int nseg /* warps per tile: the source list is cut into that many segments */, uint32_t *seg_scratch /* >= 2 * ntiles * nseg words */);
 
 #endif
