@@ -69,6 +69,8 @@ int zultra_cuda_ctx_create(zultra_cuda_ctx_t **pp, int device) {
       if ((e = getenv("ZULTRA_CUDA_PARSE_CD")) && atoi(e) >= 512) c->pipe.parse_cd = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_PARSE_WU")) && atoi(e) >= 258) c->pipe.parse_wu = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_TILE")) && atoi(e) >= 256) c->tile = (unsigned)atoi(e);
+      if ((e = getenv("ZULTRA_CUDA_TS_MIN")) && atoi(e) >= 1) c->pipe.mf_ts_min = atoi(e);
+      if ((e = getenv("ZULTRA_CUDA_TS_MUL")) && atoi(e) >= 0) c->pipe.mf_ts_mul = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_LANES")) && atoi(e) >= 1 && atoi(e) <= 16) c->nlanes = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_LANE_MIN_BLOCKS")) && atoi(e) >= 1) c->lane_min_blocks = atoi(e);
    }
@@ -149,7 +151,7 @@ static int run_lanes(zultra_cuda_ctx_t *c, int nl, const uint8_t *host_hist, int
       if (dev_in) { ZbStreamIn t = {0, l.hi - l.lo, 0, h, (finalize && l.hi == n) ? 1 : 0, 0, l.ck}; s = t; l.o.dev_in = dev_in + hist_size + l.lo - h; }
       else { ZbStreamIn t = {host_in + l.lo, l.hi - l.lo, k == 0 ? host_hist : host_in + l.lo - h, h, (finalize && l.hi == n) ? 1 : 0, 0, l.ck}; s = t; }
       l.o.phase = 1; l.o.checksum_kind = kind; l.o.tile_main = c->tile;
-      q->pipe.parse_cd = c->pipe.parse_cd; q->pipe.parse_wu = c->pipe.parse_wu;
+      q->pipe.parse_cd = c->pipe.parse_cd; q->pipe.parse_wu = c->pipe.parse_wu; q->pipe.mf_ts_min = c->pipe.mf_ts_min; q->pipe.mf_ts_mul = c->pipe.mf_ts_mul;
       q->pipe.counters.need(64);
       zb_memset(q->pipe.st, q->pipe.counters.p, 0, 64 * 4);
       q->pipe.stat_redo = 0;

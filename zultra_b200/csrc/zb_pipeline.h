@@ -14,6 +14,9 @@
 #include "zb_rt.h"
 #include <vector>
 #include <algorithm>
+#ifndef ZB_EMU
+#include <cuda_pipeline.h>
+#endif
 
 #define ZB_CG 1024        /* positions per greedy-path chunk */
 #define ZB_CP 1024        /* positions per parsed-path chunk */
@@ -110,7 +113,7 @@ struct ZbPipe {
    ZbBuf<ZbTileDesc> tiles, units, groups; ZbBuf<uint32_t> tile_iv, tile_pd, tile_cnt, tile_q, unit_words, unit_cnt, group_words, group_cnt, filt_seg;
    ZbBuf<zb_match_t> match; ZbBuf<uint16_t> glen, goff;
    /* greedy path */
-   ZbBuf<uint16_t> exitoff; ZbBuf<uint32_t> gentry, gtokcnt, gtokbase, tokpos, wtok; /* wtok[w] = tokens of window w; base in wtokbase */
+   ZbBuf<uint16_t> exitoff, exitc; ZbBuf<uint32_t> gentry, gtokcnt, gtokbase, tokpos, wtok; /* wtok[w] = tokens of window w; base in wtokbase */
    ZbBuf<uint32_t> wtokbase, wintbase; ZbBuf<int> ph; /* prefix histograms [interval][ZB_NH] */
    std::vector<uint32_t> h_gchunk_first; ZbBuf<uint32_t> gchunk_first, gchunk_win;
    /* splitter */
@@ -126,6 +129,7 @@ struct ZbPipe {
    int nsub = 0;
    /* stats */
    int parse_cd = ZB_CD, parse_wu = ZB_WU;   /* parse chunk / warm-up positions */
+   int mf_ts_min = ZB_TS_MIN, mf_ts_mul = ZB_TS_MUL;   /* rank walk -> text walk switch (zb_mf_scan) */
    int stat_sa_rounds = 0, stat_redo = 0, stat_ub = 0, stat_tiles = 0;
    double t_stage[8];
 
@@ -274,11 +278,11 @@ inline void ZbPipe::stage_sa() {
    in shared memory.  Walk lengths are heavy-tailed, so lanes do not own fixed positions: a lane that finishes fetches the next
    main position from a shared counter and all 32 lanes keep stepping (same arithmetic as the rank walk of zb_mf_scan, kept
    as a resumable state).  Records go straight to global memory as they are found.  A position whose walk reaches the
-   text-walk condition is handed to kernel B through a queue that reuses the tile's (now dead) global list: two words
-   {m | nm << 13 | moved << 17 | lvl << 18, bound | (i - 1 - best) << 9}. */
+   text-walk condition is handed to kernel B through a queue that reuses the tile's (now dead) global list: three words
+   {m | nm << 13 | moved << 17 | lvl << 18, bound | (i - 1 - best) << 9, first record}. */
 #define ZB_MF_THREADS 1024
 __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *td, int first, uint32_t *lists, size_t stride, const uint32_t *cnts, uint32_t *qcnt,
-                                                              zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, uint32_t tile_main) {
+                                                              zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, uint32_t tile_main, int ts_min, int ts_mul) {
    extern __shared__ uint32_t zb_smw[];
    __shared__ uint32_t next_m, nq;
    const int k = blockIdx.x;
@@ -331,10 +335,11 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
                if (nm == ZB_NMATCH) { fin = true; break; }
             }
             if (l < ZB_MIN_MATCH) { fin = true; break; }
-            if (steps >= ZB_TS_MIN && i - 1 - best <= ZB_TS_MUL * steps) {   /* the rest is cheaper read from the text: kernel B */
+            if (steps >= ts_min && i - 1 - best <= ts_mul * steps) {   /* the rest is cheaper read from the text: kernel B */
                const uint32_t at = atomicAdd(&nq, 1u);
-               queue[2 * at] = m | ((uint32_t)nm << 13) | ((moved ? 1u : 0u) << 17) | (lvl << 18);
-               queue[2 * at + 1] = l | ((uint32_t)(i - 1 - best) << 9);
+               queue[3 * at] = m | ((uint32_t)nm << 13) | ((moved ? 1u : 0u) << 17) | (lvl << 18);
+               queue[3 * at + 1] = l | ((uint32_t)(i - 1 - best) << 9);
+               queue[3 * at + 2] = first_rec;
                busy = false;
                break;
             }
@@ -398,17 +403,21 @@ __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *
    __syncthreads();
    const uint32_t gbase = wbs[t.win];
    const int lane = threadIdx.x & 31;
-   for (;;) {
-      uint32_t e = 0;
+   /* the next task is fetched while the current one runs */
+   uint32_t e = 0, q0 = 0, q1 = 0, q2 = 0;
+   if (lane == 0) e = atomicAdd(&next_q, 1u);
+   e = __shfl_sync(0xffffffffu, e, 0);
+   if (e < nq) { q0 = __ldg(queue + 3 * e); q1 = __ldg(queue + 3 * e + 1); q2 = __ldg(queue + 3 * e + 2); }
+   while (e < nq) {
+      const uint32_t c0 = q0, c1 = q1, c2 = q2;
       if (lane == 0) e = atomicAdd(&next_q, 1u);
       e = __shfl_sync(0xffffffffu, e, 0);
-      if (e >= nq) break;
-      const uint32_t q0 = queue[2 * e], q1 = queue[2 * e + 1];
-      const uint32_t m = q0 & 0x1fffu, lvl = q0 >> 18, bound = q1 & 0x1ffu;
-      int nm = (int)((q0 >> 13) & 15u);
-      const bool moved = (q0 >> 17) & 1u;
+      if (e < nq) { q0 = __ldg(queue + 3 * e); q1 = __ldg(queue + 3 * e + 1); q2 = __ldg(queue + 3 * e + 2); }
+      const uint32_t m = c0 & 0x1fffu, lvl = c0 >> 18, bound = c1 & 0x1ffu;
+      const int nm = (int)((c0 >> 13) & 15u);
+      const bool moved = (c0 >> 17) & 1u;
       const int i = (int)(nlook + m);
-      const int best = i - 1 - (int)(q1 >> 9);
+      const int best = i - 1 - (int)(c1 >> 9);
       const uint32_t k3 = (uint32_t)txt[i] | ((uint32_t)txt[i + 1] << 8) | ((uint32_t)txt[i + 2] << 16);
       uint32_t tr[ZB_NMATCH], curmax = 0;
       int nt = 0;
@@ -441,18 +450,21 @@ __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *
             }
          }
       }
-      if (lane == 0) {
-         const uint32_t p = t.m0 + m;
-         const uint32_t maxlen = t.wlen - p;
-         uint32_t *dst = (uint32_t *)(mt + ((size_t)(gbase + p) << 3));
-         uint32_t first_rec = nm ? dst[0] : 0u;
-#define ZB_MF_EMIT(v_) do { uint32_t v__ = (v_); if ((v__ & 0xffffu) > maxlen) v__ = (v__ & 0xffff0000u) | maxlen; if (nm == 0) first_rec = v__; dst[nm++] = v__; } while (0)
-         /* the pending record of the rank walk stands unless a nearer position reached the same level */
-         if (moved && !(nt && curmax == lvl)) ZB_MF_EMIT(lvl | ((q1 >> 9) + 1u) << 16);
+      /* slots nm.. of the record: [pending record of the rank walk, unless a nearer position reached the same level] then
+         the text-walk records, longest first; lane z writes slot z */
+      const uint32_t p = t.m0 + m;
+      const uint32_t maxlen = t.wlen - p;
+      const bool pend = moved && !(nt && curmax == lvl);
+      const int z = lane - nm - (pend ? 1 : 0);      /* index into tr[] for this lane's slot */
+      uint32_t v = 0;
+      if (pend && lane == nm) v = lvl | (((c1 >> 9) + 1u) << 16);
 #pragma unroll
-         for (int z = 0; z < ZB_NMATCH; z++) if (z < nt && nm < ZB_NMATCH) ZB_MF_EMIT(tr[z]);
-#undef ZB_MF_EMIT
-         for (int z = nm; z < ZB_NMATCH; z++) dst[z] = 0u;
+      for (int y = 0; y < ZB_NMATCH; y++) if (z == y && y < nt) v = tr[y];
+      if ((v & 0xffffu) > maxlen) v = (v & 0xffff0000u) | maxlen;
+      uint32_t *dst = (uint32_t *)(mt + ((size_t)(gbase + p) << 3));
+      if (lane >= nm && lane < ZB_NMATCH) dst[lane] = v;
+      const uint32_t first_rec = nm ? c2 : __shfl_sync(0xffffffffu, v, 0);
+      if (lane == 0) {
          const uint32_t l0 = first_rec & 0xffffu;
          gl[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)l0 : (uint16_t)1;
          go[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)(first_rec >> 16) : (uint16_t)0;
@@ -545,7 +557,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
       zb_tile_filter(st, unit_words.p, unit_cnt.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p, seg_t, filt_seg.p);
 #ifndef ZB_EMU
       if (g_zb_prof_on) { zb_tag("mf_scan"); zb_prof_begin(0, st); }
-      zb_mf_scan_k<<<cnt, ZB_MF_THREADS, smem, st>>>(td, first, ivb, stride, tc, tq, mt, gl, go, wbs, tile_main);
+      zb_mf_scan_k<<<cnt, ZB_MF_THREADS, smem, st>>>(td, first, ivb, stride, tc, tq, mt, gl, go, wbs, tile_main, mf_ts_min, mf_ts_mul);
       if (g_zb_prof_on) zb_prof_end(st);
       if (g_zb_prof_on) { zb_tag("mf_text"); zb_prof_begin(0, st); }
       zb_mf_text_k<<<cnt, ZB_MT_THREADS, smem_txt, st>>>(td, first, ivb, stride, tq, mt, gl, go, wbs, wdp, Tp);
@@ -583,6 +595,119 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    }
 }
 
+#ifndef ZB_EMU
+/* ---- path marking: where the token chain that enters a 1024-position chunk leaves it ----
+ * A chain p -> p + len(p) can only enter a chunk within its first 258 positions, so per chunk a row of 258 exit offsets is
+ * all the hop needs.  Sweep: one thread per chunk, backwards; the exit offsets of the positions behind (<= 258) sit in a
+ * shared-memory ring ([slot][thread]: conflict-free), lengths are read 16 bytes at a time.  MODE 0: greedy path, lengths
+ * from glen (u16), chunks per window.  MODE 1: chosen path, lengths from best[] (< 3 counts as a literal), chunks per
+ * sub-block; pass >= 0 skips static sub-blocks after the first pass. */
+#define ZB_SW_THREADS 64
+#define ZB_SW_RING 288
+#define ZB_EXROW 264          /* u16 per chunk row: 258 used, 528 bytes = 33 x 16 */
+template <int MODE>
+__global__ void __launch_bounds__(ZB_SW_THREADS) zb_sweep_k(long nchunk, const ZbWinDesc *wd, const uint32_t *wbs, const uint32_t *gcf, int nw, uint32_t *gcw,
+                                                            const uint16_t *gl, const ZbSub *sb, const uint32_t *pcs, int pass, const zb_match_t *bm, uint16_t *exc) {
+   __shared__ uint16_t ring_s[ZB_SW_RING * ZB_SW_THREADS];
+   const long c = (long)blockIdx.x * ZB_SW_THREADS + threadIdx.x;
+   if (c >= nchunk) return;
+   uint32_t lo, hi, gb;
+   if (MODE == 0) {
+      const int w = zb_find_win(gcf, nw, (uint32_t)c);
+      gcw[c] = (uint32_t)w;
+      lo = wd[w].hist + (uint32_t)(c - gcf[w]) * ZB_CG;
+      hi = lo + ZB_CG < wd[w].len ? lo + ZB_CG : wd[w].len;
+      gb = wbs[w];
+   } else {
+      const ZbSub s = sb[pcs[c]];
+      if (pass > 0 && !s.is_dyn) return;
+      const uint32_t k = (uint32_t)c - s.pchunk_base;
+      gb = wbs[s.win];
+      lo = s.ps + k * ZB_CP; hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+   }
+   uint16_t *ring = ring_s + threadIdx.x;
+   uint16_t *row = exc + (size_t)c * ZB_EXROW;
+   int idx = (int)((hi - 1 - lo) % ZB_SW_RING) + 1;     /* slot of position p is (p - lo) % ZB_SW_RING; idx = slot(p) + 1 before the step */
+   uint32_t p = hi;
+#define ZB_SW_STEP(len_) do { \
+      uint32_t l_ = (len_);      /* evaluated before p moves: the scalar callers index with p - 1 */ \
+      p--; idx--; if (idx < 0) idx += ZB_SW_RING; \
+      if (MODE == 1 && l_ < ZB_MIN_MATCH) l_ = 1; \
+      const uint32_t j_ = p + l_; \
+      uint32_t e_; \
+      if (j_ >= hi) e_ = j_ - hi; else { int i2_ = idx + (int)l_; if (i2_ >= ZB_SW_RING) i2_ -= ZB_SW_RING; e_ = ring[i2_ * ZB_SW_THREADS]; } \
+      ring[idx * ZB_SW_THREADS] = (uint16_t)e_; \
+      if (p - lo < 258u) row[p - lo] = (uint16_t)e_; \
+   } while (0)
+   if (MODE == 0) {
+      while (p > lo && ((gb + p) & 7u)) ZB_SW_STEP(gl[gb + p - 1]);
+      while (p >= lo + 8) {
+         const uint4 v = __ldg((const uint4 *)(gl + gb + p - 8));
+         ZB_SW_STEP(v.w >> 16); ZB_SW_STEP(v.w & 0xffffu); ZB_SW_STEP(v.z >> 16); ZB_SW_STEP(v.z & 0xffffu);
+         ZB_SW_STEP(v.y >> 16); ZB_SW_STEP(v.y & 0xffffu); ZB_SW_STEP(v.x >> 16); ZB_SW_STEP(v.x & 0xffffu);
+      }
+      while (p > lo) ZB_SW_STEP(gl[gb + p - 1]);
+   } else {
+      while (p > lo && ((gb + p) & 3u)) ZB_SW_STEP(bm[gb + p - 1].length);
+      while (p >= lo + 4) {
+         const uint4 v = *(const uint4 *)(bm + gb + p - 4);
+         ZB_SW_STEP(v.w & 0xffffu); ZB_SW_STEP(v.z & 0xffffu); ZB_SW_STEP(v.y & 0xffffu); ZB_SW_STEP(v.x & 0xffffu);
+      }
+      while (p > lo) ZB_SW_STEP(bm[gb + p - 1].length);
+   }
+#undef ZB_SW_STEP
+}
+
+/* Hop: one warp per window (MODE 0) or sub-block (MODE 1) follows the chain from chunk to chunk; the rows of the next 8
+   chunks are fetched into shared memory (cp.async, double buffered) while lane 0 walks the current 8.  MODE 1 also starts
+   the pass's fresh histogram (blockdeflate.c:887-891; EOB counted here) when pass >= 0. */
+#define ZB_HOP_G 8
+template <int MODE>
+__global__ void __launch_bounds__(32) zb_hop_k(int nunits, const ZbWinDesc *wd, const uint32_t *gcf, const ZbSub *sb, ZbSubTabs *tb, int pass, const uint16_t *exc, uint32_t *ent) {
+   __shared__ __align__(16) uint16_t buf[2][ZB_HOP_G][ZB_EXROW];
+   const int x = blockIdx.x, lane = threadIdx.x;
+   if (x >= nunits) return;
+   uint32_t start, end, cbase, nchunk, clen;
+   if (MODE == 0) { start = wd[x].hist; end = wd[x].len; cbase = gcf[x]; nchunk = gcf[x + 1] - gcf[x]; clen = ZB_CG; }
+   else {
+      const ZbSub s = sb[x];
+      if (pass > 0 && !s.is_dyn) return;
+      start = s.ps; end = s.pe; cbase = s.pchunk_base; nchunk = s.npchunk; clen = ZB_CP;
+      if (pass >= 0 && s.is_dyn) {
+         ZbSubTabs &t = tb[x];
+         for (int i = lane; i < ZB_NLIT; i += 32) t.lcnt[i] = i == ZB_EOB ? 1 : 0;
+         if (lane < ZB_NOFF) t.ocnt[lane] = 0;
+      }
+   }
+   const uint16_t *rows = exc + (size_t)cbase * ZB_EXROW;
+   const int per = ZB_EXROW * 2 / 16;      /* 16-byte pieces per row */
+   auto fetch = [&](uint32_t g0, int b) {
+      const uint32_t ng = nchunk - g0 < ZB_HOP_G ? nchunk - g0 : ZB_HOP_G;
+      for (int q = lane; q < (int)ng * per; q += 32)
+         __pipeline_memcpy_async((char *)&buf[b][0][0] + (size_t)q * 16, (const char *)(rows + (size_t)g0 * ZB_EXROW) + (size_t)q * 16, 16);
+      __pipeline_commit();
+   };
+   uint32_t e = start;
+   if (nchunk) fetch(0, 0);
+   int b = 0;
+   for (uint32_t g0 = 0; g0 < nchunk; g0 += ZB_HOP_G, b ^= 1) {
+      if (g0 + ZB_HOP_G < nchunk) { fetch(g0 + ZB_HOP_G, b ^ 1); __pipeline_wait_prior(1); }
+      else __pipeline_wait_prior(0);
+      __syncwarp();
+      if (lane == 0) {
+         const uint32_t ng = nchunk - g0 < ZB_HOP_G ? nchunk - g0 : ZB_HOP_G;
+         for (uint32_t k = 0; k < ng; k++) {
+            const uint32_t lo = start + (g0 + k) * clen, hi = lo + clen < end ? lo + clen : end;
+            ent[cbase + g0 + k] = e;
+            if (e < hi) e = hi + buf[b][k][e - lo];
+         }
+      }
+      e = __shfl_sync(0xffffffffu, e, 0);
+      __syncwarp();
+   }
+}
+#endif
+
 /* ============================================================ greedy path ============================================================
  * The greedy parse of blockdeflate.c:333-361 / :684-703 takes match[i][0] whenever its length is >= 3.  All
  * greedy walks inside a window are segments of the one path from the block start (SURVEY A-14), so the path
@@ -595,11 +720,28 @@ inline void ZbPipe::stage_greedy() {
    const long nch = h_gchunk_first[nwin];
    gchunk_first.need(nwin + 1); gchunk_win.need(nch);
    zb_h2d(st, gchunk_first.p, h_gchunk_first.data(), 4 * (nwin + 1));
-   exitoff.need(P); gentry.need(nch + 1); gtokcnt.need(nch + 1); gtokbase.need(nch + 1); tokpos.need(P);
+#ifdef ZB_EMU
+   exitoff.need(P);
+#endif
+   gentry.need(nch + 1); gtokcnt.need(nch + 1); gtokbase.need(nch + 1); tokpos.need(P);
    wtokbase.need(nwin + 1); wintbase.need(nwin + 1);
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p, *gcf = gchunk_first.p; const int nw = nwin;
    uint32_t *gcw = gchunk_win.p; uint16_t *ex = exitoff.p; const uint16_t *gl = glen.p;
    uint32_t *ent = gentry.p, *tcnt = gtokcnt.p, *tbase = gtokbase.p, *tp = tokpos.p;
+#ifndef ZB_EMU
+   exitc.need((size_t)(nch + 1) * ZB_EXROW);
+   if (nch > 0) {
+      if (g_zb_prof_on) { zb_tag("path_sweep"); zb_prof_begin(0, st); }
+      zb_sweep_k<0><<<(unsigned)((nch + ZB_SW_THREADS - 1) / ZB_SW_THREADS), ZB_SW_THREADS, 0, st>>>(nch, wd, wbs, gcf, nw, gcw, gl, 0, 0, -1, 0, exitc.p);
+      if (g_zb_prof_on) zb_prof_end(st);
+      if (g_zb_prof_on) { zb_tag("path_hop"); zb_prof_begin(0, st); }
+      zb_hop_k<0><<<nwin, 32, 0, st>>>(nwin, wd, gcf, 0, 0, -1, exitc.p, ent);
+      if (g_zb_prof_on) zb_prof_end(st);
+      zb_count_launch(2);
+      ZB_CUDA_CHECK(cudaGetLastError());
+   }
+   (void)ex;
+#else
    zb_launch(st, nch, ZB_LAMBDA(long c) {
       int w = zb_find_win(gcf, nw, (uint32_t)c);
       gcw[c] = (uint32_t)w;
@@ -621,6 +763,7 @@ inline void ZbPipe::stage_greedy() {
          if (e < hi) e = hi + ex[gb + e];
       }
    });
+#endif
    zb_launch(st, nch, ZB_LAMBDA(long c) {
       const uint32_t w = gcw[c];
       const uint32_t lo = wd[w].hist + (uint32_t)(c - gcf[w]) * ZB_CG;
@@ -909,11 +1052,85 @@ ZB_HD void zb_walk_best(const zb_match_t *best, uint32_t entry, uint32_t hi, F &
  * The 260-entry cost ring of every thread lives in shared memory ([slot][thread], so a warp's accesses fall into
  * distinct banks up to the 2-way u16 pairing); match records are fetched one position ahead (zb_parse_range). */
 #define ZB_DP_THREADS 64
+/* zb_parse_range for the thread-per-chunk kernel, same choices, fewer instructions in the candidate loop: the ring is walked
+   with a pointer (slot stride = ZB_DP_THREADS), the wrap is taken out of the loop (two straight segments), and the bit costs
+   come from a shared-memory copy of the sub-block's table when the chunk belongs to the CTA's first sub-block (almost
+   always; otherwise the same pointers address global memory). */
+__device__ __forceinline__ void zb_parse_range_dev(const uint8_t *__restrict__ T, const zb_match_t *__restrict__ match, const uint8_t *plit, const uint8_t *plen,
+                                                   const uint8_t *poff, int lo, int from, int end, int keep_hi, zb_match_t *__restrict__ best, uint16_t *ring0, int &slot) {
+   const int NT = ZB_DP_THREADS;
+   int s = slot;
+   if (from - 1 < lo) return;
+   ZbMatchRec nxt = zb_load_rec(match, from - 1);
+   uint32_t nlit = T[from - 1];
+   for (int i = from - 1; i >= lo; i--) {
+      const ZbMatchRec rec = nxt;
+      const uint32_t lit = nlit;
+      if (i - 1 >= lo) { nxt = zb_load_rec(match, i - 1); nlit = T[i - 1]; }
+      const int s1 = s;
+      s = s1 + 1; if (s >= ZB_RING) s -= ZB_RING;
+      const uint32_t base = ring0[s1 * NT];
+      int bestc = plit[lit];
+      int bestlen = 0, bestoff = 0;
+      int M = 0;
+#pragma unroll
+      for (int m = 0; m < ZB_NMATCH; m++) if (M == m && (rec.w[m] & 0xffffu) >= ZB_MIN_MATCH) M = m + 1;
+      if (M) {
+         int bt = 0x7fffffff, bl = 0, bo = 0;
+         int k = ZB_MIN_MATCH, curmin = 0x7fffffff, curk = 0;
+         int q = s1 - (ZB_MIN_MATCH - 1); if (q < 0) q += ZB_RING;   /* slot of i+3 */
+         const uint16_t *pr = ring0 + q * NT;                          /* slot of i+k, moving down by NT per k */
+         int kw = k + q + 1;                                           /* first k whose slot wraps */
+#pragma unroll
+         for (int m = ZB_NMATCH - 1; m >= 0; m--) {
+            if (m < M) {
+               const int mlen0 = (int)(rec.w[m] & 0xffffu), moff = (int)(rec.w[m] >> 16);
+               const int offc = poff[zb_off_sym((uint32_t)moff)];
+               int ml = mlen0;
+               if (i + ml > end) ml = end - i;
+               int total, kk;
+               if (mlen0 >= ZB_LEAVE_ALONE) {
+                  int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING;
+                  int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
+                  total = plen[lidx] + offc + (int)(int16_t)(uint16_t)(ring0[sl * NT] - base);
+                  kk = ml;
+               } else {
+                  while (k <= ml) {
+                     const int kstop = ml < kw - 1 ? ml : kw - 1;
+#pragma unroll 2
+                     for (; k <= kstop; k++, pr -= NT) {
+                        const int c = (int)plen[k - ZB_MIN_MATCH] + (int)(int16_t)(uint16_t)((uint32_t)*pr - base);
+                        if (c <= curmin) { curmin = c; curk = k; }
+                     }
+                     if (k == kw) { pr += ZB_RING * NT; kw += ZB_RING; }
+                  }
+                  total = curk ? curmin + offc : 0x7fffffff;
+                  kk = curk;
+               }
+               if (total <= bt && total != 0x7fffffff) { bt = total; bl = kk; bo = moff; }
+            }
+         }
+         if (bt < bestc) { bestc = bt; bestlen = bl; bestoff = bo; }
+      }
+      ring0[s * NT] = (uint16_t)(base + (uint32_t)bestc);
+      if (i < keep_hi) { zb_match_t o; o.length = (uint16_t)bestlen; o.offset = (uint16_t)bestoff; best[i] = o; }
+   }
+   slot = s;
+}
+
 __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
                                                                const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw,
                                                                int CD, int WU) {
    __shared__ uint16_t ring_s[ZB_RING * ZB_DP_THREADS];
-   const long c = (long)blockIdx.x * ZB_DP_THREADS + threadIdx.x;
+   __shared__ ZbCostTab tab_s;
+   const long c0 = (long)blockIdx.x * ZB_DP_THREADS;
+   const long c = c0 + threadIdx.x;
+   const uint32_t x0 = dcs[c0];         /* c0 < ndch by the grid size */
+   {
+      const uint32_t *src = (const uint32_t *)&tb[x0].cost; uint32_t *dstw = (uint32_t *)&tab_s;
+      for (int e = threadIdx.x; e < (int)(sizeof(ZbCostTab) / 4); e += ZB_DP_THREADS) dstw[e] = src[e];
+   }
+   __syncthreads();
    if (c >= ndch) return;
    const uint32_t x = dcs[c];
    const ZbSub s = sb[x];
@@ -928,8 +1145,9 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
    ZbRingStrided ring = {ring_s + threadIdx.x, ZB_DP_THREADS};
    for (int i = 0; i < ZB_RING; i++) ring.set(i, 0);
    int slot = 0;
-   const ZbCostTab &ct = tb[x].cost;
-   if (from > hi) zb_parse_range(t, mt + ((size_t)gb << 3), ct, hi, from, end, hi, bm + gb, ring, slot);
+   const ZbCostTab *ct = x == x0 ? &tab_s : &tb[x].cost;
+   const uint8_t *plit = ct->lit, *plen = ct->len, *poff = ct->off;
+   if (from > hi) zb_parse_range_dev(t, mt + ((size_t)gb << 3), plit, plen, poff, hi, from, end, hi, bm + gb, ring_s + threadIdx.x, slot);
    {
       int16_t *sw = sgw + (size_t)c * 260;
       const uint16_t b = ring.get(slot);
@@ -938,7 +1156,7 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
          sw[q] = (hi + q <= end && hi + q <= from) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
       }
    }
-   zb_parse_range(t, mt + ((size_t)gb << 3), ct, lo, hi, end, hi, bm + gb, ring, slot);
+   zb_parse_range_dev(t, mt + ((size_t)gb << 3), plit, plen, poff, lo, hi, end, hi, bm + gb, ring_s + threadIdx.x, slot);
    {
       int16_t *sg = sgt + (size_t)c * 260;
       const uint16_t b = ring.get(slot);
@@ -1173,6 +1391,9 @@ inline void ZbPipe::stage_parse() {
    dchunk_sub.need(ndch + 1); pchunk_sub.need(npch + 1); best.need(P);
    sig_true.need((size_t)(ndch + 1) * 260); sig_warm.need((size_t)(ndch + 1) * 260); sig_new.need((size_t)(ndch + 1) * 260); dok.need(ndch + 1); dbad.need(ndch + 1);
    pentry.need(npch + 1); pbits.need(npch + 1);
+#ifndef ZB_EMU
+   exitc.need((size_t)(npch + 1) * ZB_EXROW);
+#endif
    uint32_t *dcs = dchunk_sub.p, *pcs = pchunk_sub.p;
    zb_launch(st, ns, ZB_LAMBDA(long x) {
       for (uint32_t k = 0; k < sb[x].ndchunk; k++) dcs[sb[x].dchunk_base + k] = (uint32_t)x;
@@ -1296,6 +1517,19 @@ inline void ZbPipe::stage_parse() {
 #endif
       }
       /* D5: chosen path: exit offsets per path-chunk, serial hop per sub-block */
+#ifndef ZB_EMU
+      if (npch > 0) {
+         if (g_zb_prof_on) { zb_tag("path_sweep"); zb_prof_begin(0, st); }
+         zb_sweep_k<1><<<(unsigned)((npch + ZB_SW_THREADS - 1) / ZB_SW_THREADS), ZB_SW_THREADS, 0, st>>>(npch, wd, wbs, 0, 0, 0, 0, sb, pcs, pass, bm, exitc.p);
+         if (g_zb_prof_on) zb_prof_end(st);
+         if (g_zb_prof_on) { zb_tag("path_hop"); zb_prof_begin(0, st); }
+         zb_hop_k<1><<<ns, 32, 0, st>>>(ns, wd, 0, sb, tb, pass, exitc.p, pen);
+         if (g_zb_prof_on) zb_prof_end(st);
+         zb_count_launch(2);
+         ZB_CUDA_CHECK(cudaGetLastError());
+      }
+      (void)ex;
+#else
       zb_launch(st, npch, ZB_LAMBDA(long c) {
          const ZbSub s = sb[pcs[c]];
          if (pass > 0 && !s.is_dyn) return;
@@ -1325,6 +1559,7 @@ inline void ZbPipe::stage_parse() {
             t.lcnt[ZB_EOB] = 1;
          }
       });
+#endif
       /* D6: histogram along the chosen path (blockdeflate.c:371-400) */
       zb_launch(st, npch, ZB_LAMBDA(long c) {
          const uint32_t x = pcs[c];
@@ -1487,6 +1722,19 @@ inline void ZbPipe::stage_emit_prepare() {
       uint32_t v; zb_d2h(st, &v, cn + 5, 4); zb_sync(st); npch = v;
    }
    /* path again (the post-optimiser turned some matches into literals) */
+#ifndef ZB_EMU
+   if (npch > 0) {
+      if (g_zb_prof_on) { zb_tag("path_sweep"); zb_prof_begin(0, st); }
+      zb_sweep_k<1><<<(unsigned)((npch + ZB_SW_THREADS - 1) / ZB_SW_THREADS), ZB_SW_THREADS, 0, st>>>(npch, wd, wbs, 0, 0, 0, 0, sb, pcs, -1, bm, exitc.p);
+      if (g_zb_prof_on) zb_prof_end(st);
+      if (g_zb_prof_on) { zb_tag("path_hop"); zb_prof_begin(0, st); }
+      zb_hop_k<1><<<ns, 32, 0, st>>>(ns, wd, 0, sb, tb, -1, exitc.p, pen);
+      if (g_zb_prof_on) zb_prof_end(st);
+      zb_count_launch(2);
+      ZB_CUDA_CHECK(cudaGetLastError());
+   }
+   (void)ex;
+#else
    zb_launch(st, npch, ZB_LAMBDA(long c) {
       const ZbSub s = sb[pcs[c]];
       const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
@@ -1507,6 +1755,7 @@ inline void ZbPipe::stage_emit_prepare() {
          if (e < hi) e = hi + ex[gb + e];
       }
    });
+#endif
    /* E1: token bits per chunk */
    zb_launch(st, npch, ZB_LAMBDA(long c) {
       const uint32_t x = pcs[c];
@@ -1704,7 +1953,7 @@ inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams, u
 inline void ZbPipe::release_all() {
    win.release(); wbase.release(); in.release(); keyA.release(); keyB.release(); valA.release(); valB.release(); rank.release(); sa.release();
    actA.release(); actB.release(); tmpA.release(); tmpB.release(); scratch.release(); sa_lcp.release(); counters.release(); tiles.release();
-   tile_iv.release(); tile_pd.release(); tile_cnt.release(); tile_q.release(); groups.release(); group_words.release(); group_cnt.release(); filt_seg.release(); units.release(); unit_words.release(); unit_cnt.release(); match.release(); glen.release(); goff.release(); exitoff.release(); gentry.release();
+   tile_iv.release(); tile_pd.release(); tile_cnt.release(); tile_q.release(); groups.release(); group_words.release(); group_cnt.release(); filt_seg.release(); units.release(); unit_words.release(); unit_cnt.release(); match.release(); glen.release(); goff.release(); exitoff.release(); exitc.release(); gentry.release();
    gtokcnt.release(); gtokbase.release(); tokpos.release(); wtok.release(); wtokbase.release(); wintbase.release(); ph.release();
    gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
    chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();

@@ -199,14 +199,21 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_k(const uint64_t *keys, lo
    hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
+/* One tile (2048 pairs) per CTA: rank every pair inside the tile (warp-level match.any, per-warp digit counters), move the
+   pairs to their tile-local sorted place in shared memory, then write them out: pairs of one digit are consecutive there,
+   so the global stores go out in runs instead of 32 scattered 8-byte writes per warp (the L2 sector rate was the limit). */
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_k(const uint64_t *kin, const uint32_t *vin, uint64_t *kout, uint32_t *vout, long n,
                                                           int shift, uint32_t mask, const uint32_t *hist_scanned, int ntiles) {
    __shared__ uint32_t cnt[RS_WARPS][256];
-   __shared__ uint32_t gbase[256];
+   __shared__ uint32_t gbase[256];      /* global start of this tile's run of digit d, minus the run's tile-local start */
+   __shared__ uint32_t dstart[256];
+   __shared__ uint64_t skey[RS_TILE];
+   __shared__ uint32_t sval[RS_TILE];
+   __shared__ uint32_t wsum[RS_WARPS];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
    for (int w = 0; w < RS_WARPS; w++) cnt[w][tid] = 0;
-   gbase[tid] = hist_scanned[(size_t)tid * ntiles + blockIdx.x];
+   const uint32_t gb = hist_scanned[(size_t)tid * ntiles + blockIdx.x];
    __syncthreads();
    const long base = (long)blockIdx.x * RS_TILE + (long)warp * (32 * RS_ITEMS);
    uint64_t key[RS_ITEMS];
@@ -218,6 +225,11 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_k(const uint64_t *kin, 
       const bool valid = idx < n;
       key[k] = valid ? kin[idx] : 0;
       val[k] = valid ? vin[idx] : 0;
+   }
+#pragma unroll
+   for (int k = 0; k < RS_ITEMS; k++) {
+      const long idx = base + k * 32 + lane;
+      const bool valid = idx < n;
       const uint32_t d = valid ? ((uint32_t)(key[k] >> shift) & mask) : 0xffffffffu;
       const uint32_t peers = __match_any_sync(0xffffffffu, d);
       const uint32_t pre = __popc(peers & lt);
@@ -229,20 +241,42 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_k(const uint64_t *kin, 
       __syncwarp();
    }
    __syncthreads();
-   {
-      uint32_t acc = 0;
+   /* digit tid: exclusive prefix over the warps, tile total, then exclusive scan of the totals over the digits */
+   uint32_t tot = 0;
 #pragma unroll
-      for (int w = 0; w < RS_WARPS; w++) { uint32_t t = cnt[w][tid]; cnt[w][tid] = acc; acc += t; }
-   }
+   for (int w = 0; w < RS_WARPS; w++) { uint32_t t = cnt[w][tid]; cnt[w][tid] = tot; tot += t; }
+   uint32_t inc = tot;
+#pragma unroll
+   for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+   if (lane == 31) wsum[warp] = inc;
+   __syncthreads();
+   uint32_t woff = 0;
+#pragma unroll
+   for (int w = 0; w < RS_WARPS; w++) if (w < warp) woff += wsum[w];
+   const uint32_t ds = woff + inc - tot;
+   dstart[tid] = ds;
+   gbase[tid] = gb - ds;
    __syncthreads();
 #pragma unroll
    for (int k = 0; k < RS_ITEMS; k++) {
       const long idx = base + k * 32 + lane;
       if (idx < n) {
          const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
-         const size_t dst = (size_t)gbase[d] + cnt[warp][d] + rk[k];
-         kout[dst] = key[k];
-         vout[dst] = val[k];
+         const uint32_t lp = dstart[d] + cnt[warp][d] + rk[k];
+         skey[lp] = key[k]; sval[lp] = val[k];
+      }
+   }
+   __syncthreads();
+   const long tile_n = n - (long)blockIdx.x * RS_TILE < RS_TILE ? n - (long)blockIdx.x * RS_TILE : RS_TILE;
+#pragma unroll
+   for (int k = 0; k < RS_ITEMS; k++) {
+      const int e = k * RS_THREADS + tid;
+      if (e < tile_n) {
+         const uint64_t kk = skey[e];
+         const uint32_t d = (uint32_t)(kk >> shift) & mask;
+         const size_t dst = (size_t)(uint32_t)(gbase[d] + (uint32_t)e);   /* 32-bit wrap: gbase holds start - local start */
+         kout[dst] = kk;
+         vout[dst] = sval[e];
       }
    }
 }
