@@ -54,6 +54,9 @@ void zb_prof_begin(int line, cudaStream_t st);
 void zb_prof_end(cudaStream_t st);
 template <class F> static inline void zb_launch_(int line, zb_stream_t st, long n, F f, int blk = 128) {
    if (n <= 0) { zb_tag(0); return; }
+   /* few tasks are the serial per-sub-block / per-node ones (Huffman builds, splitter scans): give each its own warp, so that
+      32 unrelated control flows do not serialise inside one, and its own SM share instead of crowding two SMs */
+   if (n <= 4096) blk = 1;
    if (g_zb_prof_on) zb_prof_begin(line, st);
    zb_task_kernel<<<(unsigned)((n + blk - 1) / blk), blk, 0, st>>>(n, f);
    if (g_zb_prof_on) zb_prof_end(st);
