@@ -240,12 +240,11 @@ int zultra_cuda_compress_blocks(zultra_cuda_ctx_t *c, const unsigned char *hist,
    ZbStreamIn s = {in, n, hist, (uint32_t)hist_size, finalize, in_bits, checksum ? *checksum : 0};
    ZbRunOpts o;
    o.checksum_kind = (flags & 2) ? 2 : ((flags & 1) ? 1 : 0);
+   o.host_out = out; o.host_out_cap = out_cap;
    std::vector<ZbStreamRes> res;
    rc = run_one(c, s, clamp_block(block), o, res);
-   if (rc == 0) {
-      if (c->out.size() > out_cap) rc = ZULTRA_CUDA_ERR_DST;
-      else { memcpy(out, c->out.data(), c->out.size()); *out_bits = res[0].total_bits; if (checksum) *checksum = res[0].checksum; }
-   } else rc = ZULTRA_CUDA_ERR_CUDA;
+   if (rc == 0) { *out_bits = res[0].total_bits; if (checksum) *checksum = res[0].checksum; }
+   else rc = rc == -2 ? ZULTRA_CUDA_ERR_DST : ZULTRA_CUDA_ERR_CUDA;
    return ctx_leave(c, rc);
 }
 

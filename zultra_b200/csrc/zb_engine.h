@@ -28,6 +28,7 @@ struct ZbRunOpts {
    int phase = 3;                  /* 1 = stop after the phase-independent part (shards), 2 = only finish, 3 = both */
    unsigned long long phase_bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
    uint8_t *dev_out = 0; size_t dev_out_cap = 0;   /* leave the bitstream of stream 0 in device memory instead of copying back */
+   uint8_t *host_out = 0; size_t host_out_cap = 0; /* single stream: copy the bitstream straight into the caller's buffer (no staging vector) */
    ZbDump *dump = 0;
    int stop_after = 99;            /* 1 = SA, 2 = match (stage dumps) */
    float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* h2d, sa, match, greedy+split, parse, emit, d2h, total */
@@ -132,7 +133,12 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
       } else {
          size_t total_words = 0;
          for (int i = 0; i < ns; i++) total_words = std::max<size_t>(total_words, p.h_sout[i].out_word_off + (p.h_sout[i].total_bits + 31) / 32);
-         if (ns == 1) {   /* straight into the result vector */
+         if (ns == 1 && o.host_out) {   /* straight into the caller's buffer */
+            if (ob > o.host_out_cap) return -2;
+            zb_d2h(p.st, o.host_out, p.out.p, ob);
+            zb_sync(p.st);
+            out.clear();
+         } else if (ns == 1) {   /* straight into the result vector */
             out.resize(total_words * 4 + 4);
             zb_d2h(p.st, out.data(), p.out.p, total_words * 4);
             zb_sync(p.st);

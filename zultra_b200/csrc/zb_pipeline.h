@@ -128,7 +128,7 @@ struct ZbPipe {
    std::vector<ZbStreamOut> h_sout;
    int nsub = 0;
    /* stats */
-   int parse_cd = ZB_CD, parse_wu = ZB_WU;   /* parse chunk / warm-up positions */
+   int parse_cd = 0, parse_wu = ZB_WU;   /* parse chunk (0 = by batch size, see stage_parse) / warm-up positions */
    int mf_ts_min = ZB_TS_MIN, mf_ts_mul = ZB_TS_MUL;   /* rank walk -> text walk switch (zb_mf_scan) */
    int stat_sa_rounds = 0, stat_redo = 0, stat_ub = 0, stat_tiles = 0;
    double t_stage[8];
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
                if (nm == ZB_NMATCH) { fin = true; break; }
             }
             if (l < ZB_MIN_MATCH) { fin = true; break; }
-            if (steps >= ts_min && i - 1 - best <= ts_mul * steps) {   /* the rest is cheaper read from the text: kernel B */
+            if ((steps & 1) == 0 && steps >= ts_min && i - 1 - best <= ts_mul * steps) {   /* the rest is cheaper read from the text: kernel B */
                const uint32_t at = atomicAdd(&nq, 1u);
                queue[3 * at] = m | ((uint32_t)nm << 13) | ((moved ? 1u : 0u) << 17) | (lvl << 18);
                queue[3 * at + 1] = l | ((uint32_t)(i - 1 - best) << 9);
@@ -1342,7 +1342,11 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
 #endif
 
 inline void ZbPipe::stage_parse() {
-   const int CD = parse_cd, WU = parse_wu;
+   /* One thread per chunk: the chunk count is the parallelism.  ZB_CD positions per chunk when that still gives ~40 K chunks,
+      shorter chunks (more warm-up overhead, shorter serial chains) for small batches such as one GPU's shard of a stream. */
+   int cd_auto = ZB_CD;
+   while (cd_auto > 512 && (long)P / cd_auto < 40000) cd_auto >>= 1;
+   const int CD = parse_cd ? parse_cd : cd_auto, WU = parse_wu;
    const int ns = nsub;
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
    ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in_ptr, win.p};
