@@ -278,27 +278,87 @@ inline void ZbPipe::stage_sa() {
    in shared memory.  Walk lengths are heavy-tailed, so lanes do not own fixed positions: a lane that finishes fetches the next
    main position from a shared counter and all 32 lanes keep stepping (same arithmetic as the rank walk of zb_mf_scan, kept
    as a resumable state).  Records go straight to global memory as they are found.  A position whose walk reaches the
-   text-walk condition is handed to kernel B through a queue that reuses the tile's (now dead) global list: three words
+   text-walk condition is handed to kernel B through a per-tile queue in global memory: three words
    {m | nm << 13 | moved << 17 | lvl << 18, bound | (i - 1 - best) << 9, first record}. */
 #define ZB_MF_THREADS 1024
-__global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *td, int first, uint32_t *lists, size_t stride, const uint32_t *cnts, uint32_t *qcnt,
-                                                              zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, uint32_t tile_main, int ts_min, int ts_mul) {
+__global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *td, int first, const uint32_t *unit_words, const uint32_t *unit_cnt, uint32_t *queues, size_t qstride,
+                                                              size_t stride, uint32_t *qcnt, zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, uint32_t tile_main,
+                                                              int ts_min, int ts_mul) {
    extern __shared__ uint32_t zb_smw[];
-   __shared__ uint32_t next_m, nq;
+   __shared__ uint32_t next_m, nq, wcnt[32], wtail[32];
    const int k = blockIdx.x;
    const ZbTileDesc t = td[first + k];
-   const int n = (int)cnts[k];
    const uint32_t nlook = t.m0 - t.lo, nmain = t.hi - t.m0;
    uint32_t *words = zb_smw + 1;          /* words[-1] and words[n] are LCP-0 sentinels: no bounds tests in the walk */
    uint16_t *rom = (uint16_t *)(zb_smw + stride + 2);
-   uint32_t *queue = lists + (size_t)k * stride;
-   if (threadIdx.x == 0) { next_m = 0; nq = 0; zb_smw[0] = 0; words[n] = 0; }
-   for (int e = threadIdx.x; e < n; e += blockDim.x) {
-      const uint32_t w = queue[e];
-      words[e] = w;
-      const uint32_t p = w & ZB_POS_MASK;
-      if (p >= nlook) rom[p - nlook] = (uint16_t)e;
+   uint32_t *queue = queues + (size_t)k * qstride;
+   /* The tile's suffix list is filtered out of its unit's list while it is loaded (the last filter level, fused): rank order
+      kept, the LCP min-reduced over the skipped entries.  1024 entries per step: ballot compaction and a segmented shuffle
+      min-scan inside each warp, counts and trailing minima of the 32 warps combined through shared memory. */
+   int n = 0;
+   {
+      const uint32_t *src = unit_words + t.src_base;
+      const uint32_t nsrc = unit_cnt[t.src_cnt_idx];
+      const uint32_t lo_rel = t.lo - t.src_lo, span = t.hi - t.lo;
+      const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+      const uint32_t lt = (1u << lane) - 1u;
+      uint32_t count = 0, carry = 0x1ffu;
+      /* 4 x 1024 entries are in flight per thread group: the loads of the next group are issued before this one is processed */
+      uint32_t wn[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) { const uint32_t r = (uint32_t)j * ZB_MF_THREADS + threadIdx.x; wn[j] = r < nsrc ? __ldg(src + r) : 0u; }
+      for (uint32_t g0 = 0; g0 < nsrc; g0 += 4 * ZB_MF_THREADS) {
+      uint32_t wc[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) { wc[j] = wn[j]; const uint32_t r = g0 + (uint32_t)(4 + j) * ZB_MF_THREADS + threadIdx.x; wn[j] = r < nsrc ? __ldg(src + r) : 0u; }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+         const uint32_t r0 = g0 + (uint32_t)j * ZB_MF_THREADS;
+         if (r0 >= nsrc) break;
+         const uint32_t r = r0 + threadIdx.x;
+         const bool valid = r < nsrc;
+         const uint32_t w = wc[j];
+         const uint32_t pos = (w & ZB_POS_MASK) - lo_rel;
+         uint32_t v = valid ? ((w >> ZB_POS_BITS) & 0x1ffu) : 0x1ffu;
+         const bool keep = valid && pos < span;
+         const uint32_t kmask = __ballot_sync(0xffffffffu, keep);
+         const uint32_t below = kmask & lt;
+         const int start = below ? (32 - __clz((int)below)) : 0;
+#pragma unroll
+         for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+            if (lane >= start + d) v = min(v, o);
+         }
+         const uint32_t v31 = __shfl_sync(0xffffffffu, v, 31);
+         if (lane == 0) { wcnt[warp] = __popc(kmask); wtail[warp] = ((kmask >> 31) ? 0x1ffu : v31) | (kmask ? 0x10000u : 0u); }
+         __syncthreads();
+         /* every warp: exclusive count of the warps before it, the minimum carried into it, and the step's totals */
+         const uint32_t cx = wcnt[lane], tx = wtail[lane];
+         uint32_t inc = cx;
+#pragma unroll
+         for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+         const uint32_t prefix = __shfl_sync(0xffffffffu, inc - cx, warp), total = __shfl_sync(0xffffffffu, inc, 31);
+         const uint32_t hasmask = __ballot_sync(0xffffffffu, (tx >> 16) & 1u);
+         const uint32_t hb = hasmask & ((1u << warp) - 1u);
+         const int lo_u = hb ? 31 - __clz((int)hb) : 0;
+         uint32_t cin = __reduce_min_sync(0xffffffffu, (lane >= lo_u && lane < warp) ? (tx & 0xffffu) : 0x1ffu);
+         if (!hb) cin = min(cin, carry);
+         const int lo_2 = hasmask ? 31 - __clz((int)hasmask) : 0;
+         uint32_t cnew = __reduce_min_sync(0xffffffffu, lane >= lo_2 ? (tx & 0xffffu) : 0x1ffu);
+         if (!hasmask) cnew = min(cnew, carry);
+         if (start == 0) v = min(v, cin);
+         if (keep) {
+            const uint32_t at = count + prefix + __popc(below);
+            words[at] = pos | (v << ZB_POS_BITS);
+            if (pos >= nlook) rom[pos - nlook] = (uint16_t)at;
+         }
+         count += total; carry = cnew;
+         __syncthreads();
+      }
+      }
+      n = (int)count;
    }
+   if (threadIdx.x == 0) { next_m = 0; nq = 0; zb_smw[0] = 0; words[n] = 0; }
    __syncthreads();
    const uint32_t gbase = wbs[t.win];
    bool busy = false, drained = false, moved = false;
@@ -534,7 +594,12 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    const size_t stride = ZB_MAX_OFFSET + tile_main;
    const int wave = 16384;
    const int nw_tiles = std::min(ntile, wave);
+#ifdef ZB_EMU
    tile_iv.need((size_t)nw_tiles * stride); tile_cnt.need(nw_tiles);
+#else
+   const size_t qstride = 3 * (size_t)tile_main;      /* text-walk queue of a tile: 3 words per main position at most */
+   tile_iv.need((size_t)nw_tiles * qstride); tile_cnt.need(nw_tiles);
+#endif
    const ZbTileDesc *td = tiles.p; uint32_t *ivb = tile_iv.p, *tc = tile_cnt.p;
    zb_match_t *mt = match.p; uint16_t *gl = glen.p, *go = goff.p; const uint32_t *wbs = wbase.p;
    stat_tiles = ntile;
@@ -554,13 +619,15 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
 #endif
    for (int first = 0; first < ntile; first += wave) {
       const int cnt = std::min(wave, ntile - first);
+#ifdef ZB_EMU
       zb_tile_filter(st, unit_words.p, unit_cnt.p, tiles.p, cnt, first, tile_iv.p, stride, tile_cnt.p, seg_t, filt_seg.p);
+#endif
 #ifndef ZB_EMU
       if (g_zb_prof_on) { zb_tag("mf_scan"); zb_prof_begin(0, st); }
-      zb_mf_scan_k<<<cnt, ZB_MF_THREADS, smem, st>>>(td, first, ivb, stride, tc, tq, mt, gl, go, wbs, tile_main, mf_ts_min, mf_ts_mul);
+      zb_mf_scan_k<<<cnt, ZB_MF_THREADS, smem, st>>>(td, first, unit_words.p, unit_cnt.p, ivb, qstride, stride, tq, mt, gl, go, wbs, tile_main, mf_ts_min, mf_ts_mul);
       if (g_zb_prof_on) zb_prof_end(st);
       if (g_zb_prof_on) { zb_tag("mf_text"); zb_prof_begin(0, st); }
-      zb_mf_text_k<<<cnt, ZB_MT_THREADS, smem_txt, st>>>(td, first, ivb, stride, tq, mt, gl, go, wbs, wdp, Tp);
+      zb_mf_text_k<<<cnt, ZB_MT_THREADS, smem_txt, st>>>(td, first, ivb, qstride, tq, mt, gl, go, wbs, wdp, Tp);
       if (g_zb_prof_on) zb_prof_end(st);
       zb_count_launch(2);
       ZB_CUDA_CHECK(cudaGetLastError());
@@ -1182,11 +1249,16 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
 
 struct ZbDwShared {            /* per warp */
    uint16_t ring[ZB_RING];
-   uint32_t rec[32][ZB_NMATCH + 1];   /* match records of the 32 positions of the current block (+1: bank spread) */
-   uint8_t lit[32];
-   ZbCostTab tab;               /* the sub-block's bit costs */
+   uint32_t info[32][ZB_NMATCH + 1];  /* decoded matches of the 32 positions of the current block (+1: bank spread) */
+   uint32_t meta[32];                 /* M | K << 4 | literal cost << 16 */
+   ZbCostTab tab;                     /* the sub-block's bit costs */
 };
 
+/* Positions [lo, from) of one sub-block, descending.  Per block of 32 positions the lanes first decode one position each, in
+   parallel and off the serial chain: valid-match count M, longest short length K, and per match a word
+   {clamped length (9 bits) | leave-alone flag | fixed cost (6 bits: offset cost, plus the length cost for a leave-alone
+   match) | offset (16 bits)}.  What stays serial per position is: ring reads, one redux per short match, a few compares,
+   one ring write. */
 __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const zb_match_t *__restrict__ match, int lo, int from, int end,
                                           zb_match_t *__restrict__ best, ZbDwShared &sh, int &slot, const int lane) {
    int s = slot;
@@ -1202,11 +1274,31 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
       const int p = from - 1 - lane;
       if (p >= lo) { const uint4 *q = (const uint4 *)(match + ((size_t)p << 3)); na = __ldg(q); nb = __ldg(q + 1); nl = t[p]; }
    }
+   uint32_t base = ring[s];       /* cost of the position above the next one to do: carried in a register */
    for (int i0 = from - 1; i0 >= lo; i0 -= 32) {
       __syncwarp();
-      sh.rec[lane][0] = na.x; sh.rec[lane][1] = na.y; sh.rec[lane][2] = na.z; sh.rec[lane][3] = na.w;
-      sh.rec[lane][4] = nb.x; sh.rec[lane][5] = nb.y; sh.rec[lane][6] = nb.z; sh.rec[lane][7] = nb.w;
-      sh.lit[lane] = (uint8_t)nl;
+      {  /* decode position i0 - lane */
+         const int i = i0 - lane;
+         const uint32_t w[ZB_NMATCH] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+         const int rem = end - i;
+         int M = 0, K = 0;
+#pragma unroll
+         for (int m = 0; m < ZB_NMATCH; m++) {
+            const int len0 = (int)(w[m] & 0xffffu), off0 = (int)(w[m] >> 16);
+            uint32_t inf = 0;
+            if (M == m && len0 >= ZB_MIN_MATCH && i >= lo) {
+               M = m + 1;
+               const int ml = len0 < rem ? len0 : rem;
+               const bool lg = len0 >= ZB_LEAVE_ALONE;
+               int fixed = (int)tab.off[zb_off_sym((uint32_t)off0)];
+               if (lg) { int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255; fixed += (int)tab.len[lidx]; }
+               else if (ml > K) K = ml;
+               inf = (uint32_t)ml | ((lg ? 1u : 0u) << 9) | ((uint32_t)fixed << 10) | ((uint32_t)off0 << 16);
+            }
+            sh.info[lane][m] = inf;
+         }
+         sh.meta[lane] = (uint32_t)M | ((uint32_t)K << 4) | ((uint32_t)tab.lit[nl & 0xffu] << 16);
+      }
       {
          const int p = i0 - 32 - lane;
          if (p >= lo) { const uint4 *q = (const uint4 *)(match + ((size_t)p << 3)); na = __ldg(q); nb = __ldg(q + 1); nl = t[p]; }
@@ -1215,59 +1307,49 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
       const int nb_pos = i0 - lo + 1 < 32 ? i0 - lo + 1 : 32;
       uint32_t outw = 0;      /* lane x keeps the choice of position i0 - x: one coalesced store per block */
       for (int x = 0; x < nb_pos; x++) {
-         const int i = i0 - x;
-         const uint32_t w = lane < ZB_NMATCH ? sh.rec[x][lane] : 0u;
-         const int len0 = (int)(w & 0xffffu), off0 = (int)(w >> 16);
-         const unsigned vm = __ballot_sync(0xffffffffu, len0 >= ZB_MIN_MATCH) & 0xffu;
-         const int M = __ffs((int)~vm) - 1;          /* leading matches with length >= 3 (blockdeflate.c:281) */
+         const uint32_t meta = sh.meta[x];
+         const int M = (int)(meta & 15u), K = (int)((meta >> 4) & 0xfffu);
          const int s1 = s;                           /* slot of i+1 */
          s = s1 + 1; if (s >= ZB_RING) s -= ZB_RING;
-         const uint16_t base = ring[s1];
-         int bestc = (int)tab.lit[sh.lit[x]], bl = 0, bo = 0;
+         int bestc = (int)(meta >> 16), bl = 0, bo = 0;
          if (M) {
-            const int rem = end - i;
-            const int ml0 = len0 < rem ? len0 : rem;
-            const bool v0 = lane < M, lg0 = len0 >= ZB_LEAVE_ALONE;
-            const uint32_t oc0 = v0 ? (uint32_t)tab.off[zb_off_sym((uint32_t)off0)] : 0u;
-            const int K = (int)__reduce_max_sync(0xffffffffu, (v0 && !lg0) ? (unsigned)ml0 : 0u);   /* candidate lengths 3..K */
-            /* per match: clamped length (9 bits) | leave-alone flag | offset cost (6 bits) | offset (16 bits) */
-            const uint32_t infoA = (uint32_t)ml0 | ((lg0 ? 1u : 0u) << 9) | (oc0 << 10) | ((uint32_t)off0 << 16);
             uint32_t keyA = ZB_DW_INF, keyB = ZB_DW_INF;
-            {
+            if (K >= ZB_MIN_MATCH) {
                const int k = ZB_MIN_MATCH + lane;
                if (k <= K) {
                   int idx = s1 - (k - 1); if (idx < 0) idx += ZB_RING;
-                  keyA = ((uint32_t)((int)(int16_t)(uint16_t)(ring[idx] - base) + lcA + 8192) << 6) | (uint32_t)(63 - k);
+                  keyA = ((uint32_t)((int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base) + lcA + 8192) << 6) | (uint32_t)(63 - k);
                }
                const int k2 = k + 32;
                if (k2 <= K) {
                   int idx = s1 - (k2 - 1); if (idx < 0) idx += ZB_RING;
-                  keyB = ((uint32_t)((int)(int16_t)(uint16_t)(ring[idx] - base) + lcB + 8192) << 6) | (uint32_t)(63 - k2);
+                  keyB = ((uint32_t)((int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base) + lcB + 8192) << 6) | (uint32_t)(63 - k2);
                }
             }
 #pragma unroll
             for (int m = 0; m < ZB_NMATCH; m++) {
                if (m < M) {
-                  const uint32_t inf = __shfl_sync(0xffffffffu, infoA, m);
-                  const int mlm = (int)(inf & 511u), offc = (int)((inf >> 10) & 63u);
+                  const uint32_t inf = sh.info[x][m];
+                  const int mlm = (int)(inf & 511u), fixed = (int)((inf >> 10) & 63u);
                   int total = 0x7fffffff, kk = 0;
                   if ((inf >> 9) & 1u) {   /* >= 40: only the full (clamped) length, even below 3 (SURVEY A-3) */
-                     int lidx = mlm - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
                      int idx = s1 - (mlm - 1); if (idx < 0) idx += ZB_RING;
-                     total = (int)tab.len[lidx] + offc + (int)(int16_t)(uint16_t)(ring[idx] - base);
+                     const uint32_t cv = mlm == 1 ? base : (uint32_t)ring[idx];     /* cost[i+1] is the register copy */
+                     total = fixed + (int)(int16_t)(uint16_t)(cv - base);
                      kk = mlm;
                   } else if (mlm >= ZB_MIN_MATCH) {
                      uint32_t c = (ZB_MIN_MATCH + lane <= mlm) ? keyA : ZB_DW_INF;
                      if (mlm > 34) { const uint32_t c2 = (ZB_MIN_MATCH + 32 + lane <= mlm) ? keyB : ZB_DW_INF; c = c2 < c ? c2 : c; }
                      c = __reduce_min_sync(0xffffffffu, c);
-                     total = (int)(c >> 6) - 8192 + offc;
+                     total = (int)(c >> 6) - 8192 + fixed;
                      kk = 63 - (int)(c & 63u);
                   }
                   if (total < bestc) { bestc = total; bl = kk; bo = (int)(inf >> 16); }
                }
             }
          }
-         if (lane == 0) ring[s] = (uint16_t)(base + (uint16_t)bestc);
+         base = (base + (uint32_t)bestc) & 0xffffu;
+         if (lane == 0) ring[s] = (uint16_t)base;
          if (lane == x) outw = (uint32_t)bl | ((uint32_t)bo << 16);
          __syncwarp();
       }
