@@ -42,19 +42,44 @@ KERNEL_BYTES = {
 }
 
 
-def gen_workload(name, size=None):
+def gen_workload(name, size=None, seg=0):
+    """Segment `seg` of a workload (segment 0 is the configuration itself; further segments, other seeds, make up the
+    N x larger stream of a weak-scaling run).  Cached under /tmp; written atomically since ranks may race."""
     from zultra_b200 import synth
     w = WORKLOADS[name]
     n = size or w["size"]
-    cache = os.path.join("/tmp", "zb_%s_%d.npy" % (name, n))
+    cache = os.path.join("/tmp", "zb_%s_%d_s%d.npy" % (name, n, seg))
     if os.path.exists(cache):
         return np.load(cache)
-    d = getattr(synth, w["gen"])(n)
+    fn = getattr(synth, w["gen"])
+    d = fn(n) if seg == 0 else fn(n, seed=0x5A170100 + 1009 * seg)
     try:
-        np.save(cache, d)
+        tmp = cache + ".%d.tmp.npy" % os.getpid()
+        np.save(tmp, d)
+        os.replace(tmp, cache)
     except OSError:
         pass
     return d
+
+
+def stream_range(name, size, lo, hi):
+    """Bytes [lo, hi) of the stream made of consecutive segments of `size` bytes each."""
+    parts = []
+    for sg in range(lo // size, (max(lo, hi - 1)) // size + 1):
+        d = gen_workload(name, size, sg)
+        a, b = max(lo, sg * size) - sg * size, min(hi, (sg + 1) * size) - sg * size
+        if b > a:
+            parts.append(d[a:b])
+    return np.concatenate(parts) if len(parts) != 1 else np.ascontiguousarray(parts[0])
+
+
+def ncu_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture of this workload (profiles/), or None."""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return j.get(kernel)
+    except (OSError, ValueError):
+        return None
 
 
 class ClockSampler:
@@ -128,6 +153,7 @@ def run_reference(args, rank, world):
     name = args.workload
     w = WORKLOADS[name]
     data = gen_workload(name, args.size)
+    world = max(1, world)
     cores = max(1, min(os.cpu_count() or 1, 64))
     slice_bytes = 2 << 20
     vals = []
@@ -143,7 +169,9 @@ def run_reference(args, rank, world):
     print(json.dumps({"impl": "reference", "metric": "input MB/s (zultra compression hot path)", "value": round(v, 3), "unit": "MB/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                      "config": {"workload": name, "bytes": int(len(data)), "format": w["fmt"], "max_block": 1048576},
+                      "config": {"workload": name if world == 1 or name != "enwik100m" else "%s x %d (one stream of %d segments of the configuration's shape, sharded by block range)" % (name, world, world),
+                                 "bytes": int(len(data)) * (world if name == "enwik100m" else 1), "format": w["fmt"], "max_block": 1048576,
+                                 "sample": "CPU threads each compress a 2 MiB slice of segment 0 per step"},
                       "cpu_baseline": {"value": round(v, 3), "unit": "MB/s", "cores": cores, "kind": "reference", "sample": sample},
                       "e2e": {"value": round(v, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -156,6 +184,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="enwik100m")
     ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"], help="N > 1: weak = one stream of N x the configuration (default for enwik100m), strong = the configuration split N ways")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="no per-kernel CUDA events in the timed steps")
     args = ap.parse_args()
@@ -172,20 +201,28 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name = args.workload
     w = WORKLOADS[name]
-    data = gen_workload(name, args.size)
-    n = len(data)
+    seg_size = args.size or w["size"]
+    # weak scaling (default for the headline workload): the job is ONE stream of N segments of the configuration's size,
+    # sharded by contiguous max-block ranges; strong: the configuration itself split N ways
+    weak = world > 1 and (args.scaling == "weak" or (args.scaling == "auto" and name == "enwik100m"))
+    n = seg_size * (world if weak else 1)
     block = 1 << 20
     nblocks = (n + block - 1) // block
     # shard by contiguous max-block ranges; every rank keeps the 32 KiB before its first block as history
     from zultra_b200 import shard
     lo, hi = shard.plan_shards(n, block, world)[rank]
     b0, b1 = lo // block, (hi + block - 1) // block
+    hist = min(lo, 32768)
+    shard_bytes = stream_range(name, seg_size, lo - hist, hi)
     L = z.load()
     L.zultra_cuda_profile.argtypes = [C.c_int]
     L.zultra_cuda_profile_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     ctx = z.CudaCtx(local)
     from bench_shard import ShardRunner
-    runner = ShardRunner(z, ctx, data, lo, hi, w["flags"], block, rank, world, dist, torch)
+    runner = ShardRunner(z, ctx, shard_bytes, hist, lo, hi, n, w["flags"], block, rank, world, dist, torch)
+    if dist is not None:
+        dist.barrier()     # every segment is in the /tmp cache now
+    data = stream_range(name, seg_size, 0, n) if rank == 0 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def step(profile):
@@ -208,7 +245,7 @@ def main():
         raw = data.tobytes()
         assert zlib.decompress(stream, {0: -15, 1: 15, 2: 31}[w["flags"]]) == raw, "output does not inflate to the input"
         stream_sha = hashlib.sha256(stream).hexdigest()
-        if world > 1 and len(data) <= (256 << 20):
+        if world > 1 and len(data) <= (1 << 30):
             one = z.memory_compress(data, w["flags"], block)
             assert one == stream, "sharded stream differs from the single-GPU stream"
         del raw
@@ -255,14 +292,16 @@ def main():
         achieved = (alg_bytes_per_step / launches_per_step) / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
         out = {"metric": "input MB/s (zultra compression hot path, byte-identical to CPU zultra)", "value": round(value, 2), "unit": "MB/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
-               "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-               "config": {"workload": name, "bytes": int(n), "format": w["fmt"], "max_block": block, "blocks": int(nblocks),
+               "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+               "config": {"workload": name if not weak else "%s x %d (one stream of %d segments of the configuration's shape, sharded by block range)" % (name, world, world),
+                          "bytes": int(n), "format": w["fmt"], "max_block": block, "blocks": int(nblocks),
                           "parallelism": "block-range shards x%d, %d concurrent lanes (streams) per GPU" % (world, max(1, ctx.counters()["r5"])), "l2": "256 MiB flush write between iterations"},
                "clocks": clocks,
                "e2e": {"value": round(n / (e2e_ms / 1e3) / 1e6, 2), "unit": "MB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "kernel": top[0], "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
-                            "traffic": None, "algorithmic_bytes": desc, "kernel_ms_per_step": round(top[1] / args.steps, 3),
+                            "traffic": ncu_traffic(top[0]), "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, enwik100m at N=1)",
+                            "algorithmic_bytes": desc, "kernel_ms_per_step": round(top[1] / args.steps, 3),
                             "kernel_share_of_step": round(top[1] / max(1e-9, sum(r[1] for r in ktab)), 4), "kernel_share_basis": "sum of all kernel durations (lanes overlap, so wall time is shorter)",
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6.65 TB/s"},
                "stages_ms": {k: round(v, 3) for k, v in stages.items()},

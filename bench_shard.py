@@ -14,12 +14,13 @@ import numpy as np
 
 
 class ShardRunner:
-    def __init__(self, z, ctx, data, lo, hi, flags, block, rank, world, dist, torch):
+    def __init__(self, z, ctx, shard, hist, lo, hi, n_total, flags, block, rank, world, dist, torch):
+        """shard = bytes [lo - hist, hi) of the stream (hist <= 32 KiB of preceding input)."""
         self.z, self.ctx, self.flags, self.block, self.rank, self.world, self.dist, self.torch = z, ctx, flags, block, rank, world, dist, torch
-        self.lo, self.hi, self.n_total = lo, hi, len(data)
-        hist = min(lo, 32768)
+        self.lo, self.hi, self.n_total = lo, hi, n_total
         self.hist = hist
-        shard = np.ascontiguousarray(data[lo - hist:hi])
+        shard = np.ascontiguousarray(shard)
+        assert len(shard) == hi - lo + hist
         self.host = torch.from_numpy(shard).pin_memory()
         self.dev_in = self.host.cuda()
         self.cap = max(1, (hi - lo) + (hi - lo) // 8 + 65536)
@@ -37,7 +38,7 @@ class ShardRunner:
             if self.maxcap > self.cap:
                 self.dev_out = torch.zeros(self.maxcap, dtype=torch.uint8, device="cuda")
             self.gather_list = [torch.zeros(self.maxcap, dtype=torch.uint8, device="cuda") for _ in range(world)] if rank == 0 else None
-            self.final_buf = torch.zeros(len(data) + len(data) // 8 + 65536 * world, dtype=torch.uint8, device="cuda") if rank == 0 else None
+            self.final_buf = torch.zeros(n_total + n_total // 8 + 65536 * world, dtype=torch.uint8, device="cuda") if rank == 0 else None
 
     def step_device(self):
         """Input resident in HBM.  Returns milliseconds between two CUDA events around the step."""

@@ -158,6 +158,28 @@ def test_large_vs_compiled_reference(z, ref):
         assert z.memory_compress(data, flags) == ref.compress(data, flags=flags)
 
 
+def test_runs_and_periodic_vs_compiled_reference(z, ref):
+    """Byte runs and long periodic repeats: the parse does not re-synchronise there, so these inputs go through the
+    chain repair (zb_parse_fix_k), including its scan path for blocks made of literals and far leave-alone matches."""
+    rng = np.random.default_rng(17)
+    parts = []
+    for _ in range(60):
+        run = int(np.exp(rng.uniform(np.log(16), np.log(200000))))
+        parts.append(np.full(run, int(rng.choice([0, 0xFF, 0x41])), dtype=np.uint8))
+        parts.append(rng.integers(0, 256, size=int(rng.integers(1, 300))).astype(np.uint8))
+    rec = np.zeros((40000, 16), dtype=np.uint8)
+    rec[:, 0:4] = (np.arange(40000, dtype=np.uint32) + 77).astype("<u4").view(np.uint8).reshape(-1, 4)
+    rec[:, 8] = rng.integers(0, 4, size=40000)
+    parts.append(rec.reshape(-1))
+    parts.append(np.tile(rng.integers(0, 256, size=300).astype(np.uint8), 1500))
+    parts.append(np.tile(np.frombuffer(b"ab", dtype=np.uint8), 150000))
+    parts.append(synth.enwik(300000, seed=41))
+    parts.append(np.zeros(700000, dtype=np.uint8))
+    data = np.concatenate(parts)
+    for flags, block in ((0, 0), (2, 262144)):
+        assert z.memory_compress(data, flags, block) == ref.compress(data, flags=flags, block=block)
+
+
 def test_lanes_vs_compiled_reference(z, ref, monkeypatch):
     """Block ranges of one call run as concurrent lanes (zb_capi.cu run_lanes); the stitched stream must equal the
     reference byte for byte, including stored sub-blocks whose size depends on the entering bit phase, a history that

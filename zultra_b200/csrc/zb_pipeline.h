@@ -122,7 +122,7 @@ struct ZbPipe {
    /* sub-blocks */
    ZbBuf<ZbSub> sub; ZbBuf<ZbSubTabs> tabs; ZbBuf<uint32_t> dchunk_sub, pchunk_sub;
    ZbBuf<zb_match_t> best; ZbBuf<int16_t> sig_true, sig_warm, sig_new; ZbBuf<uint8_t> dok; ZbBuf<uint32_t> dbad;
-   ZbBuf<uint32_t> pentry, pbits;
+   ZbBuf<uint32_t> pentry, pbits; ZbBuf<uint16_t> dpfar;   /* dpfar: cost rows of the thread-per-chunk parse kernel */
    /* output */
    ZbBuf<uint32_t> out; ZbBuf<ZbStreamOut> sout;
    std::vector<ZbStreamOut> h_sout;
@@ -1116,88 +1116,116 @@ ZB_HD void zb_walk_best(const zb_match_t *best, uint32_t entry, uint32_t hi, F &
 
 #ifndef ZB_EMU
 /* ---- chunked backward recurrence, one thread per parse chunk (32 independent chunks per warp) ----
- * The 260-entry cost ring of every thread lives in shared memory ([slot][thread], so a warp's accesses fall into
- * distinct banks up to the 2-way u16 pairing); match records are fetched one position ahead (zb_parse_range). */
-#define ZB_DP_THREADS 64
-/* zb_parse_range for the thread-per-chunk kernel, same choices, fewer instructions in the candidate loop: the ring is walked
-   with a pointer (slot stride = ZB_DP_THREADS), the wrap is taken out of the loop (two straight segments), and the bit costs
-   come from a shared-memory copy of the sub-block's table when the chunk belongs to the CTA's first sub-block (almost
-   always; otherwise the same pointers address global memory). */
-__device__ __forceinline__ void zb_parse_range_dev(const uint8_t *__restrict__ T, const zb_match_t *__restrict__ match, const uint8_t *plit, const uint8_t *plen,
-                                                   const uint8_t *poff, int lo, int from, int end, int keep_hi, zb_match_t *__restrict__ best, uint16_t *ring0, int &slot) {
+ * Occupancy is what this kernel lives on (every thread is one long dependent chain), so the per-thread state is kept small:
+ * the costs of the last 64 positions sit in a shared-memory ring ([slot][thread]: a warp's accesses fall into distinct banks
+ * up to the 2-way u16 pairing) - short matches (< 40) only look 39 positions ahead - and every cost is also streamed to a
+ * global scratch row ([step][thread], so a warp's store is one 64-byte line) from which the rare far reads of leave-alone
+ * matches (>= 40: one cost, up to 258 ahead) and the two 259-entry signatures are taken.  A chunk starts from cost 0 and a
+ * step adds at most 15 bits, so with CD + WU <= 4368 steps the u16 costs never wrap and are compared as plain integers.
+ * The bit costs come from a per-warp shared-memory copy of the table of the warp's first sub-block; a lane whose chunk
+ * belongs to a later sub-block (one warp per sub-block boundary) reads its table from global memory instead.  Match records
+ * are fetched one position ahead. */
+#define ZB_DP_THREADS 128
+#define ZB_NR 64              /* near ring entries */
+#define ZB_DP_INF 0x7fffffffu
+
+template <bool KEEP>
+__device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const zb_match_t *__restrict__ match, const uint8_t *__restrict__ plit,
+                                            const uint8_t *__restrict__ plen, const uint8_t *__restrict__ poff, int lo, int from, int end,
+                                            zb_match_t *__restrict__ best, uint16_t *ring0, uint16_t *far0, int &t_io, uint32_t &cprev_io) {
    const int NT = ZB_DP_THREADS;
-   int s = slot;
    if (from - 1 < lo) return;
+   int t = t_io;
+   uint32_t cprev = cprev_io;                 /* cost of position i + 1 */
    ZbMatchRec nxt = zb_load_rec(match, from - 1);
    uint32_t nlit = T[from - 1];
-   for (int i = from - 1; i >= lo; i--) {
+   for (int i = from - 1; i >= lo; i--, t++) {
       const ZbMatchRec rec = nxt;
       const uint32_t lit = nlit;
       if (i - 1 >= lo) { nxt = zb_load_rec(match, i - 1); nlit = T[i - 1]; }
-      const int s1 = s;
-      s = s1 + 1; if (s >= ZB_RING) s -= ZB_RING;
-      const uint32_t base = ring0[s1 * NT];
-      int bestc = plit[lit];
-      int bestlen = 0, bestoff = 0;
+      uint32_t bestc = cprev + plit[lit];
+      uint32_t bestw = 0;
       int M = 0;
 #pragma unroll
       for (int m = 0; m < ZB_NMATCH; m++) if (M == m && (rec.w[m] & 0xffffu) >= ZB_MIN_MATCH) M = m + 1;
       if (M) {
-         int bt = 0x7fffffff, bl = 0, bo = 0;
-         int k = ZB_MIN_MATCH, curmin = 0x7fffffff, curk = 0;
-         int q = s1 - (ZB_MIN_MATCH - 1); if (q < 0) q += ZB_RING;   /* slot of i+3 */
-         const uint16_t *pr = ring0 + q * NT;                          /* slot of i+k, moving down by NT per k */
-         int kw = k + q + 1;                                           /* first k whose slot wraps */
+         uint32_t bt = ZB_DP_INF, bw = 0;
+         int k = ZB_MIN_MATCH, curk = 0;
+         uint32_t curmin = ZB_DP_INF;
+         const int q = (t - ZB_MIN_MATCH) & (ZB_NR - 1);          /* slot of i+3 (a slot not written yet reads as the zero guess) */
+         const uint16_t *pr = ring0 + q * NT;                       /* slot of i+k, moving down by NT per k */
+         int kw = k + q + 1;                                        /* first k whose slot wraps */
 #pragma unroll
          for (int m = ZB_NMATCH - 1; m >= 0; m--) {
             if (m < M) {
                const int mlen0 = (int)(rec.w[m] & 0xffffu), moff = (int)(rec.w[m] >> 16);
-               const int offc = poff[zb_off_sym((uint32_t)moff)];
+               const uint32_t offc = poff[zb_off_sym((uint32_t)moff)];
                int ml = mlen0;
                if (i + ml > end) ml = end - i;
-               int total, kk;
+               uint32_t total; int kk;
                if (mlen0 >= ZB_LEAVE_ALONE) {
-                  int sl = s1 - (ml - 1); if (sl < 0) sl += ZB_RING;
                   int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
-                  total = plen[lidx] + offc + (int)(int16_t)(uint16_t)(ring0[sl * NT] - base);
+                  const int tt = t - ml;                             /* step at which position i + ml was done */
+                  uint32_t cv;
+                  if (ml < ZB_NR) cv = ring0[(tt & (ZB_NR - 1)) * NT];
+                  else cv = tt >= 0 ? (uint32_t)far0[(size_t)tt * NT] : 0u;
+                  total = plen[lidx] + offc + cv;
                   kk = ml;
                } else {
                   while (k <= ml) {
                      const int kstop = ml < kw - 1 ? ml : kw - 1;
-#pragma unroll 2
+#pragma unroll 4
                      for (; k <= kstop; k++, pr -= NT) {
-                        const int c = (int)plen[k - ZB_MIN_MATCH] + (int)(int16_t)(uint16_t)((uint32_t)*pr - base);
+                        const uint32_t c = (uint32_t)plen[k - ZB_MIN_MATCH] + (uint32_t)*pr;
                         if (c <= curmin) { curmin = c; curk = k; }
                      }
-                     if (k == kw) { pr += ZB_RING * NT; kw += ZB_RING; }
+                     if (k == kw) { pr += ZB_NR * NT; kw += ZB_NR; }
                   }
-                  total = curk ? curmin + offc : 0x7fffffff;
+                  total = curk ? curmin + offc : ZB_DP_INF;
                   kk = curk;
                }
-               if (total <= bt && total != 0x7fffffff) { bt = total; bl = kk; bo = moff; }
+               if (total <= bt && total != ZB_DP_INF) { bt = total; bw = (uint32_t)kk | ((uint32_t)moff << 16); }
             }
          }
-         if (bt < bestc) { bestc = bt; bestlen = bl; bestoff = bo; }
+         if (bt < bestc) { bestc = bt; bestw = bw; }
       }
-      ring0[s * NT] = (uint16_t)(base + (uint32_t)bestc);
-      if (i < keep_hi) { zb_match_t o; o.length = (uint16_t)bestlen; o.offset = (uint16_t)bestoff; best[i] = o; }
+      ring0[(t & (ZB_NR - 1)) * NT] = (uint16_t)bestc;
+      far0[(size_t)t * NT] = (uint16_t)bestc;
+      cprev = bestc;
+      if (KEEP) ((uint32_t *)best)[i] = bestw;
    }
-   slot = s;
+   t_io = t; cprev_io = cprev;
+}
+
+/* the 259 relative costs at `pos0` (the signature two neighbouring chunks are compared by), read back from the scratch row:
+   position p was done at step from - 1 - p; positions at and above `from` are the zero guess */
+__device__ __forceinline__ void zb_dp_signature(int16_t *dst, const uint16_t *far0, int pos0, int from, int end, int t, uint32_t cprev, bool warm) {
+   const int NT = ZB_DP_THREADS;
+   for (int q = 0; q <= ZB_MAX_MATCH; q++) {
+      const int tt = t - 1 - q;
+      const bool in = warm ? (pos0 + q <= end && pos0 + q <= from) : (pos0 + q <= end);
+      const uint32_t v = tt >= 0 ? (uint32_t)far0[(size_t)tt * NT] : 0u;
+      dst[q] = in ? (int16_t)(uint16_t)(v - cprev) : (int16_t)0;
+   }
 }
 
 __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
                                                                const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw,
-                                                               int CD, int WU) {
-   __shared__ uint16_t ring_s[ZB_RING * ZB_DP_THREADS];
-   __shared__ ZbCostTab tab_s;
-   const long c0 = (long)blockIdx.x * ZB_DP_THREADS;
-   const long c = c0 + threadIdx.x;
-   const uint32_t x0 = dcs[c0];         /* c0 < ndch by the grid size */
+                                                               uint16_t *far, int CD, int WU) {
+   __shared__ uint16_t ring_s[ZB_NR * ZB_DP_THREADS];
+   __shared__ ZbCostTab tab_s[ZB_DP_THREADS / 32];
+   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+   const long cw = (long)blockIdx.x * ZB_DP_THREADS + wi * 32;
+   if (cw >= ndch) return;                /* the whole warp */
+   const long c = cw + lane;
+   const uint32_t x0 = dcs[cw];
    {
-      const uint32_t *src = (const uint32_t *)&tb[x0].cost; uint32_t *dstw = (uint32_t *)&tab_s;
-      for (int e = threadIdx.x; e < (int)(sizeof(ZbCostTab) / 4); e += ZB_DP_THREADS) dstw[e] = src[e];
+      const uint32_t *src = (const uint32_t *)&tb[x0].cost; uint32_t *dstw = (uint32_t *)&tab_s[wi];
+      for (int e = lane; e < (int)(sizeof(ZbCostTab) / 4); e += 32) dstw[e] = src[e];
    }
-   __syncthreads();
+   uint16_t *ring0 = ring_s + threadIdx.x;
+   for (int e = 0; e < ZB_NR; e++) ring0[e * ZB_DP_THREADS] = 0;
+   __syncwarp();
    if (c >= ndch) return;
    const uint32_t x = dcs[c];
    const ZbSub s = sb[x];
@@ -1205,33 +1233,27 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
    const uint32_t k = (uint32_t)c - s.dchunk_base;
    const uint32_t gb = wbs[s.win];
    const uint8_t *t = T + wd[s.win].in_off;
+   const zb_match_t *m0 = mt + ((size_t)gb << 3);
+   zb_match_t *b0 = bm + gb;
    const int lo = (int)(s.ps + k * CD);
    const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
    const int end = (int)s.pe;
    int from = hi + WU; if (from > end) from = end;
-   ZbRingStrided ring = {ring_s + threadIdx.x, ZB_DP_THREADS};
-   for (int i = 0; i < ZB_RING; i++) ring.set(i, 0);
-   int slot = 0;
-   const ZbCostTab *ct = x == x0 ? &tab_s : &tb[x].cost;
-   const uint8_t *plit = ct->lit, *plen = ct->len, *poff = ct->off;
-   if (from > hi) zb_parse_range_dev(t, mt + ((size_t)gb << 3), plit, plen, poff, hi, from, end, hi, bm + gb, ring_s + threadIdx.x, slot);
-   {
-      int16_t *sw = sgw + (size_t)c * 260;
-      const uint16_t b = ring.get(slot);
-      for (int q = 0; q <= ZB_MAX_MATCH; q++) {
-         int sl = slot - q; if (sl < 0) sl += ZB_RING;
-         sw[q] = (hi + q <= end && hi + q <= from) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
-      }
+   uint16_t *far0 = far + (size_t)blockIdx.x * (size_t)(CD + WU) * ZB_DP_THREADS + threadIdx.x;
+   int16_t *sw = sgw + (size_t)c * 260, *sg = sgt + (size_t)c * 260;
+   int step = 0; uint32_t cprev = 0;
+   if (x == x0) {
+      const uint8_t *plit = tab_s[wi].lit, *plen = tab_s[wi].len, *poff = tab_s[wi].off;
+      zb_dp_range<false>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
+      zb_dp_signature(sw, far0, hi, from, end, step, cprev, true);
+      zb_dp_range<true>(t, m0, plit, plen, poff, lo, hi, end, b0, ring0, far0, step, cprev);
+   } else {
+      const uint8_t *plit = tb[x].cost.lit, *plen = tb[x].cost.len, *poff = tb[x].cost.off;
+      zb_dp_range<false>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
+      zb_dp_signature(sw, far0, hi, from, end, step, cprev, true);
+      zb_dp_range<true>(t, m0, plit, plen, poff, lo, hi, end, b0, ring0, far0, step, cprev);
    }
-   zb_parse_range_dev(t, mt + ((size_t)gb << 3), plit, plen, poff, lo, hi, end, hi, bm + gb, ring_s + threadIdx.x, slot);
-   {
-      int16_t *sg = sgt + (size_t)c * 260;
-      const uint16_t b = ring.get(slot);
-      for (int q = 0; q <= ZB_MAX_MATCH; q++) {
-         int sl = slot - q; if (sl < 0) sl += ZB_RING;
-         sg[q] = (lo + q <= end) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
-      }
-   }
+   zb_dp_signature(sg, far0, lo, from, end, step, cprev, false);
 }
 
 /* ---- repair of wrong chunks: the same recurrence, ONE WARP per chain ----
@@ -1246,6 +1268,7 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
 #define ZB_DW_THREADS 128
 #define ZB_DW_WARPS (ZB_DW_THREADS / 32)
 #define ZB_DW_INF 0x7fffffffu
+#define ZB_DW_FAR_INF 0x3fffffff
 
 struct ZbDwShared {            /* per warp */
    uint16_t ring[ZB_RING];
@@ -1275,11 +1298,13 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
       if (p >= lo) { const uint4 *q = (const uint4 *)(match + ((size_t)p << 3)); na = __ldg(q); nb = __ldg(q + 1); nl = t[p]; }
    }
    uint32_t base = ring[s];       /* cost of the position above the next one to do: carried in a register */
+   bool far_ok = true; int farE = ZB_DW_FAR_INF, lita = 0; uint32_t farw = 0u;
    for (int i0 = from - 1; i0 >= lo; i0 -= 32) {
       __syncwarp();
       {  /* decode position i0 - lane */
          const int i = i0 - lane;
          const uint32_t w[ZB_NMATCH] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+         far_ok = true; farE = ZB_DW_FAR_INF; farw = 0u;
          const int rem = end - i;
          int M = 0, K = 0;
 #pragma unroll
@@ -1294,10 +1319,18 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
                if (lg) { int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255; fixed += (int)tab.len[lidx]; }
                else if (ml > K) K = ml;
                inf = (uint32_t)ml | ((lg ? 1u : 0u) << 9) | ((uint32_t)fixed << 10) | ((uint32_t)off0 << 16);
+               /* far candidate: a leave-alone match that lands past the block's top position is already final */
+               if (lg && ml > lane) {
+                  int idx = s - (ml - 1 - lane); if (idx < 0) idx += ZB_RING;
+                  const int total = fixed + (int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base);
+                  if (total < farE) { farE = total; farw = (uint32_t)ml | ((uint32_t)off0 << 16); }
+               } else far_ok = false;
             }
             sh.info[lane][m] = inf;
          }
-         sh.meta[lane] = (uint32_t)M | ((uint32_t)K << 4) | ((uint32_t)tab.lit[nl & 0xffu] << 16);
+         lita = (int)tab.lit[nl & 0xffu];
+         sh.meta[lane] = (uint32_t)M | ((uint32_t)K << 4) | ((uint32_t)lita << 16);
+         if (i < lo) { lita = 0; farE = ZB_DW_FAR_INF; }
       }
       {
          const int p = i0 - 32 - lane;
@@ -1306,6 +1339,29 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
       __syncwarp();
       const int nb_pos = i0 - lo + 1 < 32 ? i0 - lo + 1 : 32;
       uint32_t outw = 0;      /* lane x keeps the choice of position i0 - x: one coalesced store per block */
+      if (__all_sync(0xffffffffu, far_ok)) {
+         /* Every candidate of every position of the block is either its literal or a leave-alone match landing above the
+            block (byte runs, long periodic repeats - exactly the data that does not re-synchronise).  Position i0 - x then maps
+            the cost c above it to min(c + lit, far): these maps compose ((A, B) : c -> min(c + A, B)), so the 32 positions are
+            one warp scan instead of 32 serial steps.  Costs are relative to `base` = cost[i0 + 1]. */
+         int A = lita, B = farE;
+#pragma unroll
+         for (int d = 1; d < 32; d <<= 1) {
+            const int pa = __shfl_up_sync(0xffffffffu, A, d), pb = __shfl_up_sync(0xffffffffu, B, d);
+            if (lane >= d) { const int nbv = pb + A; B = nbv < B ? nbv : B; A = pa + A; }
+         }
+         const int r = A < B ? A : B;                    /* cost[i0 - lane] - base */
+         int cin = __shfl_up_sync(0xffffffffu, r, 1); if (lane == 0) cin = 0;
+         if (farE < cin + lita) outw = farw;             /* literal first, a match only on strictly lower cost */
+         if (lane < nb_pos) {
+            int sl = s + 1 + lane; if (sl >= ZB_RING) sl -= ZB_RING;
+            ring[sl] = (uint16_t)(base + (uint32_t)r);
+            ((uint32_t *)best)[i0 - lane] = outw;
+         }
+         base = (base + (uint32_t)__shfl_sync(0xffffffffu, r, nb_pos - 1)) & 0xffffu;
+         s += nb_pos; if (s >= ZB_RING) s -= ZB_RING;
+         continue;
+      }
       for (int x = 0; x < nb_pos; x++) {
          const uint32_t meta = sh.meta[x];
          const int M = (int)(meta & 15u), K = (int)((meta >> 4) & 0xfffu);
@@ -1426,9 +1482,12 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
 inline void ZbPipe::stage_parse() {
    /* One thread per chunk: the chunk count is the parallelism.  ZB_CD positions per chunk when that still gives ~40 K chunks,
       shorter chunks (more warm-up overhead, shorter serial chains) for small batches such as one GPU's shard of a stream. */
-   int cd_auto = ZB_CD;
-   while (cd_auto > 512 && (long)P / cd_auto < 40000) cd_auto >>= 1;
-   const int CD = parse_cd ? parse_cd : cd_auto, WU = parse_wu;
+   /* (the thread-per-chunk kernel keeps ~1024 chunks resident per SM: aim at one full wave, within [512, ZB_CD]) */
+   int cd_auto = (int)(((long)P / ((long)zb_sm_count() * 1024) + 63) / 64 * 64);
+   if (cd_auto < 512) cd_auto = 512;
+   if (cd_auto > ZB_CD) cd_auto = ZB_CD;
+   int WU = parse_wu; if (WU > 2048) WU = 2048;
+   int CD = parse_cd ? parse_cd : cd_auto; if (CD > 2048) CD = 2048;      /* CD + WU <= 4368: u16 costs cannot wrap (zb_parse_dp_k) */
    const int ns = nsub;
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
    ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in_ptr, win.p};
@@ -1479,6 +1538,7 @@ inline void ZbPipe::stage_parse() {
    pentry.need(npch + 1); pbits.need(npch + 1);
 #ifndef ZB_EMU
    exitc.need((size_t)(npch + 1) * ZB_EXROW);
+   dpfar.need((size_t)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS) * (size_t)(CD + WU) * ZB_DP_THREADS + 64);
 #endif
    uint32_t *dcs = dchunk_sub.p, *pcs = pchunk_sub.p;
    zb_launch(st, ns, ZB_LAMBDA(long x) {
@@ -1497,7 +1557,7 @@ inline void ZbPipe::stage_parse() {
 #ifndef ZB_EMU
       if (ndch > 0) {
          if (g_zb_prof_on) { zb_tag("parse_dp"); zb_prof_begin(0, st); }
-         zb_parse_dp_k<<<(unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS), ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, CD, WU);
+         zb_parse_dp_k<<<(unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS), ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, dpfar.p, CD, WU);
          if (g_zb_prof_on) zb_prof_end(st);
          zb_count_launch(1);
          ZB_CUDA_CHECK(cudaGetLastError());
@@ -1563,6 +1623,14 @@ inline void ZbPipe::stage_parse() {
          zb_d2h(st, &nbad, cn + 7, 4); zb_sync(st);
          if (!nbad) break;
          stat_redo += (int)nbad;
+#ifdef ZB_EMU
+         if (getenv("ZB_DUMP_BAD") && round == 0) {   /* analysis aid of the host build: which chunks failed to re-synchronise */
+            for (uint32_t e = 0; e < nbad; e++) {
+               const ZbSub &s = sb[dcs[bad[e]]];
+               fprintf(stderr, "BAD pass %d win %u pos %u sub [%u,%u)\n", pass, s.win, s.ps + (bad[e] - s.dchunk_base) * CD, s.ps, s.pe);
+            }
+         }
+#endif
 #ifndef ZB_EMU
          if (g_zb_prof_on) { zb_tag("parse_repair"); zb_prof_begin(0, st); }
          zb_parse_fix_k<<<(unsigned)((nbad + ZB_DW_WARPS - 1) / ZB_DW_WARPS), ZB_DW_THREADS, 0, st>>>(sb, tb, dcs, bad, (int)nbad, ok, wd, wbs, T, mt, bm, sgt, sgw, CD);
@@ -2043,7 +2111,7 @@ inline void ZbPipe::release_all() {
    gtokcnt.release(); gtokbase.release(); tokpos.release(); wtok.release(); wtokbase.release(); wintbase.release(); ph.release();
    gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
    chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();
-   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); dbad.release(); pentry.release(); pbits.release(); out.release(); sout.release();
+   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); dbad.release(); pentry.release(); pbits.release(); dpfar.release(); out.release(); sout.release();
 }
 
 

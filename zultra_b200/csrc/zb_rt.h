@@ -33,6 +33,7 @@ static inline int zb_atomic_add(int *p, int v) { int o = *p; *p += v; return o; 
 static inline unsigned zb_atomic_add(unsigned *p, unsigned v) { unsigned o = *p; *p += v; return o; }
 static inline int zb_atomic_max(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline unsigned zb_atomic_or(unsigned *p, unsigned v) { unsigned o = *p; *p |= v; return o; }
+static inline int zb_sm_count() { return 148; }
 #else
 /* ---------------- CUDA ---------------- */
 #include <cuda_runtime.h>
@@ -70,6 +71,11 @@ static inline void zb_h2d(zb_stream_t st, void *d, const void *h, size_t n) { if
 static inline void zb_d2h(zb_stream_t st, void *h, const void *d, size_t n) { if (n) ZB_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st)); }
 static inline void zb_d2d(zb_stream_t st, void *d, const void *s, size_t n) { if (n) ZB_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st)); }
 static inline void zb_sync(zb_stream_t st) { ZB_CUDA_CHECK(cudaStreamSynchronize(st)); }
+static inline int zb_sm_count() {   /* SMs of the current device (B200: 148) */
+   int dev = 0, n = 0;
+   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+   return n;
+}
 __device__ __forceinline__ int zb_atomic_add(int *p, int v) { return atomicAdd(p, v); }
 __device__ __forceinline__ unsigned zb_atomic_add(unsigned *p, unsigned v) { return atomicAdd(p, v); }
 __device__ __forceinline__ int zb_atomic_max(int *p, int v) { return atomicMax(p, v); }
