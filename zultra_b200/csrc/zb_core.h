@@ -81,18 +81,39 @@ ZB_HD int zb_offsym_extra(int s) { return (s < 4 || s >= 30) ? 0 : ((s - 2) >> 1
 
 /* ---- Huffman code construction (huffencoder.c) ---- */
 
-/* Sort keys ascending. Shell sort, n <= 288. */
+/* Sort keys ascending, n <= 288.  The keys are distinct and arrive ordered by their low 9 bits (the symbol index), so a
+   stable LSD radix sort of the bits above them (the count) is a full sort: 1..3 passes of <= 7 bits over the bits the largest
+   key uses, instead of a comparison sort's long chain of dependent local-memory moves (these builds run one per thread, and
+   their latency is what the splitter and the table stages wait for).  Small inputs: insertion sort. */
 ZB_HD void zb_sort_u32(uint32_t *a, int n) {
-   const int gaps[6] = {132, 57, 23, 10, 4, 1};
-   for (int g = 0; g < 6; g++) {
-      int gap = gaps[g];
-      for (int i = gap; i < n; i++) {
+   if (n <= 24) {
+      for (int i = 1; i < n; i++) {
          uint32_t v = a[i];
          int j = i;
-         while (j >= gap && a[j - gap] > v) { a[j] = a[j - gap]; j -= gap; }
+         while (j > 0 && a[j - 1] > v) { a[j] = a[j - 1]; j--; }
          a[j] = v;
       }
+      return;
    }
+   uint32_t tmp[ZB_NLIT];
+   uint16_t bin[128];
+   uint32_t top = 0;
+   for (int i = 0; i < n; i++) top |= a[i];
+   int bits = 0;
+   while ((top >> 9) >> bits) bits++;
+   if (bits == 0) return;
+   const int passes = (bits + 6) / 7, w = (bits + passes - 1) / passes, nb = 1 << w;
+   uint32_t *src = a, *dst = tmp;
+   for (int p = 0; p < passes; p++) {
+      const int sh = 9 + p * w;
+      for (int i = 0; i < nb; i++) bin[i] = 0;
+      for (int i = 0; i < n; i++) bin[(src[i] >> sh) & (uint32_t)(nb - 1)]++;
+      uint32_t run = 0;
+      for (int i = 0; i < nb; i++) { const uint32_t c = bin[i]; bin[i] = (uint16_t)run; run += c; }
+      for (int i = 0; i < n; i++) { const uint32_t v = src[i]; dst[bin[(v >> sh) & (uint32_t)(nb - 1)]++] = v; }
+      uint32_t *t = src; src = dst; dst = t;
+   }
+   if (src != a) for (int i = 0; i < n; i++) a[i] = src[i];
 }
 
 /*

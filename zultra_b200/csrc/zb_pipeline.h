@@ -922,6 +922,51 @@ struct ZbGreedyView {
    }
 };
 
+#ifndef ZB_EMU
+/* Splitter drift test (blockdeflate.c:706-721), one warp per node: lane k of a round owns check point base + k; the 18-bin
+   running statistics before it are a warp prefix sum of the per-interval statistics (same unsigned 32-bit arithmetic as the
+   reference's sequential accumulation, SURVEY A-15). */
+__global__ void __launch_bounds__(128) zb_split_drift_k(const ZbNode *cur, int ncur, const uint16_t *cs, uint8_t *cf) {
+   const int lane = threadIdx.x & 31;
+   const int x = blockIdx.x * 4 + (threadIdx.x >> 5);
+   if (x >= ncur) return;
+   const ZbNode nd = cur[x];
+   uint32_t carry[18];
+#pragma unroll
+   for (int j = 0; j < 18; j++) carry[j] = 0;
+   for (uint32_t base = 0; base < nd.nchk; base += 32) {
+      const uint32_t k = base + lane;
+      const bool valid = k < nd.nchk;
+      const uint16_t *ns = cs + (size_t)(nd.chk_base + (valid ? k : 0)) * 18;
+      uint32_t own[18], stat[18], nstat = 0;
+#pragma unroll
+      for (int j = 0; j < 18; j++) {
+         own[j] = valid ? (uint32_t)ns[j] : 0u;
+         uint32_t inc = own[j];
+#pragma unroll
+         for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+         stat[j] = carry[j] + inc - own[j];
+         nstat += stat[j];
+         carry[j] += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (valid) {
+         const uint32_t nnew = k == 0 ? nd.t0 : 256;
+         uint8_t flag = 0;
+         if (nstat) {
+            uint32_t tot = 0;
+#pragma unroll
+            for (int j = 0; j < 18; j++) {
+               const uint32_t e = stat[j] * nnew, a = own[j] * nstat;
+               tot += e > a ? e - a : a - e;
+            }
+            if ((tot / nnew) >= (nstat * 45 / 100)) flag = 1;
+         }
+         cf[nd.chk_base + k] = flag;
+      }
+   }
+}
+#endif
+
 /* ============================================================ block splitter ============================================================
  * zultra_compressor_split_subblock_recursive (blockdeflate.c:634-786), one recursion level per round.
  */
@@ -977,7 +1022,7 @@ inline void ZbPipe::stage_split() {
       zb_d2h(st, &nchk, cn + 1, 4); zb_sync(st);
       int nnext = 0;
       if (nchk > 0) {
-         chk_stat.need((size_t)nchk * 18); chk_flag.need(nchk); chk_delta.need(nchk); chk_node.need(nchk);
+         chk_stat.need((size_t)nchk * 18); chk_flag.need(nchk); chk_delta.need(2 * (size_t)nchk); chk_node.need(nchk);
          uint16_t *cs = chk_stat.p; uint8_t *cf = chk_flag.p; int *cdl = chk_delta.p; uint32_t *cnode = chk_node.p;
          zb_launch(st, ncur, ZB_LAMBDA(long x) { for (uint32_t k = 0; k < cur[x].nchk; k++) cnode[cur[x].chk_base + k] = (uint32_t)x; });
          /* S2: 18-bin statistics of each check interval (blockdeflate.c:686-703) */
@@ -997,6 +1042,13 @@ inline void ZbPipe::stage_split() {
             for (int i = 0; i < 18; i++) cs[(size_t)c * 18 + i] = s18[i];
          });
          /* S3: drift test per check point (blockdeflate.c:706-721, unsigned arithmetic) */
+#ifndef ZB_EMU
+         if (g_zb_prof_on) { zb_tag("split_drift"); zb_prof_begin(0, st); }
+         zb_split_drift_k<<<(unsigned)((ncur + 3) / 4), 128, 0, st>>>(cur, ncur, cs, cf);
+         if (g_zb_prof_on) zb_prof_end(st);
+         zb_count_launch(1);
+         ZB_CUDA_CHECK(cudaGetLastError());
+#else
          zb_launch(st, ncur, ZB_LAMBDA(long x) {
             const ZbNode nd = cur[x];
             uint32_t stat[18], nstat = 0;
@@ -1017,29 +1069,28 @@ inline void ZbPipe::stage_split() {
                for (int j = 0; j < 18; j++) { nstat += ns[j]; stat[j] += ns[j]; }
             }
          });
+#endif
          /* S4: cost delta of splitting at the PREVIOUS check point (blockdeflate.c:724-757) */
          zb_tag("split_eval");
-         zb_launch(st, nchk, ZB_LAMBDA(long c) {
-            cdl[c] = -1;
+         zb_launch(st, 2L * nchk, ZB_LAMBDA(long y) {      /* one task per side of a candidate: the two are independent */
+            const long c = y >> 1; const int right_side = (int)(y & 1);
+            cdl[y] = -1;
             if (!cf[c]) return;
             const uint32_t x = cnode[c];
             const ZbNode nd = cur[x];
             const uint32_t k = (uint32_t)c - nd.chk_base;   /* k >= 1 here */
             const uint32_t tsplit = nd.t0 + 256 * (k - 1);   /* tokens left of the split */
-            int left[ZB_NH], right[ZB_NH];
-            gv.range_hist((int)nd.win, nd.ts, nd.ts + tsplit, left);
-            left[ZB_EOB] = 1;
-            const int *tot = nh + (size_t)x * ZB_NH;
-            for (int i = 0; i < ZB_NH; i++) right[i] = tot[i] - left[i];
-            right[ZB_EOB] = 1;
+            int h[ZB_NH];
+            gv.range_hist((int)nd.win, nd.ts, nd.ts + tsplit, h);
+            if (right_side) {
+               const int *tot = nh + (size_t)x * ZB_NH;
+               for (int i = 0; i < ZB_NH; i++) h[i] = tot[i] - h[i];
+            }
+            h[ZB_EOB] = 1;
             ZbScratch s; int llen[ZB_NLIT], olen[ZB_NLIT];
-            zb_huff_lengths(left, ZB_NLIT, llen, s.key);
-            zb_huff_lengths(left + ZB_NLIT, ZB_NOFF, olen, s.key);
-            int lc = zb_dynamic_cost(left, llen, left + ZB_NLIT, olen, s);
-            zb_huff_lengths(right, ZB_NLIT, llen, s.key);
-            zb_huff_lengths(right + ZB_NLIT, ZB_NOFF, olen, s.key);
-            int rc = zb_dynamic_cost(right, llen, right + ZB_NLIT, olen, s);
-            cdl[c] = nd.total_cost - (lc + rc);
+            zb_huff_lengths(h, ZB_NLIT, llen, s.key);
+            zb_huff_lengths(h + ZB_NLIT, ZB_NOFF, olen, s.key);
+            cdl[y] = zb_dynamic_cost(h, llen, h + ZB_NLIT, olen, s);
          }, 64);
          /* S5: best candidate per node (first maximum, delta >= 0), emit children */
          zb_memset(st, cn + 2, 0, 4);
@@ -1049,7 +1100,7 @@ inline void ZbPipe::stage_split() {
             int best = -1; uint32_t bestk = 0;
             for (uint32_t k = 1; k < nd.nchk; k++) {
                if (!cf[nd.chk_base + k]) continue;
-               int d = cdl[nd.chk_base + k];
+               int d = nd.total_cost - (cdl[2 * (nd.chk_base + k)] + cdl[2 * (nd.chk_base + k) + 1]);
                if (d >= 0 && (best < 0 || best < d)) { if (best < 0 || best < d) { best = d; bestk = k; } }
             }
             if (best >= 0) {
@@ -1199,19 +1250,25 @@ __device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const
 
 /* the 259 relative costs at `pos0` (the signature two neighbouring chunks are compared by), read back from the scratch row:
    position p was done at step from - 1 - p; positions at and above `from` are the zero guess */
-__device__ __forceinline__ void zb_dp_signature(int16_t *dst, const uint16_t *far0, int pos0, int from, int end, int t, uint32_t cprev, bool warm) {
+__device__ __forceinline__ void zb_dp_signature(int16_t *__restrict__ dst, size_t SS, const uint16_t *__restrict__ far0, int pos0, int from, int end, int t, uint32_t cprev, bool warm) {
    const int NT = ZB_DP_THREADS;
-   for (int q = 0; q <= ZB_MAX_MATCH; q++) {
-      const int tt = t - 1 - q;
-      const bool in = warm ? (pos0 + q <= end && pos0 + q <= from) : (pos0 + q <= end);
-      const uint32_t v = tt >= 0 ? (uint32_t)far0[(size_t)tt * NT] : 0u;
-      dst[q] = in ? (int16_t)(uint16_t)(v - cprev) : (int16_t)0;
+   /* loads batched 8 deep: each is an L2 round trip, and nothing else of this thread is in flight here */
+   for (int q0 = 0; q0 <= ZB_MAX_MATCH; q0 += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { const int tt = t - 1 - (q0 + j); v[j] = (tt >= 0 && q0 + j <= ZB_MAX_MATCH) ? (uint32_t)far0[(size_t)tt * NT] : 0u; }
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+         const int q = q0 + j;
+         const bool in = warm ? (pos0 + q <= end && pos0 + q <= from) : (pos0 + q <= end);
+         if (q <= ZB_MAX_MATCH) dst[(size_t)q * SS] = in ? (int16_t)(uint16_t)(v[j] - cprev) : (int16_t)0;
+      }
    }
 }
 
 __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
                                                                const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw,
-                                                               uint16_t *far, int CD, int WU) {
+                                                               size_t SS, uint16_t *far, int CD, int WU) {
    __shared__ uint16_t ring_s[ZB_NR * ZB_DP_THREADS];
    __shared__ ZbCostTab tab_s[ZB_DP_THREADS / 32];
    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
@@ -1240,20 +1297,20 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
    const int end = (int)s.pe;
    int from = hi + WU; if (from > end) from = end;
    uint16_t *far0 = far + (size_t)blockIdx.x * (size_t)(CD + WU) * ZB_DP_THREADS + threadIdx.x;
-   int16_t *sw = sgw + (size_t)c * 260, *sg = sgt + (size_t)c * 260;
+   int16_t *sw = sgw + (size_t)c, *sg = sgt + (size_t)c;
    int step = 0; uint32_t cprev = 0;
    if (x == x0) {
       const uint8_t *plit = tab_s[wi].lit, *plen = tab_s[wi].len, *poff = tab_s[wi].off;
       zb_dp_range<false>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
-      zb_dp_signature(sw, far0, hi, from, end, step, cprev, true);
+      zb_dp_signature(sw, SS, far0, hi, from, end, step, cprev, true);
       zb_dp_range<true>(t, m0, plit, plen, poff, lo, hi, end, b0, ring0, far0, step, cprev);
    } else {
       const uint8_t *plit = tb[x].cost.lit, *plen = tb[x].cost.len, *poff = tb[x].cost.off;
       zb_dp_range<false>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
-      zb_dp_signature(sw, far0, hi, from, end, step, cprev, true);
+      zb_dp_signature(sw, SS, far0, hi, from, end, step, cprev, true);
       zb_dp_range<true>(t, m0, plit, plen, poff, lo, hi, end, b0, ring0, far0, step, cprev);
    }
-   zb_dp_signature(sg, far0, lo, from, end, step, cprev, false);
+   zb_dp_signature(sg, SS, far0, lo, from, end, step, cprev, false);
 }
 
 /* ---- repair of wrong chunks: the same recurrence, ONE WARP per chain ----
@@ -1420,7 +1477,7 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
    verifies again afterwards, so a race with a neighbouring run costs a round, never correctness. */
 __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, const uint32_t *badlist, int nbad, const uint8_t *ok,
                                                                 const ZbWinDesc *wd, const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm,
-                                                                int16_t *sgt, int16_t *sgw, int CD) {
+                                                                int16_t *sgt, int16_t *sgw, size_t SS, int CD) {
    __shared__ ZbDwShared sh_all[ZB_DW_WARPS];
    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
    const long g = (long)blockIdx.x * ZB_DW_WARPS + wi;
@@ -1440,11 +1497,11 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
    {
       const uint32_t *src = (const uint32_t *)&tb[x].cost; uint32_t *dstw = (uint32_t *)&sh.tab;
       for (int e = lane; e < (int)(sizeof(ZbCostTab) / 4); e += 32) dstw[e] = src[e];
-      const int16_t *b = sgt + (size_t)(c + 1) * 260;
-      int16_t *sw = sgw + (size_t)c * 260;
+      const int16_t *b = sgt + (size_t)(c + 1);
+      int16_t *sw = sgw + (size_t)c;
       for (int e = lane; e < ZB_RING; e += 32) ring[e] = 0;
       __syncwarp();
-      for (int e = lane; e <= ZB_MAX_MATCH; e += 32) { int sl = slot - e; if (sl < 0) sl += ZB_RING; const int16_t v = b[e]; ring[sl] = (uint16_t)v; sw[e] = v; }
+      for (int e = lane; e <= ZB_MAX_MATCH; e += 32) { int sl = slot - e; if (sl < 0) sl += ZB_RING; const int16_t v = b[(size_t)e * SS]; ring[sl] = (uint16_t)v; sw[(size_t)e * SS] = v; }
    }
    __syncwarp();
    for (;;) {
@@ -1452,26 +1509,26 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
       zb_dw_run(t, m0, lo, hi, end, b0, sh, slot, lane);
       /* this chunk's true costs at its start */
       const uint16_t b = ring[slot];
-      int16_t *sg = sgt + (size_t)c * 260;
+      int16_t *sg = sgt + (size_t)c;
       for (int e = lane; e <= ZB_MAX_MATCH; e += 32) {
          int sl = slot - e; if (sl < 0) sl += ZB_RING;
-         sg[e] = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
+         sg[(size_t)e * SS] = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
       }
       if ((uint32_t)c == s.dchunk_base) break;
       const long nx = c - 1;
       if (!ok[nx] && ok[c]) break;   /* c had been right, so nx heads a run of its own: another warp owns it */
-      int16_t *sw = sgw + (size_t)nx * 260;
+      int16_t *sw = sgw + (size_t)nx;
       bool same = true;
       for (int e = lane; e <= ZB_MAX_MATCH; e += 32) {
          int sl = slot - e; if (sl < 0) sl += ZB_RING;
          const int16_t v = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
-         if (sw[e] != v) same = false;
+         if (sw[(size_t)e * SS] != v) same = false;
       }
       same = __all_sync(0xffffffffu, same);
       if (ok[nx] && same) break;      /* nx was computed from exactly these costs: the run ends here */
       for (int e = lane; e <= ZB_MAX_MATCH; e += 32) {   /* what chunk nx is now computed from */
          int sl = slot - e; if (sl < 0) sl += ZB_RING;
-         sw[e] = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
+         sw[(size_t)e * SS] = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
       }
       c = nx;
       __syncwarp();
@@ -1547,6 +1604,7 @@ inline void ZbPipe::stage_parse() {
    });
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
    const zb_match_t *mt = match.p; zb_match_t *bm = best.p;
+   const size_t SS = (size_t)ndch + 1;   /* signatures are stored [entry][chunk]: neighbouring chunks' accesses coalesce */
    int16_t *sgt = sig_true.p, *sgw = sig_warm.p, *sgn = sig_new.p; uint8_t *ok = dok.p; uint32_t *bad = dbad.p; (void)sgn;
    uint16_t *ex = exitoff.p; uint32_t *pen = pentry.p;
 
@@ -1557,7 +1615,7 @@ inline void ZbPipe::stage_parse() {
 #ifndef ZB_EMU
       if (ndch > 0) {
          if (g_zb_prof_on) { zb_tag("parse_dp"); zb_prof_begin(0, st); }
-         zb_parse_dp_k<<<(unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS), ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, dpfar.p, CD, WU);
+         zb_parse_dp_k<<<(unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS), ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
          if (g_zb_prof_on) zb_prof_end(st);
          zb_count_launch(1);
          ZB_CUDA_CHECK(cudaGetLastError());
@@ -1581,20 +1639,20 @@ inline void ZbPipe::stage_parse() {
          if (from > hi) zb_parse_range(t, mt + ((size_t)gb << 3), ct, hi, from, end, hi, bm + gb, ring, slot);
          /* warm-up view of the window [hi, hi+258] */
          {
-            int16_t *sw = sgw + (size_t)c * 260;
+            int16_t *sw = sgw + (size_t)c;
             const uint16_t b = ring.get(slot);
             for (int q = 0; q <= ZB_MAX_MATCH; q++) {
                int sl = slot - q; if (sl < 0) sl += ZB_RING;
-               sw[q] = (hi + q <= end && hi + q <= from) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
+               sw[(size_t)q * SS] = (hi + q <= end && hi + q <= from) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
             }
          }
          zb_parse_range(t, mt + ((size_t)gb << 3), ct, lo, hi, end, hi, bm + gb, ring, slot);
          {
-            int16_t *sg = sgt + (size_t)c * 260;
+            int16_t *sg = sgt + (size_t)c;
             const uint16_t b = ring.get(slot);
             for (int q = 0; q <= ZB_MAX_MATCH; q++) {
                int sl = slot - q; if (sl < 0) sl += ZB_RING;
-               sg[q] = (lo + q <= end) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
+               sg[(size_t)q * SS] = (lo + q <= end) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
             }
          }
       }, 64);
@@ -1613,8 +1671,8 @@ inline void ZbPipe::stage_parse() {
             uint8_t good = 1;
             const uint32_t k = (uint32_t)c - s.dchunk_base;
             if (!(pass > 0 && !s.is_dyn) && k + 1 < s.ndchunk) {
-               const int16_t *a = sgw + (size_t)c * 260, *b = sgt + (size_t)(c + 1) * 260;
-               for (int q = 0; q <= ZB_MAX_MATCH && good; q++) if (a[q] != b[q]) good = 0;
+               const int16_t *a = sgw + (size_t)c, *b = sgt + (size_t)(c + 1);
+               for (int q = 0; q <= ZB_MAX_MATCH && good; q++) if (a[(size_t)q * SS] != b[(size_t)q * SS]) good = 0;
             }
             ok[c] = good;
             if (!good) { const int at = zb_atomic_add((int *)cn + 7, 1); bad[at] = (uint32_t)c; }
@@ -1633,7 +1691,7 @@ inline void ZbPipe::stage_parse() {
 #endif
 #ifndef ZB_EMU
          if (g_zb_prof_on) { zb_tag("parse_repair"); zb_prof_begin(0, st); }
-         zb_parse_fix_k<<<(unsigned)((nbad + ZB_DW_WARPS - 1) / ZB_DW_WARPS), ZB_DW_THREADS, 0, st>>>(sb, tb, dcs, bad, (int)nbad, ok, wd, wbs, T, mt, bm, sgt, sgw, CD);
+         zb_parse_fix_k<<<(unsigned)((nbad + ZB_DW_WARPS - 1) / ZB_DW_WARPS), ZB_DW_THREADS, 0, st>>>(sb, tb, dcs, bad, (int)nbad, ok, wd, wbs, T, mt, bm, sgt, sgw, SS, CD);
          if (g_zb_prof_on) zb_prof_end(st);
          zb_count_launch(1);
          ZB_CUDA_CHECK(cudaGetLastError());
@@ -1650,23 +1708,23 @@ inline void ZbPipe::stage_parse() {
             const ZbCostTab &ct = tb[x].cost;
             const int lo = (int)(s.ps + k * CD), hi = lo + CD;
             ZbRingLocal ring;
-            const int16_t *b = sgt + (size_t)(c + 1) * 260;
-            int16_t *sw = sgw + (size_t)c * 260;
+            const int16_t *b = sgt + (size_t)(c + 1);
+            int16_t *sw = sgw + (size_t)c;
             int slot = 0;
-            for (int q = 0; q <= ZB_MAX_MATCH; q++) { int sl = slot - q; if (sl < 0) sl += ZB_RING; ring.v[sl] = (uint16_t)b[q]; sw[q] = b[q]; }
+            for (int q = 0; q <= ZB_MAX_MATCH; q++) { int sl = slot - q; if (sl < 0) sl += ZB_RING; ring.v[sl] = (uint16_t)b[(size_t)q * SS]; sw[(size_t)q * SS] = b[(size_t)q * SS]; }
             zb_parse_range(t, mt + ((size_t)gb << 3), ct, lo, hi, end, hi, bm + gb, ring, slot);
             /* the new costs at this chunk's start go to a staging row: neighbours still read the old row this round */
-            int16_t *sg = sgn + (size_t)c * 260;
+            int16_t *sg = sgn + (size_t)c;
             const uint16_t b0 = ring.get(slot);
             for (int q = 0; q <= ZB_MAX_MATCH; q++) {
                int sl = slot - q; if (sl < 0) sl += ZB_RING;
-               sg[q] = (lo + q <= end) ? (int16_t)(uint16_t)(ring.get(sl) - b0) : (int16_t)0;
+               sg[(size_t)q * SS] = (lo + q <= end) ? (int16_t)(uint16_t)(ring.get(sl) - b0) : (int16_t)0;
             }
          }, 32);
          zb_launch(st, ndch, ZB_LAMBDA(long c) {
             if (ok[c]) return;
-            int16_t *sg = sgt + (size_t)c * 260; const int16_t *sn = sgn + (size_t)c * 260;
-            for (int q = 0; q <= ZB_MAX_MATCH; q++) sg[q] = sn[q];
+            int16_t *sg = sgt + (size_t)c; const int16_t *sn = sgn + (size_t)c;
+            for (int q = 0; q <= ZB_MAX_MATCH; q++) sg[(size_t)q * SS] = sn[(size_t)q * SS];
          });
 #endif
       }
