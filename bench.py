@@ -83,16 +83,18 @@ def ncu_traffic(kernel):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is started
+    before the warm-up (nvidia-smi needs a few hundred ms to deliver its first row); every row is stamped on arrival and only
+    rows that fall inside [mark_begin, mark_end] are reported (all rows under load if the region was shorter than a period)."""
 
     def __init__(self, index=0):
-        self.rows, self.p, self.index = [], None, index
+        self.rows, self.p, self.index, self.t0, self.t1 = [], None, index, None, None
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index),
                                        "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-                                       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
+                                       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -101,21 +103,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)   # let the row sampled at the end of the region arrive
         self.p.terminate()
         try:
             self.p.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.p.kill()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
+        rows = inside if inside else [r for (t, r) in self.rows if self.t0 is None or t >= self.t0 - 1.0]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(rows)}
 
 
 def cpu_reference_timing(data, flags, threads, slice_bytes):
@@ -235,6 +246,9 @@ def main():
         L.zultra_cuda_profile(0)
         return ms
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step(False)
     # parity gate before any timing counts: the stream must inflate back to the input (and equal the 1-GPU stream)
@@ -249,13 +263,12 @@ def main():
             one = z.memory_compress(data, w["flags"], block)
             assert one == stream, "sharded stream differs from the single-GPU stream"
         del raw
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     times, launches = [], 0
+    sampler.mark_begin()
     for _ in range(args.steps):
         times.append(step(not args.no_profile))
         launches += ctx.counters()["launches"]
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     names = C.create_string_buffer(32 * 256); kms = (C.c_float * 256)(); kcnt = (C.c_int * 256)()
     nk = L.zultra_cuda_profile_collect(names, kms, kcnt, 256)
