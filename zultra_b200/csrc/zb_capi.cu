@@ -370,9 +370,11 @@ int zultra_cuda_memory_compress_batch(zultra_cuda_ctx_t *c, const unsigned char 
       std::vector<ZbStreamRes> res;
       ZbRunOpts o;
       o.checksum_kind = (flags & 2) ? 2 : ((flags & 1) ? 1 : 0);
+      o.want_out_ptr = 1;
       c->pipe.counters.need(64);
       zb_memset(c->pipe.st, c->pipe.counters.p, 0, 64 * 4);
       if (!s.empty() && zb_run_batch(c->pipe, s.data(), (int)s.size(), block, c->out, res, o)) return ctx_leave(c, ZULTRA_CUDA_ERR_CUDA);
+      const uint8_t *obase = o.out_ptr ? o.out_ptr : c->out.data();
       for (int k = 0; k < 8; k++) ms[k] += o.ms[k];
       size_t k = 0;
       for (size_t i = i0; i < i1; i++) {
@@ -381,7 +383,7 @@ int zultra_cuda_memory_compress_batch(zultra_cuda_ctx_t *c, const unsigned char 
          if (hdr + nb + ftr > out_caps[i]) out_sizes[i] = (size_t)-1;
          else {
             size_t w = put_header(outp[i], flags);
-            memcpy(outp[i] + w, c->out.data() + res[k].out_off, nb); w += nb;
+            memcpy(outp[i] + w, obase + res[k].out_off, nb); w += nb;
             w += put_footer(outp[i] + w, flags, res[k].checksum, in_sizes[i]);
             out_sizes[i] = w;
          }

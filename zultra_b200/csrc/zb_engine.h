@@ -6,6 +6,8 @@
 #define ZB_ENGINE_H
 #include "zb_pipeline.h"
 #include <chrono>
+#include <thread>
+#include <vector>
 
 struct ZbStreamIn {
    const uint8_t *data; size_t n;          /* bytes to compress in this call (whole max-blocks except possibly the last) */
@@ -29,6 +31,8 @@ struct ZbRunOpts {
    unsigned long long phase_bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
    uint8_t *dev_out = 0; size_t dev_out_cap = 0;   /* leave the bitstream of stream 0 in device memory instead of copying back */
    uint8_t *host_out = 0; size_t host_out_cap = 0; /* single stream: copy the bitstream straight into the caller's buffer (no staging vector) */
+   int want_out_ptr = 0;           /* several streams: leave the bitstreams in the pipe's page-locked buffer; res[i].out_off is relative to out_ptr */
+   const uint8_t *out_ptr = 0;
    ZbDump *dump = 0;
    int stop_after = 99;            /* 1 = SA, 2 = match (stage dumps) */
    float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* h2d, sa, match, greedy+split, parse, emit, d2h, total */
@@ -61,16 +65,37 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
    for (int i = 0; i < ns; i++) in_bytes += s[i].hist_len + s[i].n;
    if (in_bytes >= ((size_t)1 << 31)) return -1;
    ZbTimer tm, tot;
-   std::vector<uint8_t> stage;
-   /* copy straight from the caller's buffer when [history | data] is contiguous there */
+   /* copy straight from the caller's buffer when [history | data] is contiguous there; otherwise gather the streams into
+      page-locked memory (several host threads: a single memcpy stream does not keep up with the DMA that follows) */
    const bool single_direct = (ns == 1 && !o.dev_in && (s[0].hist_len == 0 || s[0].hist + s[0].hist_len == s[0].data));
-   if (!o.dev_in && !single_direct) stage.resize(in_bytes);
+   uint8_t *stage = 0;
+   if (!o.dev_in && !single_direct) {
+      p.hin.need(in_bytes + 16);
+      stage = p.hin.p;
+      std::vector<size_t> offs(ns + 1, 0);
+      for (int i = 0; i < ns; i++) offs[i + 1] = offs[i] + s[i].hist_len + s[i].n;
+      const int nth = in_bytes > ((size_t)8 << 20) ? 4 : 1;
+      auto gather = [&](int a, int b) {
+         for (int i = a; i < b; i++) {
+            if (s[i].hist_len) memcpy(stage + offs[i], s[i].hist, s[i].hist_len);
+            memcpy(stage + offs[i] + s[i].hist_len, s[i].data, s[i].n);
+         }
+      };
+      if (nth == 1) gather(0, ns);
+      else {
+         std::vector<std::thread> th;
+         int a = 0;
+         for (int k = 0; k < nth; k++) {   /* equal byte shares */
+            int b = a;
+            while (b < ns && (k == nth - 1 || offs[b] < in_bytes / nth * (k + 1))) b++;
+            th.emplace_back(gather, a, b);
+            a = b;
+         }
+         for (auto &t : th) t.join();
+      }
+   }
    size_t off = 0, total_block = 0;
    for (int i = 0; i < ns; i++) {
-      if (!o.dev_in && !single_direct) {
-         if (s[i].hist_len) memcpy(stage.data() + off, s[i].hist, s[i].hist_len);
-         memcpy(stage.data() + off + s[i].hist_len, s[i].data, s[i].n);
-      }
       memset(&so[i], 0, sizeof(ZbStreamOut));
       so[i].first_win = (uint32_t)wins.size();
       so[i].in_bits = s[i].in_bits;
@@ -94,7 +119,7 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
    res.assign(ns, ZbStreamRes());
    for (int i = 0; i < ns; i++) res[i].checksum = s[i].checksum;
    if (wins.empty()) { out.clear(); return 0; }
-   p.setup(wins, o.dev_in ? o.dev_in : (single_direct ? s[0].data - s[0].hist_len : stage.data()), in_bytes, o.dev_in != 0);
+   p.setup(wins, o.dev_in ? o.dev_in : (single_direct ? s[0].data - s[0].hist_len : stage), in_bytes, o.dev_in != 0);
    zb_sync(p.st); o.ms[0] = tm.lap(); o.t_abs[0] = zb_now_ms();
    p.stage_sa();
    zb_sync(p.st); o.ms[1] = tm.lap(); o.t_abs[1] = zb_now_ms();
@@ -144,12 +169,18 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
             zb_sync(p.st);
             out.resize(ob);
          } else {
-            std::vector<uint32_t> words(total_words + 1);
-            zb_d2h(p.st, words.data(), p.out.p, total_words * 4);
+            p.hout.need(total_words * 4 + 16);
+            zb_d2h(p.st, p.hout.p, p.out.p, total_words * 4);
             zb_sync(p.st);
-            out.resize(ob);
-            for (int i = 0; i < ns; i++)
-               memcpy(out.data() + res[i].out_off, (const uint8_t *)(words.data() + p.h_sout[i].out_word_off), (size_t)((p.h_sout[i].total_bits + 7) / 8));
+            if (o.want_out_ptr) {   /* the caller copies each stream out of the page-locked buffer itself */
+               o.out_ptr = p.hout.p;
+               for (int i = 0; i < ns; i++) res[i].out_off = (size_t)p.h_sout[i].out_word_off * 4;
+               out.clear();
+            } else {
+               out.resize(ob);
+               for (int i = 0; i < ns; i++)
+                  memcpy(out.data() + res[i].out_off, p.hout.p + (size_t)p.h_sout[i].out_word_off * 4, (size_t)((p.h_sout[i].total_bits + 7) / 8));
+            }
          }
       }
       o.ms[6] = tm.lap();

@@ -95,8 +95,15 @@ template <class T> struct ZbBuf {
    void release() { zb_dev_free(p); p = 0; cap = 0; }
 };
 
+struct ZbHostBuf {   /* grow-only page-locked host buffer */
+   uint8_t *p = 0; size_t cap = 0;
+   void need(size_t n) { if (n > cap) { zb_host_free(p); size_t c = n + n / 8 + 4096; p = (uint8_t *)zb_host_alloc(c); cap = p ? c : 0; } }
+   void release() { zb_host_free(p); p = 0; cap = 0; }
+};
+
 struct ZbPipe {
    zb_stream_t st;
+   ZbHostBuf hin, hout;         /* staging of multi-stream batches */
    /* batch description */
    int nwin = 0, nstream = 0;
    uint32_t P = 0;              /* total window positions */
@@ -487,7 +494,10 @@ __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *
       for (int jb = i - 1; jb > best && !done; jb -= 32) {
          const int j = jb - lane;
          bool hit = false;
-         if (j > best) hit = ((uint32_t)txt[j] | ((uint32_t)txt[j + 1] << 8) | ((uint32_t)txt[j + 2] << 16)) == k3;
+         if (j > best) {   /* bytes j..j+2 out of the two aligned words around them (the buffer is padded by a word) */
+            const uint32_t w0 = zb_smw[j >> 2], w1 = zb_smw[(j >> 2) + 1];
+            hit = (__funnelshift_r(w0, w1, (uint32_t)(j & 3) << 3) & 0xffffffu) == k3;
+         }
          uint32_t hits = __ballot_sync(0xffffffffu, hit);
          while (hits && !done) {
             const int h = __ffs((int)hits) - 1;
@@ -1180,7 +1190,15 @@ ZB_HD void zb_walk_best(const zb_match_t *best, uint32_t entry, uint32_t hi, F &
 #define ZB_NR 64              /* near ring entries */
 #define ZB_DP_INF 0x7fffffffu
 
-template <bool KEEP>
+/* cost of an offset: OT = the warp's 512-entry table indexed like the reference's g_nOffsetSymbol (blockdeflate.c:45,150:
+   o - 1 for o <= 256, else 256 + ((o - 257) >> 7)); otherwise the symbol is computed and looked up in the sub-block's table */
+template <bool OT>
+__device__ __forceinline__ uint32_t zb_dp_offcost(const uint8_t *__restrict__ poff, uint32_t off) {
+   if (OT) { const uint32_t d = off - 1u; return poff[d < 256u ? d : 256u + ((d - 256u) >> 7)]; }
+   return poff[zb_off_sym(off)];
+}
+
+template <bool KEEP, bool OT>
 __device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const zb_match_t *__restrict__ match, const uint8_t *__restrict__ plit,
                                             const uint8_t *__restrict__ plen, const uint8_t *__restrict__ poff, int lo, int from, int end,
                                             zb_match_t *__restrict__ best, uint16_t *ring0, uint16_t *far0, int &t_io, uint32_t &cprev_io) {
@@ -1210,7 +1228,7 @@ __device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const
          for (int m = ZB_NMATCH - 1; m >= 0; m--) {
             if (m < M) {
                const int mlen0 = (int)(rec.w[m] & 0xffffu), moff = (int)(rec.w[m] >> 16);
-               const uint32_t offc = poff[zb_off_sym((uint32_t)moff)];
+               const uint32_t offc = zb_dp_offcost<OT>(poff, (uint32_t)moff);
                int ml = mlen0;
                if (i + ml > end) ml = end - i;
                uint32_t total; int kk;
@@ -1271,6 +1289,7 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
                                                                size_t SS, uint16_t *far, int CD, int WU) {
    __shared__ uint16_t ring_s[ZB_NR * ZB_DP_THREADS];
    __shared__ ZbCostTab tab_s[ZB_DP_THREADS / 32];
+   __shared__ uint8_t offtab_s[ZB_DP_THREADS / 32][512];
    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
    const long cw = (long)blockIdx.x * ZB_DP_THREADS + wi * 32;
    if (cw >= ndch) return;                /* the whole warp */
@@ -1282,6 +1301,8 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
    }
    uint16_t *ring0 = ring_s + threadIdx.x;
    for (int e = 0; e < ZB_NR; e++) ring0[e * ZB_DP_THREADS] = 0;
+   __syncwarp();
+   for (int e = lane; e < 512; e += 32) offtab_s[wi][e] = tab_s[wi].off[zb_off_sym(e < 256 ? (uint32_t)e + 1u : 257u + ((uint32_t)(e - 256) << 7))];
    __syncwarp();
    if (c >= ndch) return;
    const uint32_t x = dcs[c];
@@ -1300,15 +1321,15 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
    int16_t *sw = sgw + (size_t)c, *sg = sgt + (size_t)c;
    int step = 0; uint32_t cprev = 0;
    if (x == x0) {
-      const uint8_t *plit = tab_s[wi].lit, *plen = tab_s[wi].len, *poff = tab_s[wi].off;
-      zb_dp_range<false>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
+      const uint8_t *plit = tab_s[wi].lit, *plen = tab_s[wi].len, *poff = offtab_s[wi];
+      zb_dp_range<false, true>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
       zb_dp_signature(sw, SS, far0, hi, from, end, step, cprev, true);
-      zb_dp_range<true>(t, m0, plit, plen, poff, lo, hi, end, b0, ring0, far0, step, cprev);
+      zb_dp_range<true, true>(t, m0, plit, plen, poff, lo, hi, end, b0, ring0, far0, step, cprev);
    } else {
       const uint8_t *plit = tb[x].cost.lit, *plen = tb[x].cost.len, *poff = tb[x].cost.off;
-      zb_dp_range<false>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
+      zb_dp_range<false, false>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
       zb_dp_signature(sw, SS, far0, hi, from, end, step, cprev, true);
-      zb_dp_range<true>(t, m0, plit, plen, poff, lo, hi, end, b0, ring0, far0, step, cprev);
+      zb_dp_range<true, false>(t, m0, plit, plen, poff, lo, hi, end, b0, ring0, far0, step, cprev);
    }
    zb_dp_signature(sg, SS, far0, lo, from, end, step, cprev, false);
 }
@@ -2169,7 +2190,7 @@ inline void ZbPipe::release_all() {
    gtokcnt.release(); gtokbase.release(); tokpos.release(); wtok.release(); wtokbase.release(); wintbase.release(); ph.release();
    gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
    chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();
-   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); dbad.release(); pentry.release(); pbits.release(); dpfar.release(); out.release(); sout.release();
+   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); dbad.release(); pentry.release(); pbits.release(); dpfar.release(); hin.release(); hout.release(); out.release(); sout.release();
 }
 
 

@@ -24,6 +24,8 @@ template <class F> static inline void zb_launch_(int, zb_stream_t, long n, F f, 
 static inline void zb_tag(const char *) {}
 static inline void *zb_dev_alloc(size_t n) { void *p = malloc(n ? n : 1); if (!p) { fprintf(stderr, "emu alloc fail\n"); abort(); } return p; }
 static inline void zb_dev_free(void *p) { free(p); }
+static inline void *zb_host_alloc(size_t n) { return malloc(n ? n : 1); }
+static inline void zb_host_free(void *p) { free(p); }
 static inline void zb_memset(zb_stream_t, void *p, int v, size_t n) { memset(p, v, n); }
 static inline void zb_h2d(zb_stream_t, void *d, const void *h, size_t n) { memcpy(d, h, n); }
 static inline void zb_d2h(zb_stream_t, void *h, const void *d, size_t n) { memcpy(h, d, n); }
@@ -57,7 +59,8 @@ template <class F> static inline void zb_launch_(int line, zb_stream_t st, long 
    if (n <= 0) { zb_tag(0); return; }
    /* few tasks are the serial per-sub-block / per-node ones (Huffman builds, splitter scans): give each its own warp, so that
       32 unrelated control flows do not serialise inside one, and its own SM share instead of crowding two SMs */
-   if (n <= 4096) blk = 1;
+   static const long heavy_max = getenv("ZULTRA_CUDA_HEAVY_SINGLE_MAX") ? atol(getenv("ZULTRA_CUDA_HEAVY_SINGLE_MAX")) : 4096;
+   if (n <= (blk == 64 ? heavy_max : 4096)) blk = 1;   /* blk == 64 marks the heavy serial tasks at their call sites */
    if (g_zb_prof_on) zb_prof_begin(line, st);
    zb_task_kernel<<<(unsigned)((n + blk - 1) / blk), blk, 0, st>>>(n, f);
    if (g_zb_prof_on) zb_prof_end(st);
@@ -66,6 +69,9 @@ template <class F> static inline void zb_launch_(int line, zb_stream_t st, long 
 }
 void *zb_dev_alloc(size_t n);
 void zb_dev_free(void *p);
+/* page-locked host staging memory (multi-stream batches are gathered into / scattered out of it around one DMA each way) */
+static inline void *zb_host_alloc(size_t n) { void *p = 0; ZB_CUDA_CHECK(cudaHostAlloc(&p, n ? n : 1, cudaHostAllocDefault)); return p; }
+static inline void zb_host_free(void *p) { if (p) cudaFreeHost(p); }
 static inline void zb_memset(zb_stream_t st, void *p, int v, size_t n) { if (n) ZB_CUDA_CHECK(cudaMemsetAsync(p, v, n, st)); }
 static inline void zb_h2d(zb_stream_t st, void *d, const void *h, size_t n) { if (n) ZB_CUDA_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st)); }
 static inline void zb_d2h(zb_stream_t st, void *h, const void *d, size_t n) { if (n) ZB_CUDA_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st)); }
