@@ -272,6 +272,20 @@ inline void ZbPipe::stage_sa() {
          const uint8_t *t = T + wd[w].in_off;
          uint32_t lim = len - (i > q ? i : q);
          if (lim > ZB_MAX_MATCH) lim = ZB_MAX_MATCH;
+#ifdef __CUDA_ARCH__
+         /* four bytes per step out of aligned words (two loads a side): every step is a dependent round trip to L2, so
+            fewer, wider steps.  Only while both 8-byte spans lie inside the input (the first 3 bytes of the buffer and the
+            tail of the window go bytewise). */
+         if (wd[w].in_off + (i < q ? i : q) >= 4) {
+            while (l + 8 <= lim) {
+               const uintptr_t a = (uintptr_t)(t + i + l), b = (uintptr_t)(t + q + l);
+               const uint32_t *pa = (const uint32_t *)(a & ~(uintptr_t)3), *pb = (const uint32_t *)(b & ~(uintptr_t)3);
+               const uint32_t x = __funnelshift_r(pa[0], pa[1], (uint32_t)(a & 3) << 3) ^ __funnelshift_r(pb[0], pb[1], (uint32_t)(b & 3) << 3);
+               if (x) { l += (uint32_t)(__ffs((int)x) - 1) >> 3; lim = l; break; }
+               l += 4;
+            }
+         }
+#endif
          while (l < lim && t[i + l] == t[q + l]) l++;
          if (l < ZB_MIN_MATCH) l = 0;
       }
@@ -717,17 +731,30 @@ __global__ void __launch_bounds__(ZB_SW_THREADS) zb_sweep_k(long nchunk, const Z
       if (p - lo < 258u) row[p - lo] = (uint16_t)e_; \
    } while (0)
    if (MODE == 0) {
+      /* the 16-byte groups are fetched two ahead: the steps are a dependent chain through the ring, a load consumed at
+         once would put a DRAM round trip on it every few steps */
       while (p > lo && ((gb + p) & 7u)) ZB_SW_STEP(gl[gb + p - 1]);
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      uint4 v1 = p >= lo + 8 ? __ldg((const uint4 *)(gl + gb + p - 8)) : z4;
+      uint4 v2 = p >= lo + 16 ? __ldg((const uint4 *)(gl + gb + p - 16)) : z4;
       while (p >= lo + 8) {
-         const uint4 v = __ldg((const uint4 *)(gl + gb + p - 8));
+         const uint4 v = v1;
+         v1 = v2;
+         v2 = p >= lo + 24 ? __ldg((const uint4 *)(gl + gb + p - 24)) : z4;
          ZB_SW_STEP(v.w >> 16); ZB_SW_STEP(v.w & 0xffffu); ZB_SW_STEP(v.z >> 16); ZB_SW_STEP(v.z & 0xffffu);
          ZB_SW_STEP(v.y >> 16); ZB_SW_STEP(v.y & 0xffffu); ZB_SW_STEP(v.x >> 16); ZB_SW_STEP(v.x & 0xffffu);
       }
       while (p > lo) ZB_SW_STEP(gl[gb + p - 1]);
    } else {
       while (p > lo && ((gb + p) & 3u)) ZB_SW_STEP(bm[gb + p - 1].length);
+      const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+      uint4 v1 = p >= lo + 4 ? *(const uint4 *)(bm + gb + p - 4) : z4;
+      uint4 v2 = p >= lo + 8 ? *(const uint4 *)(bm + gb + p - 8) : z4;
+      uint4 v3 = p >= lo + 12 ? *(const uint4 *)(bm + gb + p - 12) : z4;
       while (p >= lo + 4) {
-         const uint4 v = *(const uint4 *)(bm + gb + p - 4);
+         const uint4 v = v1;
+         v1 = v2; v2 = v3;
+         v3 = p >= lo + 16 ? *(const uint4 *)(bm + gb + p - 16) : z4;
          ZB_SW_STEP(v.w & 0xffffu); ZB_SW_STEP(v.z & 0xffffu); ZB_SW_STEP(v.y & 0xffffu); ZB_SW_STEP(v.x & 0xffffu);
       }
       while (p > lo) ZB_SW_STEP(bm[gb + p - 1].length);
@@ -1557,6 +1584,41 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
 }
 #endif
 
+#ifndef ZB_EMU
+/* Histogram along the chosen path (blockdeflate.c:371-400), one thread per path-chunk: the counts of a CTA's chunks are
+   gathered in a shared-memory histogram of the CTA's first sub-block and flushed once (hot symbols would otherwise be one
+   global atomic per token); a chunk of another sub-block (one CTA per sub-block boundary) counts straight into global memory. */
+#define ZB_PH_THREADS 128
+__global__ void __launch_bounds__(ZB_PH_THREADS) zb_path_hist_k(long npch, const ZbSub *sb, ZbSubTabs *tb, const uint32_t *pcs, const ZbWinDesc *wd, const uint32_t *wbs,
+                                                                const uint8_t *T, const zb_match_t *bm, const uint32_t *pen) {
+   __shared__ int hl[ZB_NLIT], ho[ZB_NOFF];
+   const long c0 = (long)blockIdx.x * ZB_PH_THREADS, c = c0 + threadIdx.x;
+   const uint32_t x0 = pcs[c0];
+   for (int e = threadIdx.x; e < ZB_NLIT; e += ZB_PH_THREADS) hl[e] = 0;
+   if (threadIdx.x < ZB_NOFF) ho[threadIdx.x] = 0;
+   __syncthreads();
+   if (c < npch) {
+      const uint32_t x = pcs[c];
+      const ZbSub s = sb[x];
+      if (s.is_dyn) {
+         const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
+         const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+         const uint8_t *t = T + wd[s.win].in_off;
+         int *lc = x == x0 ? hl : tb[x].lcnt, *oc = x == x0 ? ho : tb[x].ocnt;
+         for (uint32_t p = pen[c]; p < hi;) {
+            const zb_match_t m = bm[gb + p];
+            if (m.length >= ZB_MIN_MATCH) { atomicAdd(lc + zb_len_sym(m.length - ZB_MIN_MATCH), 1); atomicAdd(oc + zb_off_sym(m.offset), 1); p += m.length; }
+            else { atomicAdd(lc + t[p], 1); p++; }
+         }
+      }
+   }
+   __syncthreads();
+   if (!sb[x0].is_dyn) return;
+   for (int e = threadIdx.x; e < ZB_NLIT; e += ZB_PH_THREADS) if (hl[e]) atomicAdd(tb[x0].lcnt + e, hl[e]);
+   if (threadIdx.x < ZB_NOFF && ho[threadIdx.x]) atomicAdd(tb[x0].ocnt + threadIdx.x, ho[threadIdx.x]);
+}
+#endif
+
 inline void ZbPipe::stage_parse() {
    /* One thread per chunk: the chunk count is the parallelism.  ZB_CD positions per chunk when that still gives ~40 K chunks,
       shorter chunks (more warm-up overhead, shorter serial chains) for small batches such as one GPU's shard of a stream. */
@@ -1794,6 +1856,15 @@ inline void ZbPipe::stage_parse() {
       });
 #endif
       /* D6: histogram along the chosen path (blockdeflate.c:371-400) */
+#ifndef ZB_EMU
+      if (npch > 0) {
+         if (g_zb_prof_on) { zb_tag("path_hist"); zb_prof_begin(0, st); }
+         zb_path_hist_k<<<(unsigned)((npch + ZB_PH_THREADS - 1) / ZB_PH_THREADS), ZB_PH_THREADS, 0, st>>>(npch, sb, tb, pcs, wd, wbs, T, bm, pen);
+         if (g_zb_prof_on) zb_prof_end(st);
+         zb_count_launch(1);
+         ZB_CUDA_CHECK(cudaGetLastError());
+      }
+#else
       zb_launch(st, npch, ZB_LAMBDA(long c) {
          const uint32_t x = pcs[c];
          const ZbSub s = sb[x];
@@ -1808,6 +1879,7 @@ inline void ZbPipe::stage_parse() {
             else { zb_atomic_add(lc + t[p], 1); p++; }
          }
       });
+#endif
       /* D7: rebuild tables (blockdeflate.c:893-919) */
       zb_launch(st, ns, ZB_LAMBDA(long x) {
          ZbSub s = sb[x];
