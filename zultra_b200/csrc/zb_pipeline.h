@@ -731,32 +731,36 @@ __global__ void __launch_bounds__(ZB_SW_THREADS) zb_sweep_k(long nchunk, const Z
       if (p - lo < 258u) row[p - lo] = (uint16_t)e_; \
    } while (0)
    if (MODE == 0) {
-      /* the 16-byte groups are fetched two ahead: the steps are a dependent chain through the ring, a load consumed at
-         once would put a DRAM round trip on it every few steps */
+      /* the 16-byte groups are fetched two ahead into three registers used in rotation (no copies: a register move would
+         wait for the load it forwards): the steps are a dependent chain through the ring, a load consumed at once would put
+         a DRAM round trip on it every few steps */
       while (p > lo && ((gb + p) & 7u)) ZB_SW_STEP(gl[gb + p - 1]);
       const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-      uint4 v1 = p >= lo + 8 ? __ldg((const uint4 *)(gl + gb + p - 8)) : z4;
-      uint4 v2 = p >= lo + 16 ? __ldg((const uint4 *)(gl + gb + p - 16)) : z4;
-      while (p >= lo + 8) {
-         const uint4 v = v1;
-         v1 = v2;
-         v2 = p >= lo + 24 ? __ldg((const uint4 *)(gl + gb + p - 24)) : z4;
-         ZB_SW_STEP(v.w >> 16); ZB_SW_STEP(v.w & 0xffffu); ZB_SW_STEP(v.z >> 16); ZB_SW_STEP(v.z & 0xffffu);
-         ZB_SW_STEP(v.y >> 16); ZB_SW_STEP(v.y & 0xffffu); ZB_SW_STEP(v.x >> 16); ZB_SW_STEP(v.x & 0xffffu);
+#define ZB_SW_LD0(k_) (p >= lo + (k_) ? __ldg((const uint4 *)(gl + gb + p - (k_))) : z4)
+#define ZB_SW_PROC0(v) do { ZB_SW_STEP((v).w >> 16); ZB_SW_STEP((v).w & 0xffffu); ZB_SW_STEP((v).z >> 16); ZB_SW_STEP((v).z & 0xffffu); \
+                            ZB_SW_STEP((v).y >> 16); ZB_SW_STEP((v).y & 0xffffu); ZB_SW_STEP((v).x >> 16); ZB_SW_STEP((v).x & 0xffffu); } while (0)
+      uint4 va = ZB_SW_LD0(8), vb = ZB_SW_LD0(16), vc = ZB_SW_LD0(24);
+      for (;;) {
+         if (p < lo + 8) break; ZB_SW_PROC0(va); va = ZB_SW_LD0(24);
+         if (p < lo + 8) break; ZB_SW_PROC0(vb); vb = ZB_SW_LD0(24);
+         if (p < lo + 8) break; ZB_SW_PROC0(vc); vc = ZB_SW_LD0(24);
       }
+#undef ZB_SW_LD0
+#undef ZB_SW_PROC0
       while (p > lo) ZB_SW_STEP(gl[gb + p - 1]);
    } else {
       while (p > lo && ((gb + p) & 3u)) ZB_SW_STEP(bm[gb + p - 1].length);
       const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-      uint4 v1 = p >= lo + 4 ? *(const uint4 *)(bm + gb + p - 4) : z4;
-      uint4 v2 = p >= lo + 8 ? *(const uint4 *)(bm + gb + p - 8) : z4;
-      uint4 v3 = p >= lo + 12 ? *(const uint4 *)(bm + gb + p - 12) : z4;
-      while (p >= lo + 4) {
-         const uint4 v = v1;
-         v1 = v2; v2 = v3;
-         v3 = p >= lo + 16 ? *(const uint4 *)(bm + gb + p - 16) : z4;
-         ZB_SW_STEP(v.w & 0xffffu); ZB_SW_STEP(v.z & 0xffffu); ZB_SW_STEP(v.y & 0xffffu); ZB_SW_STEP(v.x & 0xffffu);
+#define ZB_SW_LD1(k_) (p >= lo + (k_) ? *(const uint4 *)(bm + gb + p - (k_)) : z4)
+#define ZB_SW_PROC1(v) do { ZB_SW_STEP((v).w & 0xffffu); ZB_SW_STEP((v).z & 0xffffu); ZB_SW_STEP((v).y & 0xffffu); ZB_SW_STEP((v).x & 0xffffu); } while (0)
+      uint4 va = ZB_SW_LD1(4), vb = ZB_SW_LD1(8), vc = ZB_SW_LD1(12);
+      for (;;) {
+         if (p < lo + 4) break; ZB_SW_PROC1(va); va = ZB_SW_LD1(12);
+         if (p < lo + 4) break; ZB_SW_PROC1(vb); vb = ZB_SW_LD1(12);
+         if (p < lo + 4) break; ZB_SW_PROC1(vc); vc = ZB_SW_LD1(12);
       }
+#undef ZB_SW_LD1
+#undef ZB_SW_PROC1
       while (p > lo) ZB_SW_STEP(bm[gb + p - 1].length);
    }
 #undef ZB_SW_STEP
@@ -1605,11 +1609,26 @@ __global__ void __launch_bounds__(ZB_PH_THREADS) zb_path_hist_k(long npch, const
          const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
          const uint8_t *t = T + wd[s.win].in_off;
          int *lc = x == x0 ? hl : tb[x].lcnt, *oc = x == x0 ? ho : tb[x].ocnt;
-         for (uint32_t p = pen[c]; p < hi;) {
-            const zb_match_t m = bm[gb + p];
-            if (m.length >= ZB_MIN_MATCH) { atomicAdd(lc + zb_len_sym(m.length - ZB_MIN_MATCH), 1); atomicAdd(oc + zb_off_sym(m.offset), 1); p += m.length; }
-            else { atomicAdd(lc + t[p], 1); p++; }
+         /* The path is a pointer chase (the next token starts where this one ends); followed load by load it is one DRAM
+            round trip per token.  Instead the chunk's choices are streamed 16 bytes at a time, two groups ahead, through
+            three registers used in rotation, and the positions that are not token starts are skipped. */
+         const uint32_t *bw = (const uint32_t *)bm + gb;
+         uint32_t next = pen[c];
+         uint32_t g = next - ((gb + next) & 3u);            /* group start: (gb + g) % 4 == 0, never below the array */
+#define ZB_PH_LD(k_) (g + (k_) < hi ? *(const uint4 *)(bw + g + (k_)) : make_uint4(0u, 0u, 0u, 0u))
+#define ZB_PH_ONE(w_, pos_) do { const uint32_t pp_ = (pos_); if (pp_ == next && pp_ < hi) { const uint32_t ln_ = (w_) & 0xffffu; \
+            if (ln_ >= ZB_MIN_MATCH) { atomicAdd(lc + zb_len_sym(ln_ - ZB_MIN_MATCH), 1); atomicAdd(oc + zb_off_sym((w_) >> 16), 1); next += ln_; } \
+            else { atomicAdd(lc + t[pp_], 1); next++; } } } while (0)
+#define ZB_PH_PROC(v) do { ZB_PH_ONE((v).x, g); ZB_PH_ONE((v).y, g + 1); ZB_PH_ONE((v).z, g + 2); ZB_PH_ONE((v).w, g + 3); g += 4; } while (0)
+         uint4 va = ZB_PH_LD(0), vb = ZB_PH_LD(4), vc = ZB_PH_LD(8);
+         for (;;) {
+            if (g >= hi) break; ZB_PH_PROC(va); va = ZB_PH_LD(8);
+            if (g >= hi) break; ZB_PH_PROC(vb); vb = ZB_PH_LD(8);
+            if (g >= hi) break; ZB_PH_PROC(vc); vc = ZB_PH_LD(8);
          }
+#undef ZB_PH_LD
+#undef ZB_PH_ONE
+#undef ZB_PH_PROC
       }
    }
    __syncthreads();
