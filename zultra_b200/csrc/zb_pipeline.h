@@ -1613,18 +1613,34 @@ __global__ void __launch_bounds__(ZB_PH_THREADS) zb_path_hist_k(long npch, const
             round trip per token.  Instead the chunk's choices are streamed 16 bytes at a time, two groups ahead, through
             three registers used in rotation, and the positions that are not token starts are skipped. */
          const uint32_t *bw = (const uint32_t *)bm + gb;
-         uint32_t next = pen[c];
-         uint32_t g = next - ((gb + next) & 3u);            /* group start: (gb + g) % 4 == 0, never below the array */
-#define ZB_PH_LD(k_) (g + (k_) < hi ? *(const uint4 *)(bw + g + (k_)) : make_uint4(0u, 0u, 0u, 0u))
-#define ZB_PH_ONE(w_, pos_) do { const uint32_t pp_ = (pos_); if (pp_ == next && pp_ < hi) { const uint32_t ln_ = (w_) & 0xffffu; \
-            if (ln_ >= ZB_MIN_MATCH) { atomicAdd(lc + zb_len_sym(ln_ - ZB_MIN_MATCH), 1); atomicAdd(oc + zb_off_sym((w_) >> 16), 1); next += ln_; } \
-            else { atomicAdd(lc + t[pp_], 1); next++; } } } while (0)
-#define ZB_PH_PROC(v) do { ZB_PH_ONE((v).x, g); ZB_PH_ONE((v).y, g + 1); ZB_PH_ONE((v).z, g + 2); ZB_PH_ONE((v).w, g + 3); g += 4; } while (0)
+         int next = (int)pen[c];
+         const int hi_i = (int)hi, wlen = (int)wd[s.win].len;
+         const long toff = (long)wd[s.win].in_off;
+         int g = next - (int)((gb + (uint32_t)next) & 3u);   /* group start: (gb + g) % 4 == 0; may lie before the window (g < 0), never before the array */
+         /* the 4 text bytes of a group, fetched with it (a literal's symbol must not be one more dependent load): two aligned
+            words and a funnel shift where both lie inside the input, guarded byte loads at the edges */
+         auto text4 = [&](int q) -> uint32_t {
+            if (q >= hi_i) return 0u;
+            if (toff + q >= 4 && q + 8 <= wlen) {
+               const uintptr_t a = (uintptr_t)(t + q);
+               const uint32_t *pa = (const uint32_t *)(a & ~(uintptr_t)3);
+               return __funnelshift_r(pa[0], pa[1], (uint32_t)(a & 3) << 3);
+            }
+            uint32_t w = 0;
+            for (int j = 0; j < 4; j++) if (q + j >= 0 && q + j < wlen) w |= (uint32_t)t[q + j] << (8 * j);
+            return w;
+         };
+#define ZB_PH_LD(k_) (g + (k_) < hi_i ? *(const uint4 *)(bw + g + (k_)) : make_uint4(0u, 0u, 0u, 0u))
+#define ZB_PH_ONE(w_, j_, tw_) do { const int pp_ = g + (j_); if (pp_ == next && pp_ < hi_i) { const uint32_t ln_ = (w_) & 0xffffu; \
+            if (ln_ >= ZB_MIN_MATCH) { atomicAdd(lc + zb_len_sym(ln_ - ZB_MIN_MATCH), 1); atomicAdd(oc + zb_off_sym((w_) >> 16), 1); next += (int)ln_; } \
+            else { atomicAdd(lc + (((tw_) >> (8 * (j_))) & 0xffu), 1); next++; } } } while (0)
+#define ZB_PH_PROC(v, tw_) do { ZB_PH_ONE((v).x, 0, tw_); ZB_PH_ONE((v).y, 1, tw_); ZB_PH_ONE((v).z, 2, tw_); ZB_PH_ONE((v).w, 3, tw_); g += 4; } while (0)
          uint4 va = ZB_PH_LD(0), vb = ZB_PH_LD(4), vc = ZB_PH_LD(8);
+         uint32_t ta = text4(g), tb2 = text4(g + 4), tc = text4(g + 8);
          for (;;) {
-            if (g >= hi) break; ZB_PH_PROC(va); va = ZB_PH_LD(8);
-            if (g >= hi) break; ZB_PH_PROC(vb); vb = ZB_PH_LD(8);
-            if (g >= hi) break; ZB_PH_PROC(vc); vc = ZB_PH_LD(8);
+            if (g >= hi_i) break; ZB_PH_PROC(va, ta); va = ZB_PH_LD(8); ta = text4(g + 8);
+            if (g >= hi_i) break; ZB_PH_PROC(vb, tb2); vb = ZB_PH_LD(8); tb2 = text4(g + 8);
+            if (g >= hi_i) break; ZB_PH_PROC(vc, tc); vc = ZB_PH_LD(8); tc = text4(g + 8);
          }
 #undef ZB_PH_LD
 #undef ZB_PH_ONE
