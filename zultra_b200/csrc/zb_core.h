@@ -20,15 +20,6 @@
 #define ZB_HD inline
 #define ZB_HDN inline
 #endif
-/* Scratch arrays of the heavy serial tasks (Huffman builds, cost evaluations; launched with the ZB_HEAVY marker of zb_rt.h,
-   which always means ONE thread per block): shared memory in device code, plain locals elsewhere.  As local memory a single
-   active lane uses 4 of every 128 bytes of a cache line; 32 such blocks per SM thrash the L1 and every access becomes an L2
-   round trip. */
-#ifdef __CUDA_ARCH__
-#define ZB_TASK_SCRATCH __shared__
-#else
-#define ZB_TASK_SCRATCH
-#endif
 
 /* format constants (format.h:37-50, private.h:41-56) */
 #define ZB_MIN_MATCH 3
@@ -104,8 +95,8 @@ ZB_HD void zb_sort_u32(uint32_t *a, int n) {
       }
       return;
    }
-   ZB_TASK_SCRATCH uint32_t tmp[ZB_NLIT];      /* only called from heavy tasks (one thread per block, zb_rt.h) */
-   ZB_TASK_SCRATCH uint16_t bin[128];
+   uint32_t tmp[ZB_NLIT];
+   uint16_t bin[128];
    uint32_t top = 0;
    for (int i = 0; i < n; i++) top |= a[i];
    int bits = 0;

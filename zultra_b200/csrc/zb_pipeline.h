@@ -1036,7 +1036,7 @@ inline void ZbPipe::stage_split() {
             int *h = nh + (size_t)x * ZB_NH;
             gv.range_hist((int)nd.win, nd.ts, nd.te, h);
             h[ZB_EOB] += 1;
-            ZB_TASK_SCRATCH ZbScratch s; ZB_TASK_SCRATCH int llen[ZB_NLIT], olen[ZB_NLIT];
+            ZbScratch s; int llen[ZB_NLIT], olen[ZB_NLIT];
             zb_huff_lengths(h, ZB_NLIT, llen, s.key);
             zb_huff_lengths(h + ZB_NLIT, ZB_NOFF, olen, s.key);
             nd.total_cost = zb_dynamic_cost(h, llen, h + ZB_NLIT, olen, s);
@@ -1052,7 +1052,7 @@ inline void ZbPipe::stage_split() {
             if (t0 <= ntok) { nd.t0 = t0; nd.nchk = (ntok - t0) / 256 + 1; }
          }
          cur[x] = nd;
-      }, ZB_HEAVY);
+      });
       /* check record bases (serial, few nodes) */
       zb_launch(st, 1, ZB_LAMBDA(long) {
          uint32_t b = 0;
@@ -1121,18 +1121,18 @@ inline void ZbPipe::stage_split() {
             const ZbNode nd = cur[x];
             const uint32_t k = (uint32_t)c - nd.chk_base;   /* k >= 1 here */
             const uint32_t tsplit = nd.t0 + 256 * (k - 1);   /* tokens left of the split */
-            ZB_TASK_SCRATCH int h[ZB_NH];
+            int h[ZB_NH];
             gv.range_hist((int)nd.win, nd.ts, nd.ts + tsplit, h);
             if (right_side) {
                const int *tot = nh + (size_t)x * ZB_NH;
                for (int i = 0; i < ZB_NH; i++) h[i] = tot[i] - h[i];
             }
             h[ZB_EOB] = 1;
-            ZB_TASK_SCRATCH ZbScratch s; ZB_TASK_SCRATCH int llen[ZB_NLIT], olen[ZB_NLIT];
+            ZbScratch s; int llen[ZB_NLIT], olen[ZB_NLIT];
             zb_huff_lengths(h, ZB_NLIT, llen, s.key);
             zb_huff_lengths(h + ZB_NLIT, ZB_NOFF, olen, s.key);
             cdl[y] = zb_dynamic_cost(h, llen, h + ZB_NLIT, olen, s);
-         }, ZB_HEAVY);
+         }, 64);
          /* S5: best candidate per node (first maximum, delta >= 0), emit children */
          zb_memset(st, cn + 2, 0, 4);
          uint32_t *wsp = wsplit.p, *wns = wnsplit.p;
@@ -1669,13 +1669,13 @@ inline void ZbPipe::stage_parse() {
    /* D1: greedy histogram, static-vs-dynamic decision (libzultra.c:317-324), first tables (blockdeflate.c:863-869) */
    zb_launch(st, ns, ZB_LAMBDA(long x) {
       ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
-      ZB_TASK_SCRATCH int h[ZB_NH];
+      int h[ZB_NH];
       gv.range_hist((int)s.win, s.ts, s.te, h);
       h[ZB_EOB] += 1;
-      ZB_TASK_SCRATCH ZbScratch sc;
+      ZbScratch sc;
       s.static_cost = zb_static_cost(h, h + ZB_NLIT);
       zb_huff_lengths(h, ZB_NLIT, t.llen, sc.key);
-      ZB_TASK_SCRATCH int olen288[ZB_NLIT];
+      int olen288[ZB_NLIT];
       zb_huff_lengths(h + ZB_NLIT, ZB_NOFF, olen288, sc.key);
       s.dynamic_cost = zb_dynamic_cost(h, t.llen, h + ZB_NLIT, olen288, sc);
       s.is_dyn = s.static_cost <= s.dynamic_cost ? 0 : 1;
@@ -1684,7 +1684,7 @@ inline void ZbPipe::stage_parse() {
          zb_huff_build(h, ZB_NLIT, 15, t.llen, 0, sc.key, sc.order, &s.ub_hit);
          zb_huff_build(h + ZB_NLIT, ZB_NOFF, 15, olen288, 0, sc.key, sc.order, &s.ub_hit);
          for (int i = 0; i < ZB_NOFF; i++) t.olen[i] = olen288[i];
-         ZB_TASK_SCRATCH int ll[ZB_NLIT], ol[ZB_NOFF];
+         int ll[ZB_NLIT], ol[ZB_NOFF];
          for (int i = 0; i < ZB_NLIT; i++) ll[i] = t.llen[i] ? t.llen[i] : 9;   /* blockdeflate.c:873-881 */
          for (int i = 0; i < ZB_NOFF; i++) ol[i] = t.olen[i] ? t.olen[i] : 6;
          zb_make_costtab(ll, ol, t.cost);
@@ -1694,7 +1694,7 @@ inline void ZbPipe::stage_parse() {
          zb_make_costtab(t.llen, t.olen, t.cost);
       }
       sb[x] = s;
-   }, ZB_HEAVY);
+   }, 64);
    /* chunk lists */
    zb_launch(st, 1, ZB_LAMBDA(long) {
       uint32_t d = 0, p = 0;
@@ -1773,7 +1773,7 @@ inline void ZbPipe::stage_parse() {
                sg[(size_t)q * SS] = (lo + q <= end) ? (int16_t)(uint16_t)(ring.get(sl) - b) : (int16_t)0;
             }
          }
-      }, ZB_HEAVY);
+      }, 64);
 #endif
       /* D3/D4: verify and repair.  A chunk is right iff the relative costs its warm-up saw over the 259-position horizon
          at its end equal what its right neighbour really computed there, and the neighbour is right.  Rounds: every chunk
@@ -1926,12 +1926,12 @@ inline void ZbPipe::stage_parse() {
             if (nz == 0) t.ocnt[0] = t.ocnt[1] = 1;
             else if (nz == 1) { if (t.ocnt[0]) t.ocnt[1] = 1; else t.ocnt[0] = 1; }
          }
-         ZB_TASK_SCRATCH ZbScratch sc; ZB_TASK_SCRATCH int olen288[ZB_NLIT];
+         ZbScratch sc; int olen288[ZB_NLIT];
          zb_huff_build(t.lcnt, ZB_NLIT, 15, t.llen, 0, sc.key, sc.order, &s.ub_hit);
          zb_huff_build(t.ocnt, ZB_NOFF, 15, olen288, 0, sc.key, sc.order, &s.ub_hit);
          for (int i = 0; i < ZB_NOFF; i++) t.olen[i] = olen288[i];
          if (pass < 3) {
-            ZB_TASK_SCRATCH int ll[ZB_NLIT], ol[ZB_NOFF];
+            int ll[ZB_NLIT], ol[ZB_NOFF];
             for (int i = 0; i < ZB_NLIT; i++) ll[i] = t.llen[i] ? t.llen[i] : 9;
             for (int i = 0; i < ZB_NOFF; i++) ol[i] = t.olen[i] ? t.olen[i] : 6;
             zb_make_costtab(ll, ol, t.cost);
@@ -1939,7 +1939,7 @@ inline void ZbPipe::stage_parse() {
             zb_make_costtab(t.llen, t.olen, t.cost);   /* final lengths: used by the post-optimiser and the emitter */
          }
          sb[x] = s;
-      }, ZB_HEAVY);
+      }, 64);
    }
    /* P7: matches that are cheaper as literals (blockdeflate.c:410-458), dynamic sub-blocks only */
    zb_launch(st, npch, ZB_LAMBDA(long c) {
@@ -1968,13 +1968,13 @@ inline void ZbPipe::stage_parse() {
    /* F1a: RLE smoothing trial (blockdeflate.c:926-945); the code-length sequence to be described */
    zb_launch(st, ns, ZB_LAMBDA(long x) {
       ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
-      ZB_TASK_SCRATCH ZbScratch sc;
+      ZbScratch sc;
       if (s.is_dyn) {
-         ZB_TASK_SCRATCH int oc288[ZB_NLIT], ol288[ZB_NLIT];
+         int oc288[ZB_NLIT], ol288[ZB_NLIT];
          for (int i = 0; i < ZB_NLIT; i++) { oc288[i] = i < ZB_NOFF ? t.ocnt[i] : 0; ol288[i] = i < ZB_NOFF ? t.olen[i] : 0; }
          const int cur_cost = zb_dynamic_cost(t.lcnt, t.llen, oc288, ol288, sc);
-         ZB_TASK_SCRATCH int lc2[ZB_NLIT], oc2[ZB_NLIT], ll2[ZB_NLIT], ol2[ZB_NLIT];
-         ZB_TASK_SCRATCH uint8_t good[ZB_NLIT];
+         int lc2[ZB_NLIT], oc2[ZB_NLIT], ll2[ZB_NLIT], ol2[ZB_NLIT];
+         uint8_t good[ZB_NLIT];
          for (int i = 0; i < ZB_NLIT; i++) { lc2[i] = t.lcnt[i]; oc2[i] = oc288[i]; }
          zb_smooth_counts(ZB_NLIT, lc2, good);
          zb_smooth_counts(ZB_NOFF, oc2, good);
@@ -1996,14 +1996,14 @@ inline void ZbPipe::stage_parse() {
          s.nl = 288; s.no = 32; s.ncl = 0; s.mask = 0; s.hdr_bits = 0;
       }
       sb[x] = s;
-   }, ZB_HEAVY);
+   }, 64);
    /* F1b: the 20 RLE masks {0..7, 9, 11, .., 31} in parallel (blockdeflate.c:958-974) */
    zb_launch(st, (long)ns * 20, ZB_LAMBDA(long y) {
       const long x = y / 20; const int mi = (int)(y % 20);
       const ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
       if (!s.is_dyn) return;
       const int mask = mi < 8 ? mi : 9 + 2 * (mi - 8);
-      ZB_TASK_SCRATCH int clcnt[ZB_NCL], cllen[ZB_NLIT]; ZB_TASK_SCRATCH uint32_t key[ZB_NLIT]; ZB_TASK_SCRATCH int16_t order[ZB_NLIT]; int ub = 0;
+      int clcnt[ZB_NCL], cllen[ZB_NLIT]; uint32_t key[ZB_NLIT]; int16_t order[ZB_NLIT]; int ub = 0;
       for (int i = 0; i < ZB_NCL; i++) clcnt[i] = 0;
       ZbRleCount cv = {clcnt};
       zb_rle_scan(t.cl, s.nl + s.no, (unsigned)mask, cv);
@@ -2011,7 +2011,7 @@ inline void ZbPipe::stage_parse() {
       ZbRleSize sv = {cllen, 0};
       zb_rle_scan(t.cl, s.nl + s.no, (unsigned)mask, sv);
       t.mask_cost[mi] = sv.bits | (ub << 30);
-   }, ZB_HEAVY);
+   }, 64);
    /* F1c: pick the mask (later one wins ties, :966), final code-length code, codewords, header size */
    zb_launch(st, ns, ZB_LAMBDA(long x) {
       ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
@@ -2023,7 +2023,7 @@ inline void ZbPipe::stage_parse() {
             if (bestmi == -1 || bestcost >= c) { bestmi = mi; bestcost = c; }
          }
          const int bestmask = bestmi < 8 ? bestmi : 9 + 2 * (bestmi - 8);
-         ZB_TASK_SCRATCH int clcnt[ZB_NCL], cllen[ZB_NLIT]; ZB_TASK_SCRATCH uint32_t key[ZB_NLIT]; ZB_TASK_SCRATCH int16_t order[ZB_NLIT];
+         int clcnt[ZB_NCL], cllen[ZB_NLIT]; uint32_t key[ZB_NLIT]; int16_t order[ZB_NLIT];
          for (int i = 0; i < ZB_NCL; i++) clcnt[i] = 0;
          ZbRleCount cv = {clcnt};
          zb_rle_scan(t.cl, s.nl + s.no, (unsigned)bestmask, cv);
@@ -2035,7 +2035,7 @@ inline void ZbPipe::stage_parse() {
          if (s.nl > 286 || s.no > 30) s.hdr_bits = -1;   /* blockdeflate.c:981-983: block_deflate fails -> stored */
       }
       {
-         ZB_TASK_SCRATCH int16_t order[ZB_NLIT];
+         int16_t order[ZB_NLIT];
          int n = zb_order_by_len(t.llen, ZB_NLIT, order);
          zb_huff_codes(t.llen, order, n, t.lcode);
          int ol[ZB_NOFF]; for (int i = 0; i < ZB_NOFF; i++) ol[i] = t.olen[i];
@@ -2044,7 +2044,7 @@ inline void ZbPipe::stage_parse() {
          zb_make_costtab(t.llen, ol, t.cost);
       }
       sb[x] = s;
-   }, ZB_HEAVY);
+   }, 64);
 }
 
 /* ============================================================ emission ============================================================

@@ -190,20 +190,10 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_k(const uint64_t *keys, lo
    h[threadIdx.x] = 0;
    __syncthreads();
    const long base = (long)blockIdx.x * RS_TILE;
-   const int lane = threadIdx.x & 31;
-   uint64_t kk[RS_ITEMS];
-#pragma unroll
-   for (int k = 0; k < RS_ITEMS; k++) {           /* all loads first: the tile's keys are one burst */
-      const long idx = base + k * RS_THREADS + threadIdx.x;
-      kk[k] = idx < n ? keys[idx] : 0;
-   }
 #pragma unroll
    for (int k = 0; k < RS_ITEMS; k++) {
-      /* digits are skewed (text bytes): one shared-memory atomic per distinct digit of the warp instead of one per lane */
-      const long idx = base + k * RS_THREADS + threadIdx.x;
-      const uint32_t d = idx < n ? ((uint32_t)(kk[k] >> shift) & mask) : 0xffffffffu;
-      const uint32_t peers = __match_any_sync(0xffffffffu, d);
-      if (d != 0xffffffffu && lane == __ffs((int)peers) - 1) atomicAdd(&h[d], (uint32_t)__popc(peers));
+      long idx = base + k * RS_THREADS + threadIdx.x;
+      if (idx < n) atomicAdd(&h[(uint32_t)(keys[idx] >> shift) & mask], 1u);
    }
    __syncthreads();
    hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];

@@ -20,7 +20,6 @@
 typedef int zb_stream_t;
 #define ZB_LAMBDA [=]
 #define ZB_DEV
-#define ZB_HEAVY 64              /* launch marker of the heavy serial tasks (ignored by the host build) */
 template <class F> static inline void zb_launch_(int, zb_stream_t, long n, F f, int = 128) { for (long i = 0; i < n; i++) f(i); }
 static inline void zb_tag(const char *) {}
 static inline void *zb_dev_alloc(size_t n) { void *p = malloc(n ? n : 1); if (!p) { fprintf(stderr, "emu alloc fail\n"); abort(); } return p; }
@@ -43,7 +42,6 @@ static inline int zb_sm_count() { return 148; }
 typedef cudaStream_t zb_stream_t;
 #define ZB_LAMBDA [=] __device__
 #define ZB_DEV __device__
-#define ZB_HEAVY 64              /* launch marker of the heavy serial tasks: always one thread per block (ZB_TASK_SCRATCH, zb_core.h) */
 #define ZB_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "zultra-b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); zb_cuda_fail(e_); } } while (0)
 void zb_cuda_fail(cudaError_t e);
 extern long long g_zb_launches;   /* kernels launched by this library (bench.py reports it); several host threads count */
@@ -61,7 +59,8 @@ template <class F> static inline void zb_launch_(int line, zb_stream_t st, long 
    if (n <= 0) { zb_tag(0); return; }
    /* few tasks are the serial per-sub-block / per-node ones (Huffman builds, splitter scans): give each its own warp, so that
       32 unrelated control flows do not serialise inside one, and its own SM share instead of crowding two SMs */
-   if (n <= 4096 || blk == ZB_HEAVY) blk = 1;   /* ZB_HEAVY tasks keep their scratch in shared memory: never more than one per block */
+   static const long heavy_max = getenv("ZULTRA_CUDA_HEAVY_SINGLE_MAX") ? atol(getenv("ZULTRA_CUDA_HEAVY_SINGLE_MAX")) : 4096;
+   if (n <= (blk == 64 ? heavy_max : 4096)) blk = 1;   /* blk == 64 marks the heavy serial tasks at their call sites */
    if (g_zb_prof_on) zb_prof_begin(line, st);
    zb_task_kernel<<<(unsigned)((n + blk - 1) / blk), blk, 0, st>>>(n, f);
    if (g_zb_prof_on) zb_prof_end(st);
