@@ -124,8 +124,17 @@ ZB_HD void zb_sort_u32(uint32_t *a, int n) {
 ZB_HD void zb_huff_lengths(const int *cnt, int nsym, int *len, uint32_t *key) {
    int n = 0;
    for (int i = 0; i < ZB_NLIT; i++) len[i] = 0;
-   for (int i = 0; i < nsym; i++)
-      if (cnt[i]) key[n++] = ((uint32_t)cnt[i] << 9) | (uint32_t)i;
+   for (int i0 = 0; i0 < nsym; i0 += 8) {      /* the counts may sit in global memory: 8 loads in flight, then the compaction */
+      int c[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 8; j++) c[j] = i0 + j < nsym ? cnt[i0 + j] : 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 8; j++) if (c[j]) key[n++] = ((uint32_t)c[j] << 9) | (uint32_t)(i0 + j);
+   }
    if (n <= 1) { len[0] = 1; return; }
    zb_sort_u32(key, n);
    /* w[] lives in the upper bits of key[]; keep symbol ids aside in the low 9 bits */

@@ -71,7 +71,7 @@ struct ZbSubTabs {
    int llen[ZB_NLIT], olen[ZB_NOFF];
    uint16_t lcode[ZB_NLIT], ocode[ZB_NOFF];
    int cllen[ZB_NCL]; uint16_t clcode[ZB_NCL];
-   uint8_t cl[ZB_NLIT + ZB_NOFF]; int mask_cost[20];
+   alignas(16) uint8_t cl[ZB_NLIT + ZB_NOFF]; int mask_cost[20];   /* cl: 16-byte aligned, the mask search copies it with vector loads */
    ZbCostTab cost;
 };
 
@@ -125,7 +125,7 @@ struct ZbPipe {
    std::vector<uint32_t> h_gchunk_first; ZbBuf<uint32_t> gchunk_first, gchunk_win;
    /* splitter */
    ZbBuf<ZbNode> nodesA, nodesB; ZbBuf<int> nodehist; ZbBuf<uint16_t> chk_stat; ZbBuf<uint8_t> chk_flag; ZbBuf<int> chk_delta; ZbBuf<uint32_t> chk_node;
-   ZbBuf<uint32_t> wsplit; ZbBuf<uint32_t> wnsplit;
+   ZbBuf<uint32_t> wsplit; ZbBuf<uint32_t> wnsplit, wsubcnt, wsubbase;
    /* sub-blocks */
    ZbBuf<ZbSub> sub; ZbBuf<ZbSubTabs> tabs; ZbBuf<uint32_t> dchunk_sub, pchunk_sub;
    ZbBuf<zb_match_t> best; ZbBuf<int16_t> sig_true, sig_warm, sig_new; ZbBuf<uint8_t> dok; ZbBuf<uint32_t> dbad;
@@ -918,7 +918,22 @@ inline void ZbPipe::stage_greedy() {
       const uint32_t gb = wbs[w];
       const uint8_t *t = T + wd[w].in_off;
       const uint32_t t1 = wtb[w] + (k - 1) * ZB_TOKI, t2 = t1 + ZB_TOKI;
-      for (uint32_t q = t1; q < t2; q++) {
+      uint32_t q = t1;
+#ifdef __CUDA_ARCH__
+      for (; q + 8 <= t2; q += 8) {      /* the loads of 8 tokens level by level (see ZbGreedyView::add_tokens) */
+         uint32_t p[8], l[8], o[8], c[8];
+#pragma unroll
+         for (int j = 0; j < 8; j++) p[j] = tp[q + j];
+#pragma unroll
+         for (int j = 0; j < 8; j++) { l[j] = gl[gb + p[j]]; o[j] = go[gb + p[j]]; c[j] = t[p[j]]; }
+#pragma unroll
+         for (int j = 0; j < 8; j++) {
+            if (l[j] >= ZB_MIN_MATCH) { row[zb_len_sym(l[j] - ZB_MIN_MATCH)] += 1; row[ZB_NLIT + zb_off_sym(o[j])] += 1; }
+            else row[c[j]] += 1;
+         }
+      }
+#endif
+      for (; q < t2; q++) {
          uint32_t p = tp[q];
          uint32_t l = gl[gb + p];
          zb_tok_count(t, p, l, go[gb + p], row, row + ZB_NLIT, 1);
@@ -928,7 +943,16 @@ inline void ZbPipe::stage_greedy() {
    zb_launch(st, (long)nwin * ZB_NH, ZB_LAMBDA(long x) {
       const int w = (int)(x / ZB_NH), b = (int)(x % ZB_NH);
       int acc = 0;
-      for (uint32_t r = wib[w]; r < wib[w + 1]; r++) { acc += PH[(size_t)r * ZB_NH + b]; PH[(size_t)r * ZB_NH + b] = acc; }
+      uint32_t r = wib[w];
+      const uint32_t r1 = wib[w + 1];
+      for (; r + 8 <= r1; r += 8) {       /* 8 rows' loads in flight, then the running sums */
+         int v[8];
+#pragma unroll
+         for (int j = 0; j < 8; j++) v[j] = PH[(size_t)(r + j) * ZB_NH + b];
+#pragma unroll
+         for (int j = 0; j < 8; j++) { acc += v[j]; PH[(size_t)(r + j) * ZB_NH + b] = acc; }
+      }
+      for (; r < r1; r++) { acc += PH[(size_t)r * ZB_NH + b]; PH[(size_t)r * ZB_NH + b] = acc; }
    });
 }
 
@@ -937,7 +961,25 @@ struct ZbGreedyView {
    const int *PH; const uint32_t *wib, *wtb, *tp, *wbs; const uint16_t *gl, *go; const uint8_t *T; const ZbWinDesc *wd;
    ZB_HD void add_tokens(int w, uint32_t t1, uint32_t t2, int *h, int sign) const {
       const uint32_t gb = wbs[w]; const uint8_t *t = T + wd[w].in_off;
-      for (uint32_t q = wtb[w] + t1; q < wtb[w] + t2; q++) {
+      uint32_t q = wtb[w] + t1;
+      const uint32_t q1 = wtb[w] + t2;
+#ifdef __CUDA_ARCH__
+      /* one thread walks up to 2 x 255 edge tokens, three dependent loads each: batches of 8 with the loads of a level issued
+         together, so a batch costs three memory round trips instead of twenty-four */
+      for (; q + 8 <= q1; q += 8) {
+         uint32_t p[8], l[8], o[8], c[8];
+#pragma unroll
+         for (int j = 0; j < 8; j++) p[j] = tp[q + j];
+#pragma unroll
+         for (int j = 0; j < 8; j++) { l[j] = gl[gb + p[j]]; o[j] = go[gb + p[j]]; c[j] = t[p[j]]; }
+#pragma unroll
+         for (int j = 0; j < 8; j++) {
+            if (l[j] >= ZB_MIN_MATCH) { h[zb_len_sym(l[j] - ZB_MIN_MATCH)] += sign; h[ZB_NLIT + zb_off_sym(o[j])] += sign; }
+            else h[c[j]] += sign;
+         }
+      }
+#endif
+      for (; q < q1; q++) {
          uint32_t p = tp[q];
          zb_tok_count(t, p, gl[gb + p], go[gb + p], h, h + ZB_NLIT, sign);
       }
@@ -1170,24 +1212,32 @@ inline void ZbPipe::stage_split() {
    /* sub-block list, in stream order */
    sub.need((size_t)nwin * ZB_MAXSB); tabs.need((size_t)nwin * ZB_MAXSB);
    ZbSub *sb = sub.p; uint32_t *wsp = wsplit.p, *wns = wnsplit.p;
-   zb_launch(st, 1, ZB_LAMBDA(long) {
-      uint32_t n = 0;
-      for (int w = 0; w < nw; w++) {
-         uint32_t *sp = wsp + (size_t)w * ZB_MAXSB;
-         const uint32_t ns = wns[w];
-         for (uint32_t i = 1; i < ns; i++) { uint32_t v = sp[i]; uint32_t j = i; while (j > 0 && sp[j - 1] > v) { sp[j] = sp[j - 1]; j--; } sp[j] = v; }
-         uint32_t start = wd[w].hist;
-         const uint32_t ntok = wtb[w + 1] - wtb[w];
-         for (uint32_t i = 0; i <= ns; i++) {
-            uint32_t end = i < ns ? sp[i] : wd[w].len;
-            ZbSub s; memset(&s, 0, sizeof(s));
-            s.win = (uint32_t)w; s.idx_in_win = i; s.ps = start; s.pe = end;
-            s.ts = gv.tok_of_pos(w, start, ntok); s.te = end < wd[w].len ? gv.tok_of_pos(w, end, ntok) : ntok;
-            sb[n++] = s;
-            start = end;
-         }
+   /* per window: sort its split offsets and count its sub-blocks; exclusive sum -> first sub-block of every window; per
+      window again: fill its sub-blocks (windows are independent, only the numbering runs through them) */
+   wsubcnt.need(nwin + 1); wsubbase.need(nwin + 1);
+   uint32_t *wsc = wsubcnt.p, *wsbase = wsubbase.p;
+   zb_launch(st, nw, ZB_LAMBDA(long w) {
+      uint32_t *sp = wsp + (size_t)w * ZB_MAXSB;
+      const uint32_t ns = wns[w];
+      for (uint32_t i = 1; i < ns; i++) { uint32_t v = sp[i]; uint32_t j = i; while (j > 0 && sp[j - 1] > v) { sp[j] = sp[j - 1]; j--; } sp[j] = v; }
+      wsc[w] = ns + 1;
+   });
+   zb_exclusive_sum(st, wsc, wsbase, nw, cn + 3, scratch.p);
+   zb_launch(st, nw, ZB_LAMBDA(long w) {
+      const uint32_t *sp = wsp + (size_t)w * ZB_MAXSB;
+      const uint32_t ns = wns[w];
+      uint32_t n = wsbase[w];
+      uint32_t start = wd[w].hist;
+      const uint32_t ntok = wtb[w + 1] - wtb[w];
+      uint32_t ts = gv.tok_of_pos((int)w, start, ntok);
+      for (uint32_t i = 0; i <= ns; i++) {
+         uint32_t end = i < ns ? sp[i] : wd[w].len;
+         ZbSub s; memset(&s, 0, sizeof(s));
+         s.win = (uint32_t)w; s.idx_in_win = i; s.ps = start; s.pe = end;
+         s.ts = ts; s.te = end < wd[w].len ? gv.tok_of_pos((int)w, end, ntok) : ntok;
+         sb[n++] = s;
+         start = end; ts = s.te;
       }
-      cn[3] = n;
    });
    uint32_t ns = 0;
    zb_d2h(st, &ns, cn + 3, 4); zb_sync(st);
@@ -2004,12 +2054,16 @@ inline void ZbPipe::stage_parse() {
       if (!s.is_dyn) return;
       const int mask = mi < 8 ? mi : 9 + 2 * (mi - 8);
       int clcnt[ZB_NCL], cllen[ZB_NLIT]; uint32_t key[ZB_NLIT]; int16_t order[ZB_NLIT]; int ub = 0;
+      /* private copy of the code-length sequence (20 vector loads): the two scans read it byte by byte in dependent steps */
+      alignas(16) uint8_t cll[ZB_NLIT + ZB_NOFF];
+      { struct V16 { uint32_t a, b, c, d; }; struct alignas(16) A16 { V16 v; };
+        for (int e = 0; e < (ZB_NLIT + ZB_NOFF) / 16; e++) ((A16 *)cll)[e] = ((const A16 *)t.cl)[e]; }
       for (int i = 0; i < ZB_NCL; i++) clcnt[i] = 0;
       ZbRleCount cv = {clcnt};
-      zb_rle_scan(t.cl, s.nl + s.no, (unsigned)mask, cv);
+      zb_rle_scan(cll, s.nl + s.no, (unsigned)mask, cv);
       zb_huff_build(clcnt, ZB_NCL, 7, cllen, 0, key, order, &ub);
       ZbRleSize sv = {cllen, 0};
-      zb_rle_scan(t.cl, s.nl + s.no, (unsigned)mask, sv);
+      zb_rle_scan(cll, s.nl + s.no, (unsigned)mask, sv);
       t.mask_cost[mi] = sv.bits | (ub << 30);
    }, 64);
    /* F1c: pick the mask (later one wins ties, :966), final code-length code, codewords, header size */
@@ -2297,7 +2351,7 @@ inline void ZbPipe::release_all() {
    gtokcnt.release(); gtokbase.release(); tokpos.release(); wtok.release(); wtokbase.release(); wintbase.release(); ph.release();
    gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
    chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();
-   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); dbad.release(); pentry.release(); pbits.release(); dpfar.release(); hin.release(); hout.release(); out.release(); sout.release();
+   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); dbad.release(); pentry.release(); pbits.release(); dpfar.release(); hin.release(); hout.release(); wsubcnt.release(); wsubbase.release(); out.release(); sout.release();
 }
 
 
