@@ -500,11 +500,10 @@ __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *
       const int i = (int)(nlook + m);
       const int best = i - 1 - (int)(c1 >> 9);
       const uint32_t k3 = (uint32_t)txt[i] | ((uint32_t)txt[i + 1] << 8) | ((uint32_t)txt[i + 2] << 16);
-      uint32_t tr[ZB_NMATCH], curmax = 0;
-      int nt = 0;
+      /* record number d (in order of discovery = increasing length) is kept by lane d % 32; only the last 8 can survive */
+      uint32_t myrec = 0, curmax = 0;
+      int nd = 0;
       bool done = false;
-#pragma unroll
-      for (int z = 0; z < ZB_NMATCH; z++) tr[z] = 0;
       for (int jb = i - 1; jb > best && !done; jb -= 32) {
          const int j = jb - lane;
          bool hit = false;
@@ -525,10 +524,8 @@ __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *
                if (mm) { len = o + (uint32_t)(__ffs((int)mm) - 1); break; }
             }
             if (len > curmax) {
-#pragma unroll
-               for (int z = ZB_NMATCH - 1; z > 0; z--) tr[z] = tr[z - 1];
-               tr[0] = len | ((uint32_t)(i - jh) << 16);
-               if (nt < ZB_NMATCH) nt++;
+               if (lane == (nd & 31)) myrec = len | ((uint32_t)(i - jh) << 16);
+               nd++;
                curmax = len;
                if (len == bound) done = true;
             }
@@ -538,12 +535,13 @@ __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *
          the text-walk records, longest first; lane z writes slot z */
       const uint32_t p = t.m0 + m;
       const uint32_t maxlen = t.wlen - p;
+      const int nt = nd < ZB_NMATCH ? nd : ZB_NMATCH;
       const bool pend = moved && !(nt && curmax == lvl);
-      const int z = lane - nm - (pend ? 1 : 0);      /* index into tr[] for this lane's slot */
+      const int z = lane - nm - (pend ? 1 : 0);      /* this lane's slot takes the z-th longest text-walk record: discovery nd - 1 - z */
+      const uint32_t got = __shfl_sync(0xffffffffu, myrec, (nd - 1 - z) & 31);
       uint32_t v = 0;
       if (pend && lane == nm) v = lvl | (((c1 >> 9) + 1u) << 16);
-#pragma unroll
-      for (int y = 0; y < ZB_NMATCH; y++) if (z == y && y < nt) v = tr[y];
+      if (z >= 0 && z < nt) v = got;
       if ((v & 0xffffu) > maxlen) v = (v & 0xffff0000u) | maxlen;
       uint32_t *dst = (uint32_t *)(mt + ((size_t)(gbase + p) << 3));
       if (lane >= nm && lane < ZB_NMATCH) dst[lane] = v;
