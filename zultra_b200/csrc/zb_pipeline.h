@@ -504,42 +504,30 @@ __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *
       uint32_t myrec = 0, curmax = 0;
       int nd = 0;
       bool done = false;
-      /* 64 positions per step (two per lane): the prefix tests of both halves are issued together; a candidate is first
-         tested at the one byte that decides whether it can beat the longest so far */
-      for (int jb = i - 1; jb > best && !done; jb -= 64) {
-         const int ja = jb - lane, jc = jb - 32 - lane;
-         bool hita = false, hitc = false;
-         if (ja > best) {   /* bytes j..j+2 out of the two aligned words around them (the buffer is padded by a word) */
-            const uint32_t w0 = zb_smw[ja >> 2], w1 = zb_smw[(ja >> 2) + 1];
-            hita = (__funnelshift_r(w0, w1, (uint32_t)(ja & 3) << 3) & 0xffffffu) == k3;
+      for (int jb = i - 1; jb > best && !done; jb -= 32) {
+         const int j = jb - lane;
+         bool hit = false;
+         if (j > best) {   /* bytes j..j+2 out of the two aligned words around them (the buffer is padded by a word) */
+            const uint32_t w0 = zb_smw[j >> 2], w1 = zb_smw[(j >> 2) + 1];
+            hit = (__funnelshift_r(w0, w1, (uint32_t)(j & 3) << 3) & 0xffffffu) == k3;
          }
-         if (jc > best) {
-            const uint32_t w0 = zb_smw[jc >> 2], w1 = zb_smw[(jc >> 2) + 1];
-            hitc = (__funnelshift_r(w0, w1, (uint32_t)(jc & 3) << 3) & 0xffffffu) == k3;
-         }
-         const uint32_t hits_a = __ballot_sync(0xffffffffu, hita), hits_c = __ballot_sync(0xffffffffu, hitc);
-#pragma unroll 1
-         for (int half = 0; half < 2 && !done; half++) {
-            uint32_t hits = half ? hits_c : hits_a;
-            const int jbase = jb - 32 * half;
-            while (hits && !done) {
-               const int h = __ffs((int)hits) - 1;
-               hits &= hits - 1u;
-               const int jh = jbase - h;
-               if (curmax >= ZB_MIN_MATCH && txt[jh + curmax] != txt[i + curmax]) continue;   /* cannot be longer than curmax (< bound here) */
-               uint32_t len = bound;
-               for (uint32_t o = ZB_MIN_MATCH; o < bound; o += 32) {
-                  const uint32_t xo = o + (uint32_t)lane;
-                  const bool neq = xo < bound && txt[jh + xo] != txt[i + xo];
-                  const uint32_t mm = __ballot_sync(0xffffffffu, neq);
-                  if (mm) { len = o + (uint32_t)(__ffs((int)mm) - 1); break; }
-               }
-               if (len > curmax) {
-                  if (lane == (nd & 31)) myrec = len | ((uint32_t)(i - jh) << 16);
-                  nd++;
-                  curmax = len;
-                  if (len == bound) done = true;
-               }
+         uint32_t hits = __ballot_sync(0xffffffffu, hit);
+         while (hits && !done) {
+            const int h = __ffs((int)hits) - 1;
+            hits &= hits - 1u;
+            const int jh = jb - h;
+            uint32_t len = bound;
+            for (uint32_t o = ZB_MIN_MATCH; o < bound; o += 32) {
+               const uint32_t xo = o + (uint32_t)lane;
+               const bool neq = xo < bound && txt[jh + xo] != txt[i + xo];
+               const uint32_t mm = __ballot_sync(0xffffffffu, neq);
+               if (mm) { len = o + (uint32_t)(__ffs((int)mm) - 1); break; }
+            }
+            if (len > curmax) {
+               if (lane == (nd & 31)) myrec = len | ((uint32_t)(i - jh) << 16);
+               nd++;
+               curmax = len;
+               if (len == bound) done = true;
             }
          }
       }
