@@ -1492,6 +1492,11 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
       {
          const int p = i0 - 32 - lane;
          if (p >= lo) { const uint4 *q = (const uint4 *)(match + ((size_t)p << 3)); na = __ldg(q); nb = __ldg(q + 1); nl = t[p]; }
+         /* a scan block is over long before a DRAM round trip: the records of the blocks further ahead are pulled into L2 now,
+            so that the register prefetch above only ever waits for L2 */
+         const int pf = i0 - 32 * 6 - lane;
+         if (pf >= lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(match + ((size_t)pf << 3)));
+         if (lane == 0 && pf >= lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(t + pf - 31));
       }
       __syncwarp();
       const int nb_pos = i0 - lo + 1 < 32 ? i0 - lo + 1 : 32;
