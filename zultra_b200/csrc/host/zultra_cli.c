@@ -217,6 +217,9 @@ int main(int argc, char **argv) {
    int bad = 0, have_cmd = 0, verify = 0, i;
    char cmd = 'z';
    unsigned int opt = 0;
+   /* the tool drives one GPU: unless the caller chose, expose only the first one to the CUDA runtime, whose start-up
+      otherwise initialises every device of the box (seconds on an 8-GPU node, for a tool that may compress 48 KB) */
+   setenv("CUDA_VISIBLE_DEVICES", "0", 0);
    for (i = 1; i < argc; i++) {
       const char *a = argv[i];
       if (!strcmp(a, "-d") || !strcmp(a, "-z") || !strcmp(a, "-cbench") || !strcmp(a, "-test") || !strcmp(a, "-quicktest")) {
