@@ -34,14 +34,25 @@ def main():
         for p, o in list(zip(payloads, outs))[:200]:
             assert o == ref.compress(p, flags=1)
             checked += 1
+    import ctypes as C
+    L = z.load()
+    L.zultra_cuda_profile.argtypes = [C.c_int]
+    L.zultra_cuda_profile_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     ts = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
         ctx.memory_compress_batch(payloads, 1)
         ts.append(time.perf_counter() - t0)
     dt = min(ts)
+    # one more pass with per-kernel CUDA events (not timed above)
+    L.zultra_cuda_profile(1)
+    ctx.memory_compress_batch(payloads, 1)
+    L.zultra_cuda_profile(0)
+    names = C.create_string_buffer(32 * 256); kms = (C.c_float * 256)(); kcnt = (C.c_int * 256)()
+    nk = L.zultra_cuda_profile_collect(names, kms, kcnt, 256)
+    ktab = sorted([(names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode(), round(kms[i], 2)) for i in range(nk)], key=lambda r: -r[1])[:24]
     print(json.dumps({"workload": "batch", "payloads": args.count, "bytes": total, "MB/s_host_to_host": round(total / dt / 1e6, 2), "ms": round(dt * 1e3, 2),
-                      "stages_ms": {k: round(v, 2) for k, v in ctx.timings().items()}, "counters": ctx.counters(),
+                      "stages_ms": {k: round(v, 2) for k, v in ctx.timings().items()}, "counters": ctx.counters(), "kernels_ms": dict(ktab),
                       "verified": "all inflate; first %d equal the compiled reference" % checked}))
     ctx.close()
 
