@@ -1383,6 +1383,9 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
    __syncwarp();
    for (int e = lane; e < 512; e += 32) offtab_s[wi][e] = tab_s[wi].off[zb_off_sym(e < 256 ? (uint32_t)e + 1u : 257u + ((uint32_t)(e - 256) << 7))];
    __syncwarp();
+   /* a warp whose chunks span several sub-blocks (batches of small streams: ~10 chunks per sub-block) takes the global-table
+      path as a whole: one code path for the warp instead of the two instantiations run one after the other */
+   const bool uniform = __all_sync(0xffffffffu, (c < ndch ? dcs[c] : x0) == x0);
    if (c >= ndch) return;
    const uint32_t x = dcs[c];
    const ZbSub s = sb[x];
@@ -1399,7 +1402,7 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
    uint16_t *far0 = far + (size_t)blockIdx.x * (size_t)(CD + WU) * ZB_DP_THREADS + threadIdx.x;
    int16_t *sw = sgw + (size_t)c, *sg = sgt + (size_t)c;
    int step = 0; uint32_t cprev = 0;
-   if (x == x0) {
+   if (uniform) {
       const uint8_t *plit = tab_s[wi].lit, *plen = tab_s[wi].len, *poff = offtab_s[wi];
       zb_dp_range<false, true>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
       zb_dp_signature(sw, SS, far0, hi, from, end, step, cprev, true);
