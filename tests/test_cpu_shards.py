@@ -70,3 +70,26 @@ def test_compose_and_plan():
     maps = [[10 + p for p in range(8)], [21 + p for p in range(8)]]
     offs, nb, tot = shard.compose(maps)
     assert offs == [0, 10] and nb == [10, 21] and tot == 31
+
+
+def test_bench_stream_range_is_the_concatenation_of_segments(tmp_path, monkeypatch):
+    """bench.py's weak-scaling stream: segment r of a workload comes from its own seed, a rank's byte range [lo, hi) may
+    span two segments, and the pieces of all ranks (minus their 32 KiB history overlap) tile the stream exactly."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from zultra_b200 import shard
+    size, world, block = 300_000, 3, 65536
+    whole = bench.stream_range("enwik100m", size, 0, size * world)
+    assert len(whole) == size * world
+    segs = [bench.gen_workload("enwik100m", size, s) for s in range(world)]
+    assert bytes(whole) == b"".join(s.tobytes() for s in segs)
+    assert bytes(segs[0]) != bytes(segs[1])
+    got = bytearray()
+    for lo, hi in shard.plan_shards(size * world, block, world):
+        hist = min(lo, 32768)
+        piece = bench.stream_range("enwik100m", size, lo - hist, hi)
+        assert len(piece) == hi - lo + hist
+        got += piece[hist:].tobytes()
+    assert bytes(got) == bytes(whole)
