@@ -425,9 +425,17 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
                break;
             }
             lvl = l; steps++;
-            uint32_t w;
-            if (lL >= lR) { w = words[L]; L--; const uint32_t wl = w >> ZB_POS_BITS; lL = wl < lL ? wl : lL; }
-            else { w = words[R]; R++; const uint32_t wl = words[R] >> ZB_POS_BITS; lR = wl < lR ? wl : lR; }
+            /* one step to the side with the larger running LCP, without a branch (the two sides would split the warp): the
+               left side's new LCP is in the word it consumes, the right side's in the word after it (never read past the
+               list: with R at the end sentinel lR is 0 and the left side is taken) */
+            const bool goL = lL >= lR;
+            const int at = goL ? L : R;
+            const uint32_t w = words[at], w2 = words[at + 1];
+            const uint32_t wl = (goL ? w : w2) >> ZB_POS_BITS;
+            L -= goL ? 1 : 0; R += goL ? 0 : 1;
+            const uint32_t side = goL ? lL : lR;
+            const uint32_t nl = wl < side ? wl : side;
+            lL = goL ? nl : lL; lR = goL ? lR : nl;
             const int p = (int)(w & ZB_POS_MASK);
             if (p < i && p > best) {
                best = p; moved = true;
@@ -1363,7 +1371,7 @@ __device__ __forceinline__ void zb_dp_signature(int16_t *__restrict__ dst, size_
    }
 }
 
-__global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
+__global__ void __launch_bounds__(ZB_DP_THREADS, 10) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
                                                                const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw,
                                                                size_t SS, uint16_t *far, int CD, int WU) {
    __shared__ uint16_t ring_s[ZB_NR * ZB_DP_THREADS];
