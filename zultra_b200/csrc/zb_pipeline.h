@@ -1371,7 +1371,7 @@ __device__ __forceinline__ void zb_dp_signature(int16_t *__restrict__ dst, size_
    }
 }
 
-__global__ void __launch_bounds__(ZB_DP_THREADS, 10) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
+__global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
                                                                const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw,
                                                                size_t SS, uint16_t *far, int CD, int WU) {
    __shared__ uint16_t ring_s[ZB_NR * ZB_DP_THREADS];
