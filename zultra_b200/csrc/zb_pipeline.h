@@ -1371,7 +1371,8 @@ __device__ __forceinline__ void zb_dp_signature(int16_t *__restrict__ dst, size_
    }
 }
 
-__global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
+template <int MINB>
+__global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
                                                                const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw,
                                                                size_t SS, uint16_t *far, int CD, int WU) {
    __shared__ uint16_t ring_s[ZB_NR * ZB_DP_THREADS];
@@ -1797,7 +1798,14 @@ inline void ZbPipe::stage_parse() {
 #ifndef ZB_EMU
       if (ndch > 0) {
          if (g_zb_prof_on) { zb_tag("parse_dp"); zb_prof_begin(0, st); }
-         zb_parse_dp_k<<<(unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS), ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
+         {
+            static const int minb = getenv("ZULTRA_CUDA_DP_MINB") ? atoi(getenv("ZULTRA_CUDA_DP_MINB")) : 9;
+            const unsigned grid = (unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS);
+            if (minb == 6) zb_parse_dp_k<6><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
+            else if (minb == 7) zb_parse_dp_k<7><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
+            else if (minb == 8) zb_parse_dp_k<8><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
+            else zb_parse_dp_k<0><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
+         }
          if (g_zb_prof_on) zb_prof_end(st);
          zb_count_launch(1);
          ZB_CUDA_CHECK(cudaGetLastError());
