@@ -1799,7 +1799,10 @@ inline void ZbPipe::stage_parse() {
       if (ndch > 0) {
          if (g_zb_prof_on) { zb_tag("parse_dp"); zb_prof_begin(0, st); }
          {
-            static const int minb = getenv("ZULTRA_CUDA_DP_MINB") ? atoi(getenv("ZULTRA_CUDA_DP_MINB")) : 9;
+            /* register budget variants (ZULTRA_CUDA_DP_MINB = 8/7/6 asks for that many CTAs per SM: 64/72/72 registers; default:
+               the compiler's 56).  Measured on enwik100m: 0 and 8 equal (18.6 ms), 7 slower (21.5 ms), 10 CTAs at 48
+               registers slower still (25.6 ms). */
+            static const int minb = getenv("ZULTRA_CUDA_DP_MINB") ? atoi(getenv("ZULTRA_CUDA_DP_MINB")) : 0;
             const unsigned grid = (unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS);
             if (minb == 6) zb_parse_dp_k<6><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
             else if (minb == 7) zb_parse_dp_k<7><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
