@@ -1285,10 +1285,10 @@ __device__ __forceinline__ uint32_t zb_dp_offcost(const uint8_t *__restrict__ po
    return poff[zb_off_sym(off)];
 }
 
-template <bool KEEP, bool OT>
+template <bool OT>
 __device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const zb_match_t *__restrict__ match, const uint8_t *__restrict__ plit,
                                             const uint8_t *__restrict__ plen, const uint8_t *__restrict__ poff, int lo, int from, int end,
-                                            zb_match_t *__restrict__ best, uint16_t *ring0, uint16_t *far0, int &t_io, uint32_t &cprev_io) {
+                                            zb_match_t *__restrict__ best, uint16_t *ring0, uint16_t *far0, int &t_io, uint32_t &cprev_io, const bool KEEP) {
    const int NT = ZB_DP_THREADS;
    if (from - 1 < lo) return;
    int t = t_io;
@@ -1411,18 +1411,23 @@ __global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub
    uint16_t *far0 = far + (size_t)blockIdx.x * (size_t)(CD + WU) * ZB_DP_THREADS + threadIdx.x;
    int16_t *sw = sgw + (size_t)c, *sg = sgt + (size_t)c;
    int step = 0; uint32_t cprev = 0;
+   /* warm-up [hi, from) then the chunk [lo, hi): ONE copy of the recurrence per table path (the two phases as iterations of
+      a loop that is not unrolled) - the kernel is instruction-issue bound and its code should stay inside the I-cache */
    if (uniform) {
       const uint8_t *plit = tab_s[wi].lit, *plen = tab_s[wi].len, *poff = offtab_s[wi];
-      zb_dp_range<false, true>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
-      zb_dp_signature(sw, SS, far0, hi, from, end, step, cprev, true);
-      zb_dp_range<true, true>(t, m0, plit, plen, poff, lo, hi, end, b0, ring0, far0, step, cprev);
+#pragma unroll 1
+      for (int phase = 0; phase < 2; phase++) {
+         zb_dp_range<true>(t, m0, plit, plen, poff, phase ? lo : hi, phase ? hi : from, end, b0, ring0, far0, step, cprev, phase != 0);
+         zb_dp_signature(phase ? sg : sw, SS, far0, phase ? lo : hi, from, end, step, cprev, phase == 0);
+      }
    } else {
       const uint8_t *plit = tb[x].cost.lit, *plen = tb[x].cost.len, *poff = tb[x].cost.off;
-      zb_dp_range<false, false>(t, m0, plit, plen, poff, hi, from, end, b0, ring0, far0, step, cprev);
-      zb_dp_signature(sw, SS, far0, hi, from, end, step, cprev, true);
-      zb_dp_range<true, false>(t, m0, plit, plen, poff, lo, hi, end, b0, ring0, far0, step, cprev);
+#pragma unroll 1
+      for (int phase = 0; phase < 2; phase++) {
+         zb_dp_range<false>(t, m0, plit, plen, poff, phase ? lo : hi, phase ? hi : from, end, b0, ring0, far0, step, cprev, phase != 0);
+         zb_dp_signature(phase ? sg : sw, SS, far0, phase ? lo : hi, from, end, step, cprev, phase == 0);
+      }
    }
-   zb_dp_signature(sg, SS, far0, lo, from, end, step, cprev, false);
 }
 
 /* ---- repair of wrong chunks: the same recurrence, ONE WARP per chain ----
