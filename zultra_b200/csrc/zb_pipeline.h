@@ -209,10 +209,11 @@ inline void ZbPipe::stage_sa() {
    uint32_t *head = tmpA.p, *grp = tmpB.p, *rk = rank.p, *SA = sa.p, *act = actA.p, *act2 = actB.p, *cnt = counters.p;
    zb_launch(st, n, ZB_LAMBDA(long j) { head[j] = (j == 0 || kA[j] != kA[j - 1]) ? (uint32_t)j : 0u; SA[j] = vA[j]; }, 256);
    zb_inclusive_max(st, head, grp, n, scratch.p);
-   zb_launch(st, n, ZB_LAMBDA(long j) { rk[vA[j]] = grp[j]; }, 256);
-   /* active = members of groups with more than one suffix */
+   /* ranks, and active = members of groups with more than one suffix (one pass over grp for both) */
    zb_launch(st, n, ZB_LAMBDA(long j) {
-      bool is_head = grp[j] == (uint32_t)j;
+      const uint32_t gj = grp[j];
+      rk[vA[j]] = gj;
+      bool is_head = gj == (uint32_t)j;
       bool next_head = (j + 1 == n) || grp[j + 1] == (uint32_t)(j + 1);
       head[j] = (is_head && next_head) ? 0u : 1u;
    }, 256);
@@ -242,9 +243,10 @@ inline void ZbPipe::stage_sa() {
       zb_sort_pairs(st, keyA.p, valA.p, keyB.p, valB.p, mm, 32, 32 + rank_bits, scratch.p);
       zb_launch(st, mm, ZB_LAMBDA(long a) { head[a] = (a == 0 || kA[a] != kA[a - 1]) ? (uint32_t)a : 0u; SA[act[a]] = vA[a]; }, 256);
       zb_inclusive_max(st, head, grp, mm, scratch.p);
-      zb_launch(st, mm, ZB_LAMBDA(long a) { rk[vA[a]] = act[grp[a]]; }, 256);
       zb_launch(st, mm, ZB_LAMBDA(long a) {
-         bool is_head = grp[a] == (uint32_t)a;
+         const uint32_t ga = grp[a];
+         rk[vA[a]] = act[ga];
+         bool is_head = ga == (uint32_t)a;
          bool next_head = (a + 1 == mm) || grp[a + 1] == (uint32_t)(a + 1);
          head[a] = (is_head && next_head) ? 0u : 1u;
       }, 256);
