@@ -26,6 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+METRIC = "input MB/s (zultra compression hot path, byte-identical to CPU zultra)"   # both arms report this metric
 WORKLOADS = {
     "enwik100m": dict(size=100_000_000, flags=0, fmt="deflate", gen="enwik"),
     "mozilla51m": dict(size=51_220_480, flags=2, fmt="gzip", gen="mozilla"),
@@ -177,11 +178,12 @@ def run_reference(args, rank, world):
             vals.append((v, dt))
     v = sum(x[0] for x in vals) / len(vals)
     ms = 1000.0 * sum(x[1] for x in vals) / len(vals)
-    print(json.dumps({"impl": "reference", "metric": "input MB/s (zultra compression hot path)", "value": round(v, 3), "unit": "MB/s", "n_gpus": args.gpus,
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "MB/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                       "config": {"workload": name if world == 1 or name != "enwik100m" else "%s x %d (one stream of %d segments of the configuration's shape, sharded by block range)" % (name, world, world),
                                  "bytes": int(len(data)) * (world if name == "enwik100m" else 1), "format": w["fmt"], "max_block": 1048576,
+                                 "blocks": int((int(len(data)) * (world if name == "enwik100m" else 1) + 1048575) // 1048576),
                                  "sample": "CPU threads each compress a 2 MiB slice of segment 0 per step"},
                       "cpu_baseline": {"value": round(v, 3), "unit": "MB/s", "cores": cores, "kind": "reference", "sample": sample},
                       "e2e": {"value": round(v, 3), "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
@@ -303,7 +305,7 @@ def main():
         per_launch_ms = top[1] / max(1, top[2])
         launches_per_step = top[2] / args.steps
         achieved = (alg_bytes_per_step / launches_per_step) / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
-        out = {"metric": "input MB/s (zultra compression hot path, byte-identical to CPU zultra)", "value": round(value, 2), "unit": "MB/s",
+        out = {"metric": METRIC, "value": round(value, 2), "unit": "MB/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True,
                "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                "config": {"workload": name if not weak else "%s x %d (one stream of %d segments of the configuration's shape, sharded by block range)" % (name, world, world),
