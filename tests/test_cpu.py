@@ -152,3 +152,13 @@ def test_oracle_multi_block_dictionary_and_errors(ref):
     assert oracle_py.compress(np.zeros(0, dtype=np.uint8), 1) is None
     big = synth.mix(1500000, seed=4, seg_lo=100000, seg_hi=400000)
     assert oracle_py.compress(big, 0, 262144) == ref.compress(big, flags=0, block=262144)
+
+
+@pytest.mark.parametrize("name", ["js48k", "moz300k", "zeros100k", "period7", "lz_a96_p0.99", "rows1000", "utf16"])
+def test_emulated_lane_state_machine_vs_golden(emu, name, monkeypatch):
+    """The decoupled-lane form of the parse recurrence (zb_dpsm_open / _kstep / _close, zb_core.h), run chunk by chunk in
+    the host build: same deflate stream as the golden vector."""
+    monkeypatch.setenv("ZB_EMU_DP_SM", "1")
+    data = cases.small_cases()[name]
+    out, bits, d = emu.compress(data)
+    assert _gold_ok("%s/deflate" % name, out)

@@ -702,4 +702,104 @@ struct ZbRingStrided {
    ZB_HD void set(int s, uint16_t x) { base[s * stride] = x; }
 };
 
+/* ------------------------------------------------------------------------------------------------------------------------
+ * The recurrence of zb_parse_range as a per-lane STATE MACHINE (experimental: the thread-per-chunk kernel spends half of its
+ * instructions in candidate-length loops that only ~5 of a warp's 32 lanes are in; with the work of a position cut into
+ * "open" (decode the record, queue the short matches), "k-step" (one candidate length) and "close" (leave-alone matches,
+ * choice, write-back), a warp can run k-steps for whichever lanes have some and open/close positions for the others in
+ * batches, so that no lane waits for the longest loop of the current position - lanes simply drift apart in position).
+ * The functions below are the single-lane logic, shared by the host build (which runs them one chunk at a time to check them
+ * against the golden vectors) and the device kernel; they make the same choices as zb_parse_range (blockdeflate.c:254-323).
+ *
+ * MEM supplies: cost(tt) = cost written at step tt (0 for tt < 0: the zero guess above the start), put(t, c), best(i, w).
+ * Steps count positions from the start of the chunk's walk: position i is step t, position i + k is step t - k.
+ * Short matches (< 40) are queued as 14-bit entries {clamped length 6 | offset cost 5 | index 3}, shortest first (highest
+ * index first), 4 per 64-bit word; an entry is finished when the shared prefix minimum over the lengths reaches its length.
+ */
+struct ZbDpLane {
+   int i, t;                 /* open position and its step */
+   uint32_t cprev;           /* cost of position i + 1 */
+   int k, bnd, curk, mcur;   /* next length to try; length at which the current entry ends (0: no entry left); argmin; entry's match */
+   uint32_t curmin, offc;    /* prefix minimum of lencost(k) + cost[i + k]; offset cost of the current entry */
+   uint32_t bt; int bk, bm;  /* best match candidate so far: total, length, match index */
+   uint64_t q0, q1;          /* queued entries */
+   ZbMatchRec rec; uint32_t lit;
+};
+
+ZB_HD void zb_dpsm_pop(ZbDpLane &S) {
+   const uint32_t e = (uint32_t)(S.q0 & 0x3fffu);
+   S.q0 = (S.q0 >> 14) | ((S.q1 & 0x3fffu) << 42);
+   S.q1 >>= 14;
+   S.bnd = (int)(e & 63u); S.offc = (e >> 6) & 31u; S.mcur = (int)(e >> 11);
+}
+
+/* open position i (record and literal already in S.rec / S.lit): queue its short matches */
+template <class OFFC>
+ZB_HD void zb_dpsm_open(ZbDpLane &S, int end, const OFFC &offcost) {
+   S.q0 = 0; S.q1 = 0;
+   S.k = ZB_MIN_MATCH; S.curmin = 0x7fffffffu; S.curk = 0; S.bt = 0x7fffffffu; S.bk = 0; S.bm = 0;
+   const int rem = end - S.i;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+   for (int m = 0; m < ZB_NMATCH; m++) {        /* ascending index = descending length; pushed at the low end, so popped shortest first */
+      const int len0 = (int)(S.rec.w[m] & 0xffffu);
+      if (len0 >= ZB_MIN_MATCH && len0 < ZB_LEAVE_ALONE) {
+         const int ml = len0 < rem ? len0 : rem;
+         if (ml >= ZB_MIN_MATCH) {
+            const uint64_t e = (uint64_t)((uint32_t)ml | (offcost(S.rec.w[m] >> 16) << 6) | ((uint32_t)m << 11));
+            S.q1 = (S.q1 << 14) | ((S.q0 >> 42) & 0x3fffu);
+            S.q0 = ((S.q0 << 14) | e) & 0x00ffffffffffffffull;
+         }
+      }
+   }
+   zb_dpsm_pop(S);
+}
+
+/* one candidate length of the open position (only while S.bnd != 0) */
+template <class MEM>
+ZB_HD void zb_dpsm_kstep(ZbDpLane &S, const MEM &mem, const uint8_t *plen) {
+   const uint32_t c = (uint32_t)plen[S.k - ZB_MIN_MATCH] + mem.cost(S.t - S.k);
+   if (c <= S.curmin) { S.curmin = c; S.curk = S.k; }
+   while (S.bnd == S.k) {               /* entries ending here (several only where the sub-block end clamps them) */
+      const uint32_t total = S.curmin + S.offc;
+      if (total <= S.bt) { S.bt = total; S.bk = S.curk; S.bm = S.mcur; }
+      zb_dpsm_pop(S);
+   }
+   S.k++;
+}
+
+/* close the open position: leave-alone matches, the choice, write-back; moves to position i - 1 */
+template <class MEM, class OFFC>
+ZB_HD void zb_dpsm_close(ZbDpLane &S, MEM &mem, int end, const uint8_t *plit, const uint8_t *plen, const OFFC &offcost, bool keep) {
+   uint32_t bw = 0;
+   if (S.bt != 0x7fffffffu) {
+      uint32_t off = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int m = 0; m < ZB_NMATCH; m++) if (m == S.bm) off = S.rec.w[m] >> 16;
+      bw = (uint32_t)S.bk | (off << 16);
+   }
+   const int rem = end - S.i;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+   for (int m = ZB_NMATCH - 1; m >= 0; m--) {    /* >= 40: only the full (clamped) length, after the shorter matches, longest last */
+      const int len0 = (int)(S.rec.w[m] & 0xffffu);
+      if (len0 >= ZB_LEAVE_ALONE) {
+         const int ml = len0 < rem ? len0 : rem;
+         int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
+         const uint32_t total = (uint32_t)plen[lidx] + offcost(S.rec.w[m] >> 16) + mem.cost(S.t - ml);
+         if (total <= S.bt) { S.bt = total; bw = (uint32_t)ml | (S.rec.w[m] & 0xffff0000u); }
+      }
+   }
+   uint32_t bestc = S.cprev + plit[S.lit], bestw = 0;
+   if (S.bt < bestc) { bestc = S.bt; bestw = bw; }
+   mem.put(S.t, bestc);
+   if (keep) mem.best(S.i, bestw);
+   S.cprev = bestc;
+   S.i--; S.t++;
+}
+
 #endif /* ZB_CORE_H */

@@ -1435,6 +1435,103 @@ __global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub
    }
 }
 
+/* ---- EXPERIMENTAL (ZULTRA_CUDA_DP_SM=1; logic checked on the host against the golden vectors, kernel not yet measured):
+ * the same chunks, one thread each, but the lanes of a warp are decoupled: a lane is either inside the candidate-length loop
+ * of its open position (k-steps) or between positions (close + open).  Every warp iteration runs k-steps for the lanes that
+ * have some, unless at least ZB_SM_QUORUM lanes are waiting to close/open (or nobody has k-steps left), in which case those
+ * lanes do that together.  No lane waits for the longest loop of "the current position": lanes drift apart in position. */
+#define ZB_SM_QUORUM 16
+template <bool OT>
+__device__ __forceinline__ void zb_dp_sm_chunk(bool active, const uint8_t *__restrict__ t, const zb_match_t *__restrict__ m0, const uint8_t *plit, const uint8_t *plen,
+                                               const uint8_t *poff, int lo, int hi, int from, int end, uint16_t *ring0, uint16_t *far0, uint32_t *best) {
+   struct Mem { uint16_t *ring0, *far0; uint32_t *bp; int t_now;
+      __device__ __forceinline__ uint32_t cost(int tt) const {
+         if (tt < 0) return 0u;
+         return (t_now - tt < ZB_NR) ? (uint32_t)ring0[(tt & (ZB_NR - 1)) * ZB_DP_THREADS] : (uint32_t)far0[(size_t)tt * ZB_DP_THREADS];
+      }
+      __device__ __forceinline__ void put(int tt, uint32_t c) { ring0[(tt & (ZB_NR - 1)) * ZB_DP_THREADS] = (uint16_t)c; far0[(size_t)tt * ZB_DP_THREADS] = (uint16_t)c; }
+      __device__ __forceinline__ void best(int i, uint32_t w) { bp[i] = w; }
+   } mem = {ring0, far0, best, 0};
+   auto offcost = [&](uint32_t off) -> uint32_t { return zb_dp_offcost<OT>(poff, off); };
+   ZbDpLane S;
+   S.i = from - 1; S.t = 0; S.cprev = 0; S.bnd = 0; S.q0 = 0; S.q1 = 0; S.k = ZB_MIN_MATCH; S.curk = 0; S.mcur = 0; S.curmin = 0; S.offc = 0; S.bt = 0; S.bk = 0; S.bm = 0; S.lit = 0;
+   bool finished = !active || S.i < lo, open = false;
+   ZbMatchRec nxt; uint32_t nlit = 0;
+#pragma unroll
+   for (int m = 0; m < ZB_NMATCH; m++) nxt.w[m] = 0;
+   if (!finished) { nxt = zb_load_rec(m0, S.i); nlit = t[S.i]; }
+   for (;;) {
+      const bool want_k = !finished && open && S.bnd != 0;
+      const bool want_adv = !finished && !want_k;
+      const uint32_t mk = __ballot_sync(0xffffffffu, want_k), ma = __ballot_sync(0xffffffffu, want_adv);
+      if (!(mk | ma)) break;
+      if (__popc(ma) >= ZB_SM_QUORUM || !mk) {
+         if (want_adv) {
+            if (open) {
+               mem.t_now = S.t;
+               zb_dpsm_close(S, mem, end, plit, plen, offcost, S.i < hi);
+               open = false;
+               if (S.i < lo) finished = true;
+            }
+            if (!finished) {
+               S.rec = nxt; S.lit = nlit;
+               if (S.i - 1 >= lo) { nxt = zb_load_rec(m0, S.i - 1); nlit = t[S.i - 1]; }
+               zb_dpsm_open(S, end, offcost);
+               open = true;
+            }
+         }
+      } else {
+         if (want_k) { mem.t_now = S.t; zb_dpsm_kstep(S, mem, plen); }
+         if (want_k && S.bnd != 0) zb_dpsm_kstep(S, mem, plen);
+      }
+   }
+}
+
+__global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_sm_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
+                                                                  const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw,
+                                                                  size_t SS, uint16_t *far, int CD, int WU) {
+   __shared__ uint16_t ring_s[ZB_NR * ZB_DP_THREADS];
+   __shared__ ZbCostTab tab_s[ZB_DP_THREADS / 32];
+   __shared__ uint8_t offtab_s[ZB_DP_THREADS / 32][512];
+   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+   const long cw = (long)blockIdx.x * ZB_DP_THREADS + wi * 32;
+   if (cw >= ndch) return;                /* the whole warp */
+   const long c = cw + lane;
+   const uint32_t x0 = dcs[cw];
+   {
+      const uint32_t *src = (const uint32_t *)&tb[x0].cost; uint32_t *dstw = (uint32_t *)&tab_s[wi];
+      for (int e = lane; e < (int)(sizeof(ZbCostTab) / 4); e += 32) dstw[e] = src[e];
+   }
+   uint16_t *ring0 = ring_s + threadIdx.x;
+   for (int e = 0; e < ZB_NR; e++) ring0[e * ZB_DP_THREADS] = 0;
+   __syncwarp();
+   for (int e = lane; e < 512; e += 32) offtab_s[wi][e] = tab_s[wi].off[zb_off_sym(e < 256 ? (uint32_t)e + 1u : 257u + ((uint32_t)(e - 256) << 7))];
+   __syncwarp();
+   const bool uniform = __all_sync(0xffffffffu, (c < ndch ? dcs[c] : x0) == x0);
+   /* every lane stays in the warp loop (it votes); lanes without a chunk are inactive */
+   bool active = c < ndch;
+   const uint32_t x = active ? dcs[c] : x0;
+   const ZbSub s = sb[x];
+   if (pass > 0 && !s.is_dyn) active = false;
+   const uint32_t k = active ? (uint32_t)c - s.dchunk_base : 0u;
+   const uint32_t gb = wbs[s.win];
+   const uint8_t *t = T + wd[s.win].in_off;
+   const zb_match_t *m0 = mt + ((size_t)gb << 3);
+   const int lo = (int)(s.ps + k * CD);
+   const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
+   const int end = (int)s.pe;
+   int from = hi + WU; if (from > end) from = end;
+   uint16_t *far0 = far + (size_t)blockIdx.x * (size_t)(CD + WU) * ZB_DP_THREADS + threadIdx.x;
+   if (uniform) zb_dp_sm_chunk<true>(active, t, m0, tab_s[wi].lit, tab_s[wi].len, offtab_s[wi], lo, hi, from, end, ring0, far0, (uint32_t *)(bm + gb));
+   else zb_dp_sm_chunk<false>(active, t, m0, tb[x].cost.lit, tb[x].cost.len, tb[x].cost.off, lo, hi, from, end, ring0, far0, (uint32_t *)(bm + gb));
+   if (!active) return;
+   /* both signatures out of the cost row (position p was done at step from - 1 - p) */
+   const int tw = from - hi, tall = from - lo;
+   const uint32_t cw_ = tw > 0 ? (uint32_t)far0[(size_t)(tw - 1) * ZB_DP_THREADS] : 0u, ct_ = tall > 0 ? (uint32_t)far0[(size_t)(tall - 1) * ZB_DP_THREADS] : 0u;
+   zb_dp_signature(sgw + (size_t)c, SS, far0, hi, from, end, tw, cw_, true);
+   zb_dp_signature(sgt + (size_t)c, SS, far0, lo, from, end, tall, ct_, false);
+}
+
 /* ---- repair of wrong chunks: the same recurrence, ONE WARP per chain ----
  * Chunks whose warm-up did not re-synchronise (byte runs, periodic records: the state never forgets the phase it was
  * started with) have to be redone from their right neighbour's true costs, one after the other.  That is a serial chain,
@@ -1813,8 +1910,10 @@ inline void ZbPipe::stage_parse() {
                the compiler's 56).  Measured on enwik100m: 0 and 8 equal (18.6 ms), 7 slower (21.5 ms), 10 CTAs at 48
                registers slower still (25.6 ms). */
             static const int minb = getenv("ZULTRA_CUDA_DP_MINB") ? atoi(getenv("ZULTRA_CUDA_DP_MINB")) : 0;
+            static const int use_sm = getenv("ZULTRA_CUDA_DP_SM") ? atoi(getenv("ZULTRA_CUDA_DP_SM")) : 0;
             const unsigned grid = (unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS);
-            if (minb == 6) zb_parse_dp_k<6><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
+            if (use_sm) zb_parse_dp_sm_k<<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
+            else if (minb == 6) zb_parse_dp_k<6><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
             else if (minb == 7) zb_parse_dp_k<7><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
             else if (minb == 8) zb_parse_dp_k<8><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
             else zb_parse_dp_k<0><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
@@ -1825,9 +1924,48 @@ inline void ZbPipe::stage_parse() {
       }
 #else
       zb_tag("parse_dp");
+      const bool emu_sm = getenv("ZB_EMU_DP_SM") != 0;    /* host build only: run the chunks through the lane state machine (zb_dpsm_*) */
       zb_launch(st, ndch, ZB_LAMBDA(long c) {
          const ZbSub s = sb[dcs[c]];
          if (pass > 0 && !s.is_dyn) return;
+         if (emu_sm) {
+            if (c == 0 && pass == 0 && getenv("ZB_EMU_DP_SM")[0] == '2') fprintf(stderr, "parse: lane state machine path\n");
+            const uint32_t kc = (uint32_t)c - s.dchunk_base;
+            const uint32_t gb = wbs[s.win];
+            const uint8_t *t = T + wd[s.win].in_off;
+            const zb_match_t *m0 = mt + ((size_t)gb << 3);
+            const int lo = (int)(s.ps + kc * CD);
+            const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
+            const int end = (int)s.pe;
+            int from = hi + WU; if (from > end) from = end;
+            const ZbCostTab &ct = tb[dcs[c]].cost;
+            struct Mem {
+               std::vector<uint32_t> v; zb_match_t *bp;
+               uint32_t cost(int tt) const { return tt >= 0 ? v[(size_t)tt] : 0u; }
+               void put(int t, uint32_t x) { if (x > 0xffffu) { fprintf(stderr, "dp cost overflow\n"); abort(); } v[(size_t)t] = x; }
+               void best(int i, uint32_t w) { bp[i].length = (uint16_t)(w & 0xffffu); bp[i].offset = (uint16_t)(w >> 16); }
+            } mem;
+            mem.v.assign((size_t)(from - lo) + 1, 0u); mem.bp = bm + gb;
+            auto offcost = [&](uint32_t off) -> uint32_t { return ct.off[zb_off_sym(off)]; };
+            ZbDpLane S; memset(&S, 0, sizeof(S));
+            S.i = from - 1; S.t = 0; S.cprev = 0;
+            while (S.i >= lo) {
+               S.rec = zb_load_rec(m0, S.i); S.lit = t[S.i];
+               zb_dpsm_open(S, end, offcost);
+               while (S.bnd) zb_dpsm_kstep(S, mem, ct.len);
+               zb_dpsm_close(S, mem, end, ct.lit, ct.len, offcost, S.i < hi);
+            }
+            /* signatures from the cost row, as zb_dp_signature does on the device */
+            const int tw = from - hi, tall = from - lo;
+            const uint32_t bw_ = tw > 0 ? mem.v[(size_t)tw - 1] : 0u, bt_ = tall > 0 ? mem.v[(size_t)tall - 1] : 0u;
+            int16_t *sw = sgw + (size_t)c, *sg = sgt + (size_t)c;
+            for (int q = 0; q <= ZB_MAX_MATCH; q++) {
+               const uint32_t vw = mem.cost(tw - 1 - q), vt = mem.cost(tall - 1 - q);
+               sw[(size_t)q * SS] = (hi + q <= end && hi + q <= from) ? (int16_t)(uint16_t)(vw - bw_) : (int16_t)0;
+               sg[(size_t)q * SS] = (lo + q <= end) ? (int16_t)(uint16_t)(vt - bt_) : (int16_t)0;
+            }
+            return;
+         }
          const uint32_t k = (uint32_t)c - s.dchunk_base;
          const uint32_t gb = wbs[s.win];
          const uint8_t *t = T + wd[s.win].in_off;
