@@ -162,3 +162,11 @@ def test_emulated_lane_state_machine_vs_golden(emu, name, monkeypatch):
     data = cases.small_cases()[name]
     out, bits, d = emu.compress(data)
     assert _gold_ok("%s/deflate" % name, out)
+
+
+def test_emulated_lane_state_machine_multi_block(emu, ref, monkeypatch):
+    """Same, over several max-blocks with history, sub-block splits and clamped matches at sub-block ends."""
+    monkeypatch.setenv("ZB_EMU_DP_SM", "1")
+    for name, data, block in cases.multi_block_cases()[1:3]:
+        out, bits, _ = emu.compress(data, block=block or (1 << 20))
+        assert out == ref.compress(data, flags=0, block=block), name
