@@ -13,10 +13,16 @@ import numpy as np
 SEED_JS, SEED_ENWIK, SEED_MOZ, SEED_MIX, SEED_BATCH = 0x5A170001, 0x5A170002, 0x5A170003, 0x5A170004, 0x5A170005
 
 
+_ZIPF_CDF = {}
+
+
 def _zipf_ids(rng, n, vocab, s=1.1):
-    w = 1.0 / np.arange(1, vocab + 1) ** s
-    cdf = np.cumsum(w)
-    cdf /= cdf[-1]
+    cdf = _ZIPF_CDF.get((vocab, s))
+    if cdf is None:      # the table depends on (vocab, s) only: computing it once per page cost half the generator's time
+        w = 1.0 / np.arange(1, vocab + 1) ** s
+        cdf = np.cumsum(w)
+        cdf /= cdf[-1]
+        _ZIPF_CDF[(vocab, s)] = cdf
     return np.searchsorted(cdf, rng.random(n)).astype(np.int64)
 
 
