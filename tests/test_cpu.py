@@ -170,3 +170,8 @@ def test_emulated_lane_state_machine_multi_block(emu, ref, monkeypatch):
     for name, data, block in cases.multi_block_cases()[1:3]:
         out, bits, _ = emu.compress(data, block=block or (1 << 20))
         assert out == ref.compress(data, flags=0, block=block), name
+
+
+def test_cost_row_buffer_selftest(emu):
+    """ZbCostRowBuf: the 8-steps-at-a-time cost row of the decoupled-lane parse kernel."""
+    assert emu.lib.emu_selftest_rowbuf() == 0

@@ -802,4 +802,25 @@ ZB_HD void zb_dpsm_close(ZbDpLane &S, MEM &mem, int end, const uint8_t *plit, co
    S.i--; S.t++;
 }
 
+/* Cost row of one decoupled lane (zb_parse_dp_sm_k): lanes drift apart in step, so a [step][thread] row would be written one
+   2-byte store per lane and line.  Instead every lane owns a contiguous row and writes it 8 steps (16 bytes) at a time out of
+   a 128-bit shift register; a step is readable from the row once its group of 8 has been flushed, which is always the case
+   for the far reads (>= 64 steps back) and for the signatures (taken after finish()). */
+struct ZbCostRowBuf {
+   uint32_t b0, b1, b2, b3;
+   ZB_HD void init() { b0 = b1 = b2 = b3 = 0; }
+   /* append the cost of step t (t = 0, 1, 2, ...); flushes the group when it is complete */
+   ZB_HD void put(uint16_t *row, int t, uint32_t c) {
+      b0 = (b0 >> 16) | (b1 << 16); b1 = (b1 >> 16) | (b2 << 16); b2 = (b2 >> 16) | (b3 << 16); b3 = (b3 >> 16) | (c << 16);
+      if ((t & 7) == 7) { uint32_t *d = (uint32_t *)(row + (t - 7)); d[0] = b0; d[1] = b1; d[2] = b2; d[3] = b3; }
+   }
+   /* after the last put (nsteps steps in total): write the incomplete last group */
+   ZB_HD void finish(uint16_t *row, int nsteps) {
+      const int rem = nsteps & 7;
+      if (!rem) return;
+      for (int j = rem; j < 8; j++) { b0 = (b0 >> 16) | (b1 << 16); b1 = (b1 >> 16) | (b2 << 16); b2 = (b2 >> 16) | (b3 << 16); b3 >>= 16; }
+      uint32_t *d = (uint32_t *)(row + (nsteps - rem)); d[0] = b0; d[1] = b1; d[2] = b2; d[3] = b3;
+   }
+};
+
 #endif /* ZB_CORE_H */

@@ -1360,8 +1360,8 @@ __device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const
 
 /* the 259 relative costs at `pos0` (the signature two neighbouring chunks are compared by), read back from the scratch row:
    position p was done at step from - 1 - p; positions at and above `from` are the zero guess */
-__device__ __forceinline__ void zb_dp_signature(int16_t *__restrict__ dst, size_t SS, const uint16_t *__restrict__ far0, int pos0, int from, int end, int t, uint32_t cprev, bool warm) {
-   const int NT = ZB_DP_THREADS;
+__device__ __forceinline__ void zb_dp_signature(int16_t *__restrict__ dst, size_t SS, const uint16_t *__restrict__ far0, int pos0, int from, int end, int t, uint32_t cprev, bool warm,
+                                                const int NT = ZB_DP_THREADS /* elements between consecutive steps of the cost row */) {
    /* loads batched 8 deep: each is an L2 round trip, and nothing else of this thread is in flight here */
    for (int q0 = 0; q0 <= ZB_MAX_MATCH; q0 += 8) {
       uint32_t v[8];
@@ -1444,14 +1444,16 @@ __global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub
 template <bool OT>
 __device__ __forceinline__ void zb_dp_sm_chunk(bool active, const uint8_t *__restrict__ t, const zb_match_t *__restrict__ m0, const uint8_t *plit, const uint8_t *plen,
                                                const uint8_t *poff, int lo, int hi, int from, int end, uint16_t *ring0, uint16_t *far0, uint32_t *best) {
-   struct Mem { uint16_t *ring0, *far0; uint32_t *bp; int t_now;
+   /* far0 = this lane's own contiguous cost row (steps 0, 1, 2, ...), written 8 steps at a time (ZbCostRowBuf) */
+   struct Mem { uint16_t *ring0, *far0; uint32_t *bp; int t_now; ZbCostRowBuf rb;
       __device__ __forceinline__ uint32_t cost(int tt) const {
          if (tt < 0) return 0u;
-         return (t_now - tt < ZB_NR) ? (uint32_t)ring0[(tt & (ZB_NR - 1)) * ZB_DP_THREADS] : (uint32_t)far0[(size_t)tt * ZB_DP_THREADS];
+         return (t_now - tt < ZB_NR) ? (uint32_t)ring0[(tt & (ZB_NR - 1)) * ZB_DP_THREADS] : (uint32_t)far0[tt];
       }
-      __device__ __forceinline__ void put(int tt, uint32_t c) { ring0[(tt & (ZB_NR - 1)) * ZB_DP_THREADS] = (uint16_t)c; far0[(size_t)tt * ZB_DP_THREADS] = (uint16_t)c; }
+      __device__ __forceinline__ void put(int tt, uint32_t c) { ring0[(tt & (ZB_NR - 1)) * ZB_DP_THREADS] = (uint16_t)c; rb.put(far0, tt, c); }
       __device__ __forceinline__ void best(int i, uint32_t w) { bp[i] = w; }
-   } mem = {ring0, far0, best, 0};
+   } mem;
+   mem.ring0 = ring0; mem.far0 = far0; mem.bp = best; mem.t_now = 0; mem.rb.init();
    auto offcost = [&](uint32_t off) -> uint32_t { return zb_dp_offcost<OT>(poff, off); };
    ZbDpLane S;
    S.i = from - 1; S.t = 0; S.cprev = 0; S.bnd = 0; S.q0 = 0; S.q1 = 0; S.k = ZB_MIN_MATCH; S.curk = 0; S.mcur = 0; S.curmin = 0; S.offc = 0; S.bt = 0; S.bk = 0; S.bm = 0; S.lit = 0;
@@ -1485,6 +1487,7 @@ __device__ __forceinline__ void zb_dp_sm_chunk(bool active, const uint8_t *__res
          if (want_k && S.bnd != 0) zb_dpsm_kstep(S, mem, plen);
       }
    }
+   if (active) mem.rb.finish(far0, S.t);
 }
 
 __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_sm_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
@@ -1521,15 +1524,16 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_sm_k(const ZbSub *s
    const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
    const int end = (int)s.pe;
    int from = hi + WU; if (from > end) from = end;
-   uint16_t *far0 = far + (size_t)blockIdx.x * (size_t)(CD + WU) * ZB_DP_THREADS + threadIdx.x;
+   const size_t rstride = (size_t)((CD + WU + 7) & ~7);      /* u16 per lane row: a multiple of 8, so the 16-byte groups are aligned */
+   uint16_t *far0 = far + ((size_t)blockIdx.x * ZB_DP_THREADS + threadIdx.x) * rstride;
    if (uniform) zb_dp_sm_chunk<true>(active, t, m0, tab_s[wi].lit, tab_s[wi].len, offtab_s[wi], lo, hi, from, end, ring0, far0, (uint32_t *)(bm + gb));
    else zb_dp_sm_chunk<false>(active, t, m0, tb[x].cost.lit, tb[x].cost.len, tb[x].cost.off, lo, hi, from, end, ring0, far0, (uint32_t *)(bm + gb));
    if (!active) return;
    /* both signatures out of the cost row (position p was done at step from - 1 - p) */
    const int tw = from - hi, tall = from - lo;
-   const uint32_t cw_ = tw > 0 ? (uint32_t)far0[(size_t)(tw - 1) * ZB_DP_THREADS] : 0u, ct_ = tall > 0 ? (uint32_t)far0[(size_t)(tall - 1) * ZB_DP_THREADS] : 0u;
-   zb_dp_signature(sgw + (size_t)c, SS, far0, hi, from, end, tw, cw_, true);
-   zb_dp_signature(sgt + (size_t)c, SS, far0, lo, from, end, tall, ct_, false);
+   const uint32_t cw_ = tw > 0 ? (uint32_t)far0[tw - 1] : 0u, ct_ = tall > 0 ? (uint32_t)far0[tall - 1] : 0u;
+   zb_dp_signature(sgw + (size_t)c, SS, far0, hi, from, end, tw, cw_, true, 1);
+   zb_dp_signature(sgt + (size_t)c, SS, far0, lo, from, end, tall, ct_, false, 1);
 }
 
 /* ---- repair of wrong chunks: the same recurrence, ONE WARP per chain ----
@@ -1885,7 +1889,7 @@ inline void ZbPipe::stage_parse() {
    pentry.need(npch + 1); pbits.need(npch + 1);
 #ifndef ZB_EMU
    exitc.need((size_t)(npch + 1) * ZB_EXROW);
-   dpfar.need((size_t)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS) * (size_t)(CD + WU) * ZB_DP_THREADS + 64);
+   dpfar.need((size_t)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS) * (size_t)(CD + WU + 8) * ZB_DP_THREADS + 64);   /* + 8: per-lane rows of the decoupled-lane kernel are padded to 8 steps */
 #endif
    uint32_t *dcs = dchunk_sub.p, *pcs = pchunk_sub.p;
    zb_launch(st, ns, ZB_LAMBDA(long x) {
