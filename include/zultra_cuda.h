@@ -67,6 +67,32 @@ int zultra_cuda_shard_prepare(zultra_cuda_ctx_t *pCtx, const void *pDevInData, i
 int zultra_cuda_shard_emit(zultra_cuda_ctx_t *pCtx, unsigned int nInBitCount, void *pDevOutData, size_t nMaxOutDataSize, unsigned long long *pnOutBitCount);
 unsigned int zultra_cuda_checksum_combine(unsigned int nFlags, unsigned int nChecksum1, unsigned int nChecksum2, unsigned long long nLength2);
 
+/*
+ * Several GPUs behind one context (SURVEY 8(b) extension ii; north_star "sharded across the GPUs of one 8xB200 box").  After
+ * zultra_cuda_ctx_set_devices(ctx, n) every zultra_cuda_compress_blocks call on that context with at least two max-blocks
+ * spreads them over devices device .. device+n-1 (mod the device count): chunks of a few max-blocks dealt round-robin, one
+ * host thread and pipeline per device, phase maps composed on the host, every chunk's bytes copied from its device straight
+ * to their byte offset in pOutData.  The libzultra front end sets this from ZULTRA_CUDA_DEVICES, so zultra_memory_compress,
+ * the streaming API and the CLI use n GPUs.  Returns the device count actually used.  (Per-block loop: libzultra.c:269-438.)
+ */
+int zultra_cuda_ctx_set_devices(zultra_cuda_ctx_t *pCtx, int nDevices);
+
+/*
+ * One process per GPU (bench.py under torchrun): the same chunk scheme with the exchange left to the caller (NCCL).
+ * chunks_prepare: nChunks chunks of ONE device-resident buffer, chunk i = [pnChunkHistory[i] bytes of preceding input |
+ * pnChunkSize[i] bytes] starting at byte pnChunkOffset[i]; returns an 8-entry phase map (pnPhaseBits8 + 8 i) and the
+ * checksum of the chunk's own bytes from the initial value, per chunk.  chunks_emit: entering phase per chunk (from the
+ * composed maps of ALL ranks); leaves chunk i's bitstream at *ppDevOut + pnOutOffset[i] (device memory owned by the context,
+ * valid until its next call), pnOutBits[i] bits including the entering ones.  stitch_device (the gathering rank): OR-merges
+ * parts at their absolute bit offsets into a zeroed device buffer - the "shift and concatenate" of the stitch.
+ */
+int zultra_cuda_chunks_prepare(zultra_cuda_ctx_t *pCtx, const void *pDevInData, int nChunks, const size_t *pnChunkOffset, const int *pnChunkHistory,
+                               const size_t *pnChunkSize, const int *pnChunkFinalize, unsigned int nMaxBlockSize, unsigned int nFlags,
+                               unsigned int *pnChecksums, unsigned long long *pnPhaseBits8);
+int zultra_cuda_chunks_emit(zultra_cuda_ctx_t *pCtx, const unsigned int *pnInBitCounts, void **ppDevOut, size_t *pnOutOffset, unsigned long long *pnOutBits);
+int zultra_cuda_stitch_device(zultra_cuda_ctx_t *pCtx, void *pDevDst, int nParts, const void *const *ppDevSrc, const unsigned long long *pnDstBitOffset,
+                              const unsigned long long *pnBits);
+
 /* Batch of independent streams, each equal to zultra_memory_compress(p, n, .., nFlags, nMaxBlockSize) (config 5 of
    BASELINE.json; an extension, not in the reference).  pnOutSizes[i] = (size_t)-1 on per-stream failure. */
 int zultra_cuda_memory_compress_batch(zultra_cuda_ctx_t *pCtx, const unsigned char *const *ppInData, const size_t *pnInSizes,
@@ -92,6 +118,9 @@ int zultra_cuda_block_stages(zultra_cuda_ctx_t *pCtx, const unsigned char *pWind
 int zultra_cuda_last_timings(zultra_cuda_ctx_t *pCtx, float *pMs8);
 /* counters of the last call: {windows, sub-blocks, suffix-sort rounds, parse chunks redone, kernel launches, stored sub-blocks, ub_hits, tiles} */
 int zultra_cuda_last_counters(zultra_cuda_ctx_t *pCtx, long long *pCounters8);
+
+/* kernels this library has launched in this process so far (all contexts, all host threads) */
+long long zultra_cuda_launch_count(void);
 
 /* per-kernel CUDA-event timing: zultra_cuda_profile(1) turns it on; collect returns rows {32-byte name, total ms, launches} and clears */
 void zultra_cuda_profile(int nOn);

@@ -18,6 +18,30 @@ long emu_shard_emit(int in_bits, uint8_t *out, long cap, unsigned long long *bit
    return (long)((*bits + 7) / 8);
 }
 
+/* several chunks of one buffer per call, host build: same two calls as zultra_cuda_chunks_prepare / _emit */
+static ZbPipe g_chunk_pipe;
+int emu_chunks_prepare(const uint8_t *buf, int nchunks, const size_t *off, const int *hist, const size_t *len, const int *fin, unsigned block_size, unsigned flags,
+                       unsigned *cks, unsigned long long *maps8) {
+   g_chunk_pipe.st = 0;
+   const int kind = (flags & 2) ? 2 : ((flags & 1) ? 1 : 0);
+   std::vector<ZbStreamIn> s((size_t)nchunks);
+   for (int i = 0; i < nchunks; i++) { ZbStreamIn t = {0, len[i], 0, (uint32_t)hist[i], fin[i], 0, kind == 1 ? 1u : 0u, off[i]}; s[i] = t; }
+   std::vector<uint8_t> o; std::vector<ZbStreamRes> r;
+   ZbRunOpts opt; opt.dev_in = buf; opt.dev_offsets = 1; opt.phase = 1; opt.checksum_kind = kind;
+   if (zb_run_batch(g_chunk_pipe, s.data(), nchunks, block_size, o, r, opt)) return -1;
+   memcpy(maps8, opt.phase_maps.data(), sizeof(unsigned long long) * 8 * (size_t)nchunks);
+   for (int i = 0; i < nchunks; i++) cks[i] = r[i].checksum;
+   return 0;
+}
+long emu_chunks_emit(const unsigned *in_bits, uint8_t *out, long cap, size_t *out_off, unsigned long long *bits) {
+   if (zb_finish_chunks(g_chunk_pipe, in_bits, out_off, bits)) return -1;
+   size_t end = 0;
+   for (size_t i = 0; i < g_chunk_pipe.plan.size(); i++) end = std::max(end, out_off[i] + (size_t)((bits[i] + 7) / 8));
+   if ((long)end > cap) return -2;
+   memcpy(out, g_chunk_pipe.out.p, end);
+   return (long)end;
+}
+
 /* single stream, one call; returns bytes written (ceil(bits/8)), *bits = total bits */
 long emu_compress(const uint8_t *data, long n, const uint8_t *hist, int hist_len, unsigned block_size, int finalize, int in_bits,
                   uint8_t *out, long out_cap, unsigned long long *bits, unsigned tile_main,

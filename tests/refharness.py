@@ -103,3 +103,24 @@ class Emu:
         n = self.lib.emu_shard_emit(in_bits, _p(out), C.c_long(cap), C.byref(bits))
         assert n >= 0
         return out[:n].tobytes(), bits.value
+
+    def chunks_prepare(self, buf, chunks, block=1 << 20, flags=0):
+        """chunks: [(offset of the chunk's history start in buf, history bytes, chunk bytes, finalize)] -> (maps [n][8], checksums)."""
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self._keep = buf
+        n = len(chunks)
+        off = (C.c_size_t * n)(*[c[0] for c in chunks]); hist = (C.c_int * n)(*[c[1] for c in chunks])
+        ln = (C.c_size_t * n)(*[c[2] for c in chunks]); fin = (C.c_int * n)(*[c[3] for c in chunks])
+        cks = (C.c_uint * n)(); maps = (C.c_ulonglong * (8 * n))()
+        rc = self.lib.emu_chunks_prepare(_p(buf), n, off, hist, ln, fin, C.c_uint(block), C.c_uint(flags), cks, maps)
+        assert rc == 0
+        return [[int(maps[8 * i + p]) for p in range(8)] for i in range(n)], [int(c) for c in cks]
+
+    def chunks_emit(self, in_bits, cap):
+        n = len(in_bits)
+        ib = (C.c_uint * n)(*in_bits); off = (C.c_size_t * n)(); bits = (C.c_ulonglong * n)()
+        out = np.zeros(cap, dtype=np.uint8)
+        self.lib.emu_chunks_emit.restype = C.c_long
+        r = self.lib.emu_chunks_emit(ib, _p(out), C.c_long(cap), off, bits)
+        assert r >= 0, r
+        return [out[off[i]:off[i] + (bits[i] + 7) // 8].tobytes() for i in range(n)], [int(b) for b in bits]

@@ -65,6 +65,13 @@ def load():
         L.zultra_cuda_window_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint]
         L.zultra_cuda_block_stages.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.zultra_cuda_checksum_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p]
+        L.zultra_cuda_ctx_set_devices.argtypes = [C.c_void_p, C.c_int]
+        L.zultra_cuda_chunks_prepare.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p]
+        L.zultra_cuda_chunks_emit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.zultra_cuda_stitch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.zultra_cuda_profile.argtypes = [C.c_int]
+        L.zultra_cuda_launch_count.restype = C.c_longlong
+        L.zultra_cuda_profile_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.zultra_cuda_last_timings.argtypes = [C.c_void_p, C.c_void_p]
         L.zultra_cuda_last_counters.argtypes = [C.c_void_p, C.c_void_p]
         _lib = L
@@ -181,6 +188,38 @@ class CudaCtx:
             raise RuntimeError("zultra_cuda_shard_emit failed: %d" % rc)
         return bits.value
 
+    def set_devices(self, n):
+        """Spread every compress_blocks call of this context over n devices (zultra_cuda_ctx_set_devices); returns the count used."""
+        return self.L.zultra_cuda_ctx_set_devices(self.p, n)
+
+    def chunks_prepare(self, dev_in_ptr, chunks, block=0, flags=0):
+        """chunks: [(offset of the chunk's history start in the resident buffer, history bytes, chunk bytes, finalize)].
+        Returns (maps [n][8], checksums [n])."""
+        n = len(chunks)
+        off = (C.c_size_t * n)(*[c[0] for c in chunks]); hist = (C.c_int * n)(*[c[1] for c in chunks])
+        ln = (C.c_size_t * n)(*[c[2] for c in chunks]); fin = (C.c_int * n)(*[c[3] for c in chunks])
+        cks = (C.c_uint * n)(); maps = (C.c_ulonglong * (8 * n))()
+        rc = self.L.zultra_cuda_chunks_prepare(self.p, dev_in_ptr, n, off, hist, ln, fin, block, flags, cks, maps)
+        if rc != 0:
+            raise RuntimeError("zultra_cuda_chunks_prepare failed: %d" % rc)
+        return [[int(maps[8 * i + p]) for p in range(8)] for i in range(n)], [int(c) for c in cks]
+
+    def chunks_emit(self, in_bits):
+        """Emit the prepared chunks at their entering phases; returns (device pointer, byte offsets [n], bits [n])."""
+        n = len(in_bits)
+        ib = (C.c_uint * n)(*in_bits); off = (C.c_size_t * n)(); bits = (C.c_ulonglong * n)(); ptr = C.c_void_p()
+        rc = self.L.zultra_cuda_chunks_emit(self.p, ib, C.byref(ptr), off, bits)
+        if rc != 0:
+            raise RuntimeError("zultra_cuda_chunks_emit failed: %d" % rc)
+        return ptr.value, [int(o) for o in off], [int(b) for b in bits]
+
+    def stitch_device(self, dev_dst_ptr, src_ptrs, dst_bits, nbits):
+        n = len(src_ptrs)
+        sp = (C.c_void_p * n)(*src_ptrs); db = (C.c_ulonglong * n)(*dst_bits); nb = (C.c_ulonglong * n)(*nbits)
+        rc = self.L.zultra_cuda_stitch_device(self.p, dev_dst_ptr, n, sp, db, nb)
+        if rc != 0:
+            raise RuntimeError("zultra_cuda_stitch_device failed: %d" % rc)
+
     def window_sa_lcp(self, win):
         w = _u8(win)
         out = np.zeros(len(w), dtype=np.uint32)
@@ -214,7 +253,7 @@ class CudaCtx:
     def counters(self):
         v = (C.c_longlong * 8)()
         self.L.zultra_cuda_last_counters(self.p, v)
-        return dict(zip(["windows", "sub_blocks", "sa_rounds", "parse_redo", "launches", "r5", "r6", "r7"], [int(x) for x in v]))
+        return dict(zip(["windows", "sub_blocks", "sa_rounds", "parse_redo", "launches", "r5", "devices", "r7"], [int(x) for x in v]))
 
     def memory_compress_batch(self, payloads, flags=ZULTRA_FLAG_ZLIB_FRAMING, block=0):
         n = len(payloads)

@@ -4,13 +4,22 @@
  *
  * Same observable contract as the reference state machine (libzultra.c:82-619): header first, deflate data
  * for whole max-blocks, footer after FINALIZE, ZULTRA_STREAM_END exactly once, identical output bytes.
- * What differs is pacing: input is staged on the host and handed to the GPU many max-blocks at a time
- * (ZULTRA_CUDA_BATCH_BLOCKS, default 64), because one block per launch would leave the device idle.  As in the
- * reference a full block is only compressed once more input is visible or on FINALIZE (libzultra.c:269), so
- * block boundaries - and therefore the bytes - are the same.  There is no CPU compressor in this library.
+ * What differs is pacing: input is staged on the host and handed to the GPU a BATCH of max-blocks at a time
+ * (ZULTRA_CUDA_BATCH_BLOCKS, default 64; never more than that per engine call, whatever avail_in is), because one
+ * block per launch would leave the device idle.  As in the reference a full block is only compressed once more
+ * input is visible or on FINALIZE (libzultra.c:269), so block boundaries - and therefore the bytes - are the same.
+ *
+ * Overlap (reference libzultra.c:255-267,441-462 does input copy, compression and output
+ * draining strictly one after the other): a batch is compressed by a worker thread (H2D, kernels, D2H) while
+ * the calling thread keeps absorbing the caller's input into the other of two staging buffers and draining the
+ * previous batch's output.  The bit phase and the running checksum travel from batch to batch inside the
+ * worker's job record, so jobs are submitted in order and at most one is in flight.
+ *
+ * There is no CPU compressor in this library: no CUDA device -> ZULTRA_ERROR_COMPRESSION.
  */
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 #include "libzultra.h"
 #include "zultra_cuda.h"
 
@@ -21,16 +30,29 @@
 #define CSTATE_STREAM_ENDED 16
 #define CSTATE_STARTED 32
 
+/* one staged batch: [history (<= 32 KiB) | bytes]; n bytes of it (whole max-blocks unless finalizing) go to the GPU */
+typedef struct {
+   unsigned char *in; size_t in_cap, in_len; int hist_len;      /* staging buffer, bytes after the history, history length */
+   unsigned char *out; size_t out_cap;                          /* compressed bytes of this batch */
+   size_t n; int finalize;
+   unsigned int bit_count_in; unsigned char bit_byte_in; unsigned int adler;   /* carried in, adler also carried out */
+   unsigned long long bits; int rc;
+   struct _zultra_compressor_s *owner;
+   pthread_t th; int running;                                   /* 1: thread started and not yet joined, 2: ran inline (no thread could be made) */
+   int done;                                                    /* set (release) by the worker when rc / bits / out are final */
+} zb_job_t;
+
 struct _zultra_compressor_s {
    unsigned int flags, block_size, state;
    const void *dict; int dict_size;
    zultra_cuda_ctx_t *ctx;
-   /* staged input: [history (<=32K) | pending bytes] */
-   unsigned char *in; size_t in_cap, in_len; int hist_len;
    unsigned int batch_blocks;
-   /* compressed bytes waiting to be drained */
-   unsigned char *out; size_t out_cap, out_len, out_pos;
+   zb_job_t job[2];
+   int fill;                                         /* job[fill] is being filled; job[fill ^ 1] may be in flight */
+   /* compressed bytes waiting to be drained (they live in a finished job's out buffer) */
+   const unsigned char *out; size_t out_len, out_pos;
    unsigned int bit_count; unsigned char bit_byte;   /* partial byte carried between engine calls */
+   unsigned int adler;                               /* checksum after the last collected batch */
    unsigned char frame[16]; size_t frame_pos, frame_len;
 };
 
@@ -60,9 +82,11 @@ static int grow(zultra_stream_t *s, unsigned char **buf, size_t *cap, size_t kee
    return 0;
 }
 
+static int env_int(const char *name, int dflt) { const char *e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
+
 zultra_status_t zultra_stream_init(zultra_stream_t *pStream, const unsigned int nFlags, unsigned int nMaxBlockSize) {
    zultra_compressor_t *c;
-   const char *e;
+   int nb, ndev;
    if (!pStream->zalloc) pStream->zalloc = def_alloc;
    if (!pStream->zfree) pStream->zfree = def_free;
    pStream->adler = 0;
@@ -71,16 +95,18 @@ zultra_status_t zultra_stream_init(zultra_stream_t *pStream, const unsigned int 
    memset(c, 0, sizeof(*c));
    c->flags = nFlags;
    c->block_size = clamp_block(nMaxBlockSize);
-   c->batch_blocks = 64;
-   e = getenv("ZULTRA_CUDA_BATCH_BLOCKS");
-   if (e && atoi(e) > 0) c->batch_blocks = (unsigned int)atoi(e);
-   if ((size_t)c->batch_blocks * c->block_size > ((size_t)512 << 20)) c->batch_blocks = (unsigned int)(((size_t)512 << 20) / c->block_size);
-   e = getenv("ZULTRA_CUDA_DEVICE");
-   if (zultra_cuda_ctx_acquire(&c->ctx, e ? atoi(e) : -1) != 0) {
+   ndev = env_int("ZULTRA_CUDA_DEVICES", 1);
+   if (ndev < 1) ndev = 1;
+   nb = env_int("ZULTRA_CUDA_BATCH_BLOCKS", 0);
+   c->batch_blocks = nb > 0 ? (unsigned int)nb : 64u * (unsigned int)ndev;
+   if ((size_t)c->batch_blocks * c->block_size > ((size_t)512 << 20) * (size_t)ndev) c->batch_blocks = (unsigned int)(((size_t)512 << 20) * (size_t)ndev / c->block_size);
+   c->job[0].owner = c->job[1].owner = c;
+   if (zultra_cuda_ctx_acquire(&c->ctx, env_int("ZULTRA_CUDA_DEVICE", -1)) != 0) {
       /* no usable GPU: this library has no other way to compress */
       zultra_stream_end(pStream);
       return ZULTRA_ERROR_COMPRESSION;
    }
+   zultra_cuda_ctx_set_devices(c->ctx, ndev);
    return ZULTRA_OK;
 }
 
@@ -94,30 +120,56 @@ zultra_status_t zultra_stream_set_dictionary(zultra_stream_t *pStream, const voi
    return ZULTRA_ERROR_COMPRESSION;
 }
 
-/* hand `n` staged bytes (whole max-blocks unless finalizing) to the GPU */
-static zultra_status_t run_gpu(zultra_stream_t *s, size_t n, int finalize) {
+/* worker: one engine call for one staged batch */
+static void *job_main(void *arg) {
+   zb_job_t *j = (zb_job_t *)arg;
+   zultra_compressor_t *c = j->owner;
+   j->rc = zultra_cuda_compress_blocks(c->ctx, j->in, j->hist_len, j->in + j->hist_len, j->n, c->block_size, j->finalize, j->bit_count_in, c->flags,
+                                       &j->adler, j->out, j->out_cap, &j->bits);
+   __atomic_store_n(&j->done, 1, __ATOMIC_RELEASE);
+   return NULL;
+}
+
+/* wait for the batch in flight (if any) and make its bytes the ones being drained */
+static zultra_status_t collect(zultra_stream_t *s) {
    zultra_compressor_t *c = s->state;
-   unsigned long long bits = 0;
-   size_t cap = n + n / 8 + 4096 + (n / c->block_size + 1) * 64 * 6;
-   int rc;
-   if (grow(s, &c->out, &c->out_cap, 0, cap)) return ZULTRA_ERROR_MEMORY;
-   rc = zultra_cuda_compress_blocks(c->ctx, c->in, c->hist_len, c->in + c->hist_len, n, c->block_size, finalize, c->bit_count, c->flags,
-                                    &s->adler, c->out, c->out_cap, &bits);
-   if (rc) return rc == ZULTRA_CUDA_ERR_DST ? ZULTRA_ERROR_DST : ZULTRA_ERROR_COMPRESSION;
-   c->out[0] |= c->bit_byte;
-   c->out_pos = 0;
-   c->out_len = (size_t)(bits >> 3);
-   c->bit_count = (unsigned int)(bits & 7);
-   c->bit_byte = c->bit_count ? c->out[c->out_len] : 0;
-   if (finalize && c->bit_count) { c->out_len++; c->bit_count = 0; c->bit_byte = 0; }   /* flush_bits, libzultra.c:416 */
-   /* slide: keep the last 32 KiB as history (libzultra.c:406-412) */
-   {
-      size_t total = (size_t)c->hist_len + n, rest = c->in_len - n;
-      size_t keep = total > HISTORY_SIZE ? HISTORY_SIZE : total;
-      memmove(c->in, c->in + total - keep, keep + rest);
-      c->hist_len = (int)keep;
-      c->in_len = rest;
-   }
+   zb_job_t *j = &c->job[c->fill ^ 1];
+   if (!j->running) return ZULTRA_OK;
+   if (j->running == 1) pthread_join(j->th, NULL);
+   j->running = 0;
+   if (j->rc) return j->rc == ZULTRA_CUDA_ERR_DST ? ZULTRA_ERROR_DST : ZULTRA_ERROR_COMPRESSION;
+   j->out[0] |= j->bit_byte_in;
+   c->out = j->out; c->out_pos = 0;
+   c->out_len = (size_t)(j->bits >> 3);
+   c->bit_count = (unsigned int)(j->bits & 7);
+   c->bit_byte = c->bit_count ? j->out[c->out_len] : 0;
+   if (j->finalize && c->bit_count) { c->out_len++; c->bit_count = 0; c->bit_byte = 0; }   /* flush_bits, libzultra.c:416 */
+   s->adler = c->adler = j->adler;
+   if (j->finalize) c->state |= CSTATE_FINALIZED;
+   return ZULTRA_OK;
+}
+
+/* Hand the first n staged bytes of the fill buffer to the worker; the rest, preceded by the last 32 KiB as history
+   (libzultra.c:406-412), moves to the other buffer, which becomes the fill buffer.  The caller has collected AND drained
+   the previous batch: its staging buffer is reused right now, its out buffer one batch later. */
+static zultra_status_t submit(zultra_stream_t *s, size_t n, int finalize) {
+   zultra_compressor_t *c = s->state;
+   zb_job_t *j = &c->job[c->fill], *o = &c->job[c->fill ^ 1];
+   const size_t total = (size_t)j->hist_len + n, rest = j->in_len - n;
+   const size_t keep = total > HISTORY_SIZE ? HISTORY_SIZE : total;
+   const size_t cap = n + n / 8 + 4096 + (n / c->block_size + 1) * 64 * 6;
+   if (grow(s, &j->out, &j->out_cap, 0, cap)) return ZULTRA_ERROR_MEMORY;
+   if (!finalize) {
+      if (grow(s, &o->in, &o->in_cap, 0, keep + rest + 65536)) return ZULTRA_ERROR_MEMORY;
+      memcpy(o->in, j->in + total - keep, keep + rest);
+      o->hist_len = (int)keep; o->in_len = rest;
+   } else { o->hist_len = 0; o->in_len = 0; }
+   j->n = n; j->finalize = finalize;
+   j->bit_count_in = c->bit_count; j->bit_byte_in = c->bit_byte; j->adler = c->adler;
+   j->rc = 0; j->bits = 0; j->done = 0;
+   if (pthread_create(&j->th, NULL, job_main, j) == 0) j->running = 1;
+   else { job_main(j); j->running = 2; }      /* no thread to be had: same result, no overlap */
+   c->fill ^= 1;
    return ZULTRA_OK;
 }
 
@@ -132,30 +184,34 @@ static void drain(zultra_stream_t *s, const unsigned char *src, size_t *pos, siz
 zultra_status_t zultra_stream_compress(zultra_stream_t *pStream, const int nDoFinalize) {
    zultra_compressor_t *c = pStream->state;
    zultra_status_t err = ZULTRA_OK;
+   size_t batch;
    if (!c || (c->state & CSTATE_STREAM_ENDED)) return ZULTRA_ERROR_COMPRESSION;
+   batch = (size_t)c->batch_blocks * c->block_size;
 
    if (!(c->state & CSTATE_HEADER_EMITTED)) {
       int n = zultra_frame_encode_header(c->frame, 16, c->flags, c->dict, c->dict_size);
       c->state |= CSTATE_HEADER_EMITTED | CSTATE_STARTED;
       if (n < 0) return ZULTRA_ERROR_COMPRESSION;
       c->frame_pos = 0; c->frame_len = (size_t)n;
-      pStream->adler = zultra_frame_init_checksum(c->flags);
+      pStream->adler = c->adler = zultra_frame_init_checksum(c->flags);
       if (c->dict && c->dict_size > 0) {   /* dictionary becomes the first history (libzultra.c:250-253) */
          const unsigned char *d = (const unsigned char *)c->dict;
+         zb_job_t *f = &c->job[c->fill];
          int k = c->dict_size > HISTORY_SIZE ? HISTORY_SIZE : c->dict_size;
-         if (grow(pStream, &c->in, &c->in_cap, 0, (size_t)HISTORY_SIZE + c->block_size)) return ZULTRA_ERROR_MEMORY;
-         memcpy(c->in, d + c->dict_size - k, (size_t)k);
-         c->hist_len = k;
+         if (grow(pStream, &f->in, &f->in_cap, 0, (size_t)HISTORY_SIZE + c->block_size)) return ZULTRA_ERROR_MEMORY;
+         memcpy(f->in, d + c->dict_size - k, (size_t)k);
+         f->hist_len = k;
       }
    }
 
    for (;;) {
+      zb_job_t *f, *o;
       /* 1. frame bytes (header or footer) */
       if (c->frame_pos < c->frame_len) {
          drain(pStream, c->frame, &c->frame_pos, c->frame_len);
          if (c->frame_pos < c->frame_len) break;   /* caller must provide more room */
       }
-      /* 2. compressed bytes */
+      /* 2. compressed bytes of the last collected batch */
       if (c->out_pos < c->out_len) {
          drain(pStream, c->out, &c->out_pos, c->out_len);
          if (c->out_pos < c->out_len) break;
@@ -168,22 +224,29 @@ zultra_status_t zultra_stream_compress(zultra_stream_t *pStream, const int nDoFi
          c->frame_pos = 0; c->frame_len = (size_t)n;
          continue;
       }
-      /* 3. absorb all caller input */
-      if (pStream->avail_in) {
-         size_t n = pStream->avail_in;
-         if (grow(pStream, &c->in, &c->in_cap, (size_t)c->hist_len + c->in_len, (size_t)c->hist_len + c->in_len + n)) { err = ZULTRA_ERROR_MEMORY; break; }
-         memcpy(c->in + c->hist_len + c->in_len, pStream->next_in, n);
-         c->in_len += n; pStream->next_in += n; pStream->avail_in = 0; pStream->total_in += n;
+      f = &c->job[c->fill]; o = &c->job[c->fill ^ 1];
+      /* 3. a batch that finished in the meantime: its bytes can flow now */
+      if (o->running && __atomic_load_n(&o->done, __ATOMIC_ACQUIRE)) { err = collect(pStream); if (err) break; continue; }
+      /* 4. absorb caller input, never more than one batch plus the byte that proves the last block has a successor */
+      if (pStream->avail_in && f->in_len <= batch) {
+         size_t n = batch + 1 - f->in_len;
+         if (n > pStream->avail_in) n = pStream->avail_in;
+         if (grow(pStream, &f->in, &f->in_cap, (size_t)f->hist_len + f->in_len, (size_t)f->hist_len + f->in_len + n)) { err = ZULTRA_ERROR_MEMORY; break; }
+         memcpy(f->in + f->hist_len + f->in_len, pStream->next_in, n);
+         f->in_len += n; pStream->next_in += n; pStream->avail_in -= n; pStream->total_in += n;
       }
-      /* 4. compress: everything on FINALIZE, else whole blocks while at least one further byte is staged */
-      if (nDoFinalize) {
-         if (c->in_len) { err = run_gpu(pStream, c->in_len, 1); if (err) break; c->state |= CSTATE_FINALIZED; continue; }
-         break;   /* nothing was ever staged for this call: the reference emits no block either (libzultra.c:275) */
-      } else {
-         size_t full = (c->in_len - 1) / c->block_size;   /* blocks that have a successor byte */
-         if (c->in_len && full >= c->batch_blocks) { err = run_gpu(pStream, full * c->block_size, 0); if (err) break; continue; }
-         break;
+      /* 5. compress: a whole batch once a further byte is staged; everything that is left on FINALIZE */
+      if (f->in_len > batch) {
+         if (o->running) { err = collect(pStream); if (err) break; continue; }      /* one batch in flight: wait, drain, come back */
+         err = submit(pStream, batch, 0); if (err) break;
+         continue;
       }
+      if (pStream->avail_in) continue;
+      if (!nDoFinalize) break;
+      if (o->running) { err = collect(pStream); if (err) break; continue; }
+      if (!f->in_len) break;   /* nothing was ever staged: the reference emits no block either (libzultra.c:275) */
+      err = submit(pStream, f->in_len, 1); if (err) break;
+      err = collect(pStream); if (err) break;
    }
    if (err) return err;
    if ((c->state & CSTATE_FOOTER_EMITTED) && c->frame_pos >= c->frame_len && c->out_pos >= c->out_len) {
@@ -196,9 +259,13 @@ zultra_status_t zultra_stream_compress(zultra_stream_t *pStream, const int nDoFi
 void zultra_stream_end(zultra_stream_t *pStream) {
    if (pStream->state && pStream->zfree) {
       zultra_compressor_t *c = pStream->state;
-      if (c->ctx) zultra_cuda_ctx_release(c->ctx);
-      if (c->in) pStream->zfree(pStream->opaque, c->in);
-      if (c->out) pStream->zfree(pStream->opaque, c->out);
+      int k;
+      for (k = 0; k < 2; k++) if (c->job[k].running == 1) { pthread_join(c->job[k].th, NULL); c->job[k].running = 0; }
+      if (c->ctx) zultra_cuda_ctx_release(c->ctx);      /* a context that saw a CUDA failure is destroyed there, not pooled */
+      for (k = 0; k < 2; k++) {
+         if (c->job[k].in) pStream->zfree(pStream->opaque, c->job[k].in);
+         if (c->job[k].out) pStream->zfree(pStream->opaque, c->job[k].out);
+      }
       pStream->zfree(pStream->opaque, c);
       pStream->state = NULL;
    }
@@ -211,25 +278,29 @@ size_t zultra_memory_bound(size_t nInputSize, const unsigned int nFlags, unsigne
 }
 
 /*
- * One-shot: no staging copy - the caller's buffer goes to the GPU in batches of up to 256 max-blocks with the
- * preceding 32 KiB as history and the bit phase carried across batches.  Returns (size_t)-1 on any failure,
+ * One-shot: no staging copy - the caller's buffer goes to the GPU(s) in batches of up to 256 max-blocks per device with
+ * the preceding 32 KiB as history and the bit phase carried across batches.  Returns (size_t)-1 on any failure,
  * including empty input and an output buffer that is too small (libzultra.c:608,617).
  */
 size_t zultra_memory_compress(const unsigned char *pInputData, size_t nInputSize, unsigned char *pOutBuffer, size_t nMaxOutBufferSize,
                               const unsigned int nFlags, unsigned int nMaxBlockSize) {
    zultra_cuda_ctx_t *ctx = NULL;
    const unsigned int block = clamp_block(nMaxBlockSize);
-   const size_t batch = (size_t)256 * block > ((size_t)256 << 20) ? ((size_t)256 << 20) / block * block : (size_t)256 * block;
+   int ndev = env_int("ZULTRA_CUDA_DEVICES", 1);
+   size_t batch;
    unsigned int ck = zultra_frame_init_checksum(nFlags), bit_count = 0;
    unsigned char bit_byte = 0;
    size_t w = 0, done = 0;
    int n;
-   const char *e = getenv("ZULTRA_CUDA_DEVICE");
+   if (ndev < 1) ndev = 1;
+   batch = (size_t)256 * block > ((size_t)256 << 20) ? ((size_t)256 << 20) / block * block : (size_t)256 * block;
+   batch *= (size_t)ndev;
    if (!nInputSize || !pInputData || !pOutBuffer) return (size_t)-1;
    n = zultra_frame_encode_header(pOutBuffer, nMaxOutBufferSize > 16 ? 16 : (int)nMaxOutBufferSize, nFlags, NULL, 0);
    if (n < 0) return (size_t)-1;
    w = (size_t)n;
-   if (zultra_cuda_ctx_acquire(&ctx, e ? atoi(e) : -1) != 0) return (size_t)-1;
+   if (zultra_cuda_ctx_acquire(&ctx, env_int("ZULTRA_CUDA_DEVICE", -1)) != 0) return (size_t)-1;
+   zultra_cuda_ctx_set_devices(ctx, ndev);
    while (done < nInputSize) {
       size_t k = nInputSize - done > batch ? batch : nInputSize - done;
       const int fin = done + k == nInputSize;

@@ -7,10 +7,10 @@
 #include <mutex>
 #include <thread>
 
-extern int g_zb_cuda_error;
 
 struct zultra_cuda_ctx_s {
    int device;
+   int broken = 0;      /* a CUDA call or allocation failed in this context: it is destroyed, never pooled again */
    unsigned tile = 0;
    ZbPipe pipe;
    float ms[8];
@@ -21,7 +21,20 @@ struct zultra_cuda_ctx_s {
    int nlanes = 1, lane_min_blocks = 4;   /* measured on B200: lanes do not pay (the big kernels are shared-memory / issue limited), kept for H2D overlap experiments */
    std::vector<zultra_cuda_ctx_s *> lanes;
    ZbBuf<uint32_t> lane_out;
+   /* several devices behind one context (zultra_cuda_ctx_set_devices): peers[k - 1] is the context on device (device + k) % count */
+   int ndev = 1;
+   std::vector<zultra_cuda_ctx_s *> peers;
+   int nchunks = 0;      /* chunks of the last zultra_cuda_chunks_prepare */
 };
+
+/* ZULTRA_CUDA_TRACE=1: timestamps (ms since the first traced event of the process) of the API's milestones on stderr */
+static void zb_trace(const char *what, const float *ms = 0) {
+   static const int on = getenv("ZULTRA_CUDA_TRACE") ? atoi(getenv("ZULTRA_CUDA_TRACE")) : 0;
+   if (!on) return;
+   static const double t0 = zb_now_ms();
+   if (ms) fprintf(stderr, "[zb %9.2f ms] %s: h2d %.2f sa %.2f match %.2f split %.2f parse %.2f emit %.2f d2h %.2f total %.2f\n", zb_now_ms() - t0, what, ms[0], ms[1], ms[2], ms[3], ms[4], ms[5], ms[6], ms[7]);
+   else fprintf(stderr, "[zb %9.2f ms] %s\n", zb_now_ms() - t0, what);
+}
 
 static int ctx_enter(zultra_cuda_ctx_t *c) {
    if (!c) return ZULTRA_CUDA_ERR_ARG;
@@ -30,10 +43,10 @@ static int ctx_enter(zultra_cuda_ctx_t *c) {
    return 0;
 }
 static int ctx_leave(zultra_cuda_ctx_t *c, int rc) {
-   if (g_zb_cuda_error) { cudaGetLastError(); return ZULTRA_CUDA_ERR_CUDA; }
+   if (g_zb_cuda_error) { cudaGetLastError(); c->broken = 1; return ZULTRA_CUDA_ERR_CUDA; }
    cudaError_t e = cudaGetLastError();
-   if (e != cudaSuccess) { fprintf(stderr, "zultra-b200: CUDA error %s\n", cudaGetErrorString(e)); return ZULTRA_CUDA_ERR_CUDA; }
-   (void)c;
+   if (e != cudaSuccess) { fprintf(stderr, "zultra-b200: CUDA error %s\n", cudaGetErrorString(e)); c->broken = 1; return ZULTRA_CUDA_ERR_CUDA; }
+   if (rc == ZULTRA_CUDA_ERR_CUDA) c->broken = 1;
    return rc;
 }
 static void fill_counters(zultra_cuda_ctx_t *c, long long launches0) {
@@ -54,7 +67,9 @@ int zultra_cuda_device_count(void) {
 int zultra_cuda_ctx_create(zultra_cuda_ctx_t **pp, int device) {
    if (!pp) return ZULTRA_CUDA_ERR_ARG;
    *pp = 0;
+   zb_trace("ctx_create: begin");
    int n = zultra_cuda_device_count();
+   zb_trace("ctx_create: device count known (driver initialised)");
    if (n <= 0) return ZULTRA_CUDA_ERR_NODEVICE;
    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
    if (device >= n) return ZULTRA_CUDA_ERR_NODEVICE;
@@ -64,6 +79,7 @@ int zultra_cuda_ctx_create(zultra_cuda_ctx_t **pp, int device) {
    c->device = device;
    memset(c->ms, 0, sizeof(c->ms)); memset(c->counters, 0, sizeof(c->counters));
    if (cudaStreamCreateWithFlags(&c->pipe.st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ZULTRA_CUDA_ERR_CUDA; }
+   zb_trace("ctx_create: stream created (primary context up)");
    {  /* tuning knobs (never change the output) */
       const char *e;
       if ((e = getenv("ZULTRA_CUDA_PARSE_CD")) && atoi(e) >= 512) c->pipe.parse_cd = atoi(e);
@@ -82,6 +98,8 @@ void zultra_cuda_ctx_destroy(zultra_cuda_ctx_t *c) {
    if (!c) return;
    cudaSetDevice(c->device);
    for (size_t i = 0; i < c->lanes.size(); i++) zultra_cuda_ctx_destroy(c->lanes[i]);
+   for (size_t i = 0; i < c->peers.size(); i++) zultra_cuda_ctx_destroy(c->peers[i]);
+   cudaSetDevice(c->device);
    c->lane_out.release();
    c->pipe.release_all();
    cudaStreamDestroy(c->pipe.st);
@@ -145,6 +163,7 @@ static int run_lanes(zultra_cuda_ctx_t *c, int nl, const uint8_t *host_hist, int
       zultra_cuda_ctx_t *q = k == 0 ? c : c->lanes[k];
       Lane &l = L[k];
       if (l.hi <= l.lo) return;
+      if (k) g_zb_cuda_error = 0;      /* the error flag is per host thread: a lane's failure comes back through l.rc */
       cudaSetDevice(c->device);
       const uint32_t h = k == 0 ? (uint32_t)hist_size : (uint32_t)ZB_HISTORY;
       ZbStreamIn s;
@@ -157,6 +176,7 @@ static int run_lanes(zultra_cuda_ctx_t *c, int nl, const uint8_t *host_hist, int
       q->pipe.stat_redo = 0;
       std::vector<ZbStreamRes> res;
       l.rc = zb_run_batch(q->pipe, &s, 1, block, q->out, res, l.o);
+      if (zb_failed()) l.rc = -3;
       if (l.rc == 0) l.ck = res[0].checksum;
    };
    {
@@ -187,8 +207,10 @@ static int run_lanes(zultra_cuda_ctx_t *c, int nl, const uint8_t *host_hist, int
    auto emit = [&](int k) {
       zultra_cuda_ctx_t *q = k == 0 ? c : c->lanes[k];
       if (L[k].hi <= L[k].lo) return;
+      if (k) g_zb_cuda_error = 0;
       cudaSetDevice(c->device);
       L[k].rc = zb_finish_lane(q->pipe, L[k].abs_bits, c->lane_out.p, &L[k].end_bits);
+      if (zb_failed()) L[k].rc = -3;
    };
    {
       std::vector<std::thread> th;
@@ -220,6 +242,149 @@ static int run_lanes(zultra_cuda_ctx_t *c, int nl, const uint8_t *host_hist, int
    return 0;
 }
 
+/* ============================================================ several GPUs behind one call ============================================================
+ * A call = consecutive max-blocks of one stream (host memory in, host memory out).  The range is cut into CHUNKS of a few
+ * max-blocks, dealt round-robin to the devices: every device gets a sample of the whole range, so a stream whose cost per
+ * byte varies along its length (text next to binaries next to byte runs) still loads all devices evenly, without a cost
+ * model.  A chunk is a shard in the sense of zultra_cuda_shard_prepare: its own 32 KiB of preceding input as history,
+ * everything up to the sub-block sizes independent of the entering bit phase.  Per device ONE pipeline pass over all its
+ * chunks (they are streams of one batch), driven by its own host thread:
+ *   1. DMA of every chunk [history | bytes] straight from the caller's buffer, pipeline up to the sub-block sizes,
+ *      an 8-entry phase map and a checksum per chunk;
+ *   2. (host) the maps compose left to right into every chunk's entering phase and absolute bit offset - the bit-offset
+ *      scan of the stitch (same algebra as run_lanes; tests/test_cpu_shards.py checks it against the reference);
+ *   3. emission for the true phases, then every chunk's bytes go by DMA from its device straight to their byte offset in
+ *      the caller's output buffer; the byte a chunk shares with its predecessor is OR-merged on the host.
+ * No device-to-device traffic at all: the shard bitstreams meet in host memory, where the caller wants them.
+ * Replaces the per-block loop of libzultra.c:269-438 across devices. */
+static zultra_cuda_ctx_t *multi_dev_ctx(zultra_cuda_ctx_t *c, int k) {
+   if (k == 0) return c;
+   int count = zultra_cuda_device_count();
+   while ((int)c->peers.size() < k) {
+      zultra_cuda_ctx_t *q = 0;
+      const int dev = (c->device + (int)c->peers.size() + 1) % count;
+      if (zultra_cuda_ctx_create(&q, dev)) return 0;
+      q->pipe.parse_cd = c->pipe.parse_cd; q->pipe.parse_wu = c->pipe.parse_wu; q->pipe.mf_ts_min = c->pipe.mf_ts_min; q->pipe.mf_ts_mul = c->pipe.mf_ts_mul; q->tile = c->tile;
+      c->peers.push_back(q);
+   }
+   return c->peers[k - 1];
+}
+
+static size_t multi_chunk_blocks(size_t nblocks, int ndev) {
+   static const int forced = getenv("ZULTRA_CUDA_CHUNK_BLOCKS") ? atoi(getenv("ZULTRA_CUDA_CHUNK_BLOCKS")) : 0;
+   if (forced > 0) return (size_t)forced;
+   size_t g = nblocks / ((size_t)ndev * 4);
+   return g < 1 ? 1 : (g > 8 ? 8 : g);
+}
+
+static int run_multi(zultra_cuda_ctx_t *c, int ndev, const uint8_t *host_hist, int hist_size, const uint8_t *host_in, size_t n, unsigned block, int finalize,
+                     unsigned in_bits, unsigned flags, unsigned *checksum, uint8_t *host_out, size_t out_cap, unsigned long long *out_bits) {
+   const long long l0 = g_zb_launches;
+   const int kind = (flags & 2) ? 2 : ((flags & 1) ? 1 : 0);
+   const size_t nblocks = (n + block - 1) / block, G = multi_chunk_blocks(nblocks, ndev), nchunk = (nblocks + G - 1) / G;
+   struct Chunk { size_t lo, hi; int dev, idx; unsigned ck; unsigned long long map[8], abs_bits, bits; size_t out_off; uint32_t first_word; };
+   struct Dev { zultra_cuda_ctx_t *q; std::vector<int> chunks; int rc; ZbRunOpts o; };
+   std::vector<Chunk> ch(nchunk);
+   std::vector<Dev> D(ndev);
+   for (int k = 0; k < ndev; k++) { D[k].q = multi_dev_ctx(c, k); D[k].rc = 0; if (!D[k].q) return ZULTRA_CUDA_ERR_CUDA; }
+   for (size_t j = 0; j < nchunk; j++) {
+      ch[j].lo = j * G * block; ch[j].hi = std::min(n, (j + 1) * G * block); ch[j].dev = (int)(j % ndev); ch[j].idx = (int)D[ch[j].dev].chunks.size();
+      D[ch[j].dev].chunks.push_back((int)j);
+   }
+   ZbTimer tot;
+   auto prepare = [&](int k) {
+      Dev &d = D[k];
+      if (d.chunks.empty()) return;
+      g_zb_cuda_error = 0;
+      if (cudaSetDevice(d.q->device) != cudaSuccess) { d.rc = -3; return; }
+      std::vector<ZbStreamIn> s(d.chunks.size());
+      for (size_t i = 0; i < d.chunks.size(); i++) {
+         const Chunk &x = ch[d.chunks[i]];
+         const bool first = d.chunks[i] == 0;
+         const uint32_t h = first ? (uint32_t)hist_size : (uint32_t)ZB_HISTORY;
+         ZbStreamIn t = {host_in + x.lo, x.hi - x.lo, first ? host_hist : host_in + x.lo - h, h, (finalize && x.hi == n) ? 1 : 0, 0,
+                         kind == 1 ? 1u : 0u /* every chunk from the initial value; folded into the running checksum below */, 0};
+         s[i] = t;
+      }
+      d.o = ZbRunOpts();
+      d.o.phase = 1; d.o.checksum_kind = kind; d.o.tile_main = c->tile; d.o.direct_h2d = 1;
+      d.q->pipe.counters.need(64);
+      zb_memset(d.q->pipe.st, d.q->pipe.counters.p, 0, 64 * 4);
+      d.q->pipe.stat_redo = 0;
+      std::vector<ZbStreamRes> res;
+      d.rc = zb_run_batch(d.q->pipe, s.data(), (int)s.size(), block, d.q->out, res, d.o);
+      if (zb_failed()) d.rc = -3;
+      if (d.rc) { d.q->broken = 1; return; }
+      for (size_t i = 0; i < d.chunks.size(); i++) {
+         Chunk &x = ch[d.chunks[i]];
+         memcpy(x.map, d.o.phase_maps.data() + 8 * i, sizeof(x.map));
+         x.ck = res[i].checksum;
+      }
+   };
+   {
+      std::vector<std::thread> th;
+      for (int k = 1; k < ndev; k++) th.emplace_back(prepare, k);
+      prepare(0);
+      for (size_t i = 0; i < th.size(); i++) th[i].join();
+   }
+   for (int k = 0; k < ndev; k++) if (D[k].rc) return ZULTRA_CUDA_ERR_CUDA;
+   /* the bit-offset scan */
+   unsigned long long pos = in_bits;
+   for (size_t j = 0; j < nchunk; j++) { ch[j].abs_bits = pos; pos += ch[j].map[pos & 7] - (pos & 7); }
+   const size_t nb_total = (size_t)((pos + 7) / 8);
+   if (nb_total > out_cap) return ZULTRA_CUDA_ERR_DST;
+   const float t_prep = tot.lap();
+   auto emit = [&](int k) {
+      Dev &d = D[k];
+      if (d.chunks.empty()) return;
+      g_zb_cuda_error = 0;
+      if (cudaSetDevice(d.q->device) != cudaSuccess) { d.rc = -3; return; }
+      const size_t m = d.chunks.size();
+      std::vector<unsigned> ib(m); std::vector<size_t> off(m); std::vector<unsigned long long> bits(m);
+      for (size_t i = 0; i < m; i++) ib[i] = (unsigned)(ch[d.chunks[i]].abs_bits & 7);
+      d.rc = zb_finish_chunks(d.q->pipe, ib.data(), off.data(), bits.data());
+      if (d.rc) { d.q->broken = 1; return; }
+      const uint8_t *ob = (const uint8_t *)d.q->pipe.out.p;
+      for (size_t i = 0; i < m; i++) {
+         Chunk &x = ch[d.chunks[i]];
+         x.bits = bits[i]; x.out_off = off[i];
+         const size_t nb = (size_t)((bits[i] + 7) / 8), at = (size_t)(x.abs_bits >> 3);
+         /* a chunk entered at phase p != 0 shares its first byte with its predecessor: that byte is merged on the host below
+            (the very first chunk's pending bits belong to the caller, its low bits are zero here) */
+         const size_t skip = (ib[i] != 0 && d.chunks[i] != 0) ? 1 : 0;
+         if (skip) zb_d2h(d.q->pipe.st, &x.first_word, ob + off[i], 4);
+         if (nb > skip) zb_d2h(d.q->pipe.st, host_out + at + skip, ob + off[i] + skip, nb - skip);
+      }
+      zb_sync(d.q->pipe.st);
+      if (zb_failed()) { d.rc = -3; d.q->broken = 1; }
+   };
+   {
+      std::vector<std::thread> th;
+      for (int k = 1; k < ndev; k++) th.emplace_back(emit, k);
+      emit(0);
+      for (size_t i = 0; i < th.size(); i++) th[i].join();
+   }
+   for (int k = 0; k < ndev; k++) if (D[k].rc) return ZULTRA_CUDA_ERR_CUDA;
+   for (size_t j = 1; j < nchunk; j++) if (ch[j].abs_bits & 7) host_out[ch[j].abs_bits >> 3] |= (uint8_t)(ch[j].first_word & 0xffu);
+   *out_bits = pos;
+   if (checksum) {
+      unsigned ck = *checksum;
+      for (size_t j = 0; j < nchunk; j++) ck = zultra_cuda_checksum_combine(flags, ck, ch[j].ck, ch[j].hi - ch[j].lo);
+      *checksum = ck;
+   }
+   memset(c->ms, 0, sizeof(c->ms)); memset(c->counters, 0, sizeof(c->counters));
+   for (int k = 0; k < ndev; k++) {
+      if (D[k].chunks.empty()) continue;
+      ZbPipe &p = D[k].q->pipe;
+      for (int i = 0; i < 7; i++) c->ms[i] = std::max(c->ms[i], D[k].o.ms[i]);
+      c->counters[0] += p.nwin; c->counters[1] += p.nsub; c->counters[2] = std::max<long long>(c->counters[2], p.stat_sa_rounds);
+      c->counters[3] += p.stat_redo; c->counters[7] += p.stat_tiles;
+   }
+   c->ms[6] = tot.lap(); c->ms[7] = t_prep + c->ms[6];
+   c->counters[4] = g_zb_launches - l0; c->counters[5] = 1; c->counters[6] = ndev;
+   return 0;
+}
+
 static unsigned clamp_block(unsigned b) {
    if (!b) b = 1048576;
    if (b < 32768) b = 32768;
@@ -233,6 +398,13 @@ int zultra_cuda_compress_blocks(zultra_cuda_ctx_t *c, const unsigned char *hist,
    int rc = ctx_enter(c);
    if (rc) return rc;
    if (!in || !out || !out_bits || in_bits > 7 || hist_size < 0 || hist_size > ZB_HISTORY) return ZULTRA_CUDA_ERR_ARG;
+   if (c->ndev > 1 && n > clamp_block(block)) {      /* at least two max-blocks: spread them over the context's devices */
+      const size_t nblocks = (n + clamp_block(block) - 1) / clamp_block(block);
+      const int nd = (int)std::min<size_t>((size_t)c->ndev, nblocks);
+      rc = run_multi(c, nd, hist, hist_size, in, n, clamp_block(block), finalize, in_bits, flags, checksum, out, out_cap, out_bits);
+      cudaSetDevice(c->device);
+      return ctx_leave(c, rc);
+   }
    {
       const int nl = lanes_wanted(c, n, clamp_block(block));
       if (nl > 1) return ctx_leave(c, run_lanes(c, nl, hist, hist_size, in, 0, n, clamp_block(block), finalize, in_bits, flags, checksum, out, 0, out_cap, out_bits));
@@ -242,7 +414,9 @@ int zultra_cuda_compress_blocks(zultra_cuda_ctx_t *c, const unsigned char *hist,
    o.checksum_kind = (flags & 2) ? 2 : ((flags & 1) ? 1 : 0);
    o.host_out = out; o.host_out_cap = out_cap;
    std::vector<ZbStreamRes> res;
+   zb_trace("compress_blocks: begin");
    rc = run_one(c, s, clamp_block(block), o, res);
+   zb_trace("compress_blocks: end", c->ms);
    if (rc == 0) { *out_bits = res[0].total_bits; if (checksum) *checksum = res[0].checksum; }
    else rc = rc == -2 ? ZULTRA_CUDA_ERR_DST : ZULTRA_CUDA_ERR_CUDA;
    return ctx_leave(c, rc);
@@ -309,6 +483,102 @@ int zultra_cuda_compress_blocks_device(zultra_cuda_ctx_t *c, const void *dev_in,
    return ctx_leave(c, rc);
 }
 
+int zultra_cuda_ctx_set_devices(zultra_cuda_ctx_t *c, int n) {
+   if (!c) return ZULTRA_CUDA_ERR_ARG;
+   const int count = zultra_cuda_device_count();
+   if (n < 1) n = 1;
+   if (n > count) n = count;
+   c->ndev = n;
+   return n;
+}
+
+/* ---- several chunks of one device-resident buffer per call (one process per GPU: bench.py under torchrun) ---- */
+int zultra_cuda_chunks_prepare(zultra_cuda_ctx_t *c, const void *dev_in, int nchunks, const size_t *chunk_off, const int *chunk_hist, const size_t *chunk_len,
+                               const int *chunk_final, unsigned int block, unsigned int flags, unsigned int *cks, unsigned long long *maps8) {
+   int rc = ctx_enter(c);
+   if (rc) return rc;
+   if (!dev_in || nchunks <= 0 || !chunk_off || !chunk_hist || !chunk_len || !maps8) return ZULTRA_CUDA_ERR_ARG;
+   const int kind = (flags & 2) ? 2 : ((flags & 1) ? 1 : 0);
+   std::vector<ZbStreamIn> s((size_t)nchunks);
+   for (int i = 0; i < nchunks; i++) {
+      if (chunk_hist[i] < 0 || chunk_hist[i] > ZB_HISTORY || !chunk_len[i]) return ZULTRA_CUDA_ERR_ARG;
+      ZbStreamIn t = {0, chunk_len[i], 0, (uint32_t)chunk_hist[i], chunk_final ? chunk_final[i] : 0, 0, kind == 1 ? 1u : 0u, chunk_off[i]};
+      s[i] = t;
+   }
+   const long long l0 = g_zb_launches;
+   ZbRunOpts o;
+   o.dev_in = (const uint8_t *)dev_in; o.dev_offsets = 1; o.phase = 1; o.checksum_kind = kind; o.tile_main = c->tile;
+   c->pipe.counters.need(64);
+   zb_memset(c->pipe.st, c->pipe.counters.p, 0, 64 * 4);
+   c->pipe.stat_redo = 0;
+   std::vector<ZbStreamRes> res;
+   rc = zb_run_batch(c->pipe, s.data(), nchunks, clamp_block(block), c->out, res, o);
+   memcpy(c->ms, o.ms, sizeof(c->ms));
+   fill_counters(c, l0);
+   if (rc == 0) {
+      memcpy(maps8, o.phase_maps.data(), sizeof(unsigned long long) * 8 * (size_t)nchunks);
+      if (cks) for (int i = 0; i < nchunks; i++) cks[i] = res[i].checksum;
+      c->nchunks = nchunks;
+   }
+   return ctx_leave(c, rc ? ZULTRA_CUDA_ERR_CUDA : 0);
+}
+
+int zultra_cuda_chunks_emit(zultra_cuda_ctx_t *c, const unsigned int *in_bits, void **dev_out, size_t *out_off, unsigned long long *out_bits) {
+   int rc = ctx_enter(c);
+   if (rc) return rc;
+   if (!in_bits || !dev_out || !out_off || !out_bits || c->nchunks <= 0 || (int)c->pipe.plan.size() != c->nchunks) return ZULTRA_CUDA_ERR_ARG;
+   const long long l0 = g_zb_launches;
+   rc = zb_finish_chunks(c->pipe, in_bits, out_off, out_bits);
+   *dev_out = c->pipe.out.p;
+   c->counters[4] += g_zb_launches - l0;
+   return ctx_leave(c, rc ? ZULTRA_CUDA_ERR_CUDA : 0);
+}
+
+/* The stitch on one device: part i = src[i][0 .. ceil((phase_i + nbits_i) / 8)) bytes whose first bit sits at phase_i = dst_bit[i] & 7 of its
+   first byte (low bits zero) goes to byte dst_bit[i] >> 3 of dst; bytes two parts share are OR-merged.  dst must be zero where parts
+   meet: the caller clears it (cudaMemsetAsync) before the call.  One thread per aligned 4-byte word of the destination span of a part. */
+__global__ void zb_stitch_k(uint32_t *dst, int nparts, const uint8_t *const *src, const unsigned long long *dst_bit, const unsigned long long *nbits, const unsigned long long *word_base) {
+   const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+   int lo = 0, hi = nparts - 1;
+   if (g >= word_base[nparts]) return;
+   while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (word_base[mid] <= g) lo = mid; else hi = mid - 1; }
+   const unsigned long long b0 = dst_bit[lo] >> 3;                                   /* first destination byte of the part */
+   const unsigned long long nb = ((dst_bit[lo] & 7) + nbits[lo] + 7) >> 3;           /* bytes of the part */
+   const unsigned long long w = (b0 >> 2) + (g - word_base[lo]);                     /* destination word */
+   const long long s0 = (long long)(w << 2) - (long long)b0;                         /* source byte that lands in byte 0 of the word */
+   const uint8_t *sp = src[lo];
+   uint32_t v = 0;
+#pragma unroll
+   for (int k = 0; k < 4; k++) { const long long q = s0 + k; if (q >= 0 && (unsigned long long)q < nb) v |= (uint32_t)sp[q] << (8 * k); }
+   if (!v) return;
+   const bool edge = s0 < 1 || (unsigned long long)(s0 + 4) >= nb;                   /* may share bytes with a neighbouring part */
+   if (edge) atomicOr(dst + w, v); else dst[w] = v;
+}
+
+int zultra_cuda_stitch_device(zultra_cuda_ctx_t *c, void *dev_dst, int nparts, const void *const *dev_src, const unsigned long long *dst_bit, const unsigned long long *nbits) {
+   int rc = ctx_enter(c);
+   if (rc) return rc;
+   if (!dev_dst || nparts <= 0 || !dev_src || !dst_bit || !nbits || ((uintptr_t)dev_dst & 3)) return ZULTRA_CUDA_ERR_ARG;
+   std::vector<unsigned long long> h((size_t)4 * nparts + 1);
+   unsigned long long words = 0;
+   for (int i = 0; i < nparts; i++) {
+      const unsigned long long b0 = dst_bit[i] >> 3, nb = ((dst_bit[i] & 7) + nbits[i] + 7) >> 3;
+      h[i] = (unsigned long long)(uintptr_t)dev_src[i]; h[nparts + i] = dst_bit[i]; h[2 * nparts + i] = nbits[i]; h[3 * nparts + i] = words;
+      words += nb ? ((b0 + nb + 3) >> 2) - (b0 >> 2) : 0;
+   }
+   h[4 * (size_t)nparts] = words;
+   c->pipe.ck_rng.need(h.size());
+   if (zb_failed()) return ctx_leave(c, ZULTRA_CUDA_ERR_CUDA);
+   zb_h2d(c->pipe.st, c->pipe.ck_rng.p, h.data(), h.size() * 8);
+   const unsigned long long *d = (const unsigned long long *)c->pipe.ck_rng.p;
+   if (words) {
+      zb_stitch_k<<<(unsigned)((words + 255) / 256), 256, 0, c->pipe.st>>>((uint32_t *)dev_dst, nparts, (const uint8_t *const *)d, d + nparts, d + 2 * nparts, d + 3 * nparts);
+      zb_count_launch(1);
+   }
+   zb_sync(c->pipe.st);
+   return ctx_leave(c, 0);
+}
+
 /* ---- context pool: contexts (device buffers, stream) are expensive to build; the libzultra front end borrows them ---- */
 static std::mutex g_pool_mu;
 static std::vector<zultra_cuda_ctx_t *> g_pool;
@@ -325,8 +595,9 @@ int zultra_cuda_ctx_acquire(zultra_cuda_ctx_t **pp, int device) {
 }
 void zultra_cuda_ctx_release(zultra_cuda_ctx_t *c) {
    if (!c) return;
+   if (c->broken) { zultra_cuda_ctx_destroy(c); return; }
    std::lock_guard<std::mutex> g(g_pool_mu);
-   if (g_pool.size() < 4) g_pool.push_back(c); else zultra_cuda_ctx_destroy(c);
+   if (g_pool.size() < 16) g_pool.push_back(c); else zultra_cuda_ctx_destroy(c);
 }
 void zultra_cuda_release_cached(void) {
    std::lock_guard<std::mutex> g(g_pool_mu);
@@ -449,6 +720,7 @@ int zultra_cuda_block_stages(zultra_cuda_ctx_t *c, const unsigned char *win, int
    return ctx_leave(c, (int)d.sub.size());
 }
 
+long long zultra_cuda_launch_count(void) { return __atomic_load_n(&g_zb_launches, __ATOMIC_RELAXED); }
 int zultra_cuda_last_timings(zultra_cuda_ctx_t *c, float *ms) { if (!c) return ZULTRA_CUDA_ERR_ARG; memcpy(ms, c->ms, sizeof(c->ms)); return 0; }
 int zultra_cuda_last_counters(zultra_cuda_ctx_t *c, long long *v) { if (!c) return ZULTRA_CUDA_ERR_ARG; memcpy(v, c->counters, sizeof(c->counters)); return 0; }
 

@@ -35,8 +35,6 @@
 #define ZB_MAX_SPLITS 64
 #define ZB_POS_BITS 22
 #define ZB_POS_MASK 0x3fffffu
-#define ZB_LCP_MASK 0x7fc00000u
-#define ZB_VISITED 0x80000000u
 
 typedef struct { uint16_t length, offset; } zb_match_t;
 
@@ -402,101 +400,7 @@ struct ZbBitSink {
    ZB_HD void finish() { if (nacc > 0) orword(wpos, (uint32_t)acc, true); }
 };
 
-/* ---- match finder: lcp-interval tree over one tile, wimlib "lcpit" scheme (matchfinder.c:98-234) ----
- *
- * A tile is a contiguous range of window positions [lo, m1); positions [lo, m0) are look-back (they only
- * serve as match candidates), [m0, m1) get matches recorded.  iv[] comes in holding the tile's suffixes in
- * suffix-array order, one word each: (pos - lo) | clamped_lcp << 22, where lcp is the LCP with the previous
- * suffix OF THE TILE (min-reduced over the skipped window ranks).  pd[] is scratch of the same size.
- *
- * zb_mf_build is the stack scan of matchfinder.c:98-155 with one addition: the state the reference reaches
- * by calling zultra_skip_matches over the look-back positions (matchfinder.c:243-252) is written directly.
- * For every interval, the newest look-back position below it is kept while its children are closed; an
- * interval that has one is stored as visited-by-that-position, and every other look-back position gets, in
- * pd[], the deepest interval at which a newer look-back position supersedes it.  That is exactly the state
- * the lazy walker maintains ("fully caught up"), so the walk over [m0, m1) continues from it unchanged.
- */
-struct ZbMfStack { uint32_t ref[260]; int32_t last[260]; };
-
-ZB_HD void zb_mf_merge(ZbMfStack &st, int sp, int32_t q, uint32_t *pd) {
-   if (st.last[sp] < 0) st.last[sp] = q;
-   else if (q > st.last[sp]) { pd[st.last[sp]] = st.ref[sp]; st.last[sp] = q; }
-   else pd[q] = st.ref[sp];
-}
-ZB_HD void zb_mf_leaf(ZbMfStack &st, int sp, uint32_t p, uint32_t nlook, uint32_t *pd) {
-   if (p < nlook) zb_mf_merge(st, sp, (int32_t)p, pd);
-   else pd[p] = st.ref[sp];
-}
-
-ZB_HDN void zb_mf_build(uint32_t *iv, uint32_t *pd, int n, uint32_t nlook, ZbMfStack &st) {
-   if (n <= 0) return;
-   int sp = 0;
-   uint32_t next_id = 1;
-   uint32_t prev_pos = iv[0] & ZB_POS_MASK;
-   st.ref[0] = 0; st.last[0] = -1;
-   iv[0] = 0;
-   for (int r = 1; r < n; r++) {
-      const uint32_t w = iv[r];
-      const uint32_t next_pos = w & ZB_POS_MASK, next_lcp = w & ZB_LCP_MASK;
-      const uint32_t top_lcp = st.ref[sp] & ZB_LCP_MASK;
-      if (next_lcp == top_lcp) {
-         zb_mf_leaf(st, sp, prev_pos, nlook, pd);
-      } else if (next_lcp > top_lcp) {
-         sp++; st.ref[sp] = next_lcp | next_id++; st.last[sp] = -1;
-         zb_mf_leaf(st, sp, prev_pos, nlook, pd);
-      } else {
-         zb_mf_leaf(st, sp, prev_pos, nlook, pd);
-         for (;;) {
-            const int32_t clast = st.last[sp];
-            const uint32_t cid = st.ref[sp] & ZB_POS_MASK;
-            sp--;
-            const uint32_t sup_lcp = st.ref[sp] & ZB_LCP_MASK;
-            bool done = true;
-            if (next_lcp > sup_lcp) { sp++; st.ref[sp] = next_lcp | next_id++; st.last[sp] = -1; }
-            else if (next_lcp < sup_lcp) done = false;
-            iv[cid] = clast >= 0 ? (ZB_VISITED | (uint32_t)clast) : st.ref[sp];
-            if (clast >= 0) zb_mf_merge(st, sp, clast, pd);
-            if (done) break;
-         }
-      }
-      prev_pos = next_pos;
-   }
-   zb_mf_leaf(st, sp, prev_pos, nlook, pd);
-   while (sp > 0) {
-      const int32_t clast = st.last[sp];
-      const uint32_t cid = st.ref[sp] & ZB_POS_MASK;
-      sp--;
-      iv[cid] = clast >= 0 ? (ZB_VISITED | (uint32_t)clast) : st.ref[sp];
-      if (clast >= 0) zb_mf_merge(st, sp, clast, pd);
-   }
-   if (st.last[0] >= 0) pd[st.last[0]] = 0;
-}
-
-/* zultra_find_matches_at (matchfinder.c:171-234) for tile position i; out gets <= 8 {lcp, offset} longest first */
-ZB_HD int zb_mf_walk(uint32_t *iv, uint32_t *pd, uint32_t i, zb_match_t *out) {
-   uint32_t ref = pd[i], sup;
-   pd[i] = 0;
-   while ((sup = iv[ref & ZB_POS_MASK]) & ZB_LCP_MASK) { iv[ref & ZB_POS_MASK] = i | ZB_VISITED; ref = sup; }
-   if (sup == 0) {
-      if (ref) iv[ref & ZB_POS_MASK] = i | ZB_VISITED;
-      return 0;
-   }
-   uint32_t mp = sup & 0x7fffffffu;
-   int n = 0;
-   for (;;) {
-      while ((sup = pd[mp]) > ref) mp = iv[sup & ZB_POS_MASK] & 0x7fffffffu;
-      iv[ref & ZB_POS_MASK] = i | ZB_VISITED;
-      pd[mp] = ref;
-      if (n < ZB_NMATCH) {
-         uint32_t off = i - mp;
-         if (off <= ZB_MAX_OFFSET) { out[n].length = (uint16_t)(ref >> ZB_POS_BITS); out[n].offset = (uint16_t)off; n++; }
-      }
-      if (sup == 0) break;
-      ref = sup;
-      mp = iv[ref & ZB_POS_MASK] & 0x7fffffffu;
-   }
-   return n;
-}
+/* ---- match finder ---- */
 
 /*
  * Match list of one main position by direct scan of the tile's suffix array - no interval tree, no mutation, so every

@@ -15,6 +15,7 @@ struct ZbStreamIn {
    int finalize;                           /* 1: the last window is the end of the stream (BFINAL) */
    uint32_t in_bits;                       /* bits already pending in the current output byte (0..7) */
    uint32_t checksum;                      /* running checksum in */
+   size_t dev_off;                         /* with ZbRunOpts::dev_in and dev_offsets: where this stream's [history | data] starts in the resident buffer */
 };
 struct ZbStreamRes { uint64_t total_bits; size_t out_off; int err; uint32_t checksum; };
 
@@ -27,8 +28,12 @@ struct ZbRunOpts {
    uint32_t tile_main = 0;
    int checksum_kind = 0;          /* 0 none, 1 Adler-32, 2 CRC-32 (frame.c:473) */
    const uint8_t *dev_in = 0;      /* single stream already in device memory: [hist_len history bytes | data] */
+   int dev_offsets = 0;            /* dev_in holds several streams (chunks of one resident buffer): ZbStreamIn::dev_off locates each */
+   int direct_h2d = 0;             /* several streams from host memory, each [history | data] contiguous there: one DMA per stream straight from the
+                                      caller's buffer instead of gathering them into page-locked staging first */
    int phase = 3;                  /* 1 = stop after the phase-independent part (shards), 2 = only finish, 3 = both */
    unsigned long long phase_bits[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+   std::vector<unsigned long long> phase_maps;   /* phase 1: 8 entries per stream (phase_bits = those of stream 0) */
    uint8_t *dev_out = 0; size_t dev_out_cap = 0;   /* leave the bitstream of stream 0 in device memory instead of copying back */
    uint8_t *host_out = 0; size_t host_out_cap = 0; /* single stream: copy the bitstream straight into the caller's buffer (no staging vector) */
    int want_out_ptr = 0;           /* several streams: leave the bitstreams in the pipe's page-locked buffer; res[i].out_off is relative to out_ptr */
@@ -68,10 +73,13 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
    /* copy straight from the caller's buffer when [history | data] is contiguous there; otherwise gather the streams into
       page-locked memory (several host threads: a single memcpy stream does not keep up with the DMA that follows) */
    const bool single_direct = (ns == 1 && !o.dev_in && (s[0].hist_len == 0 || s[0].hist + s[0].hist_len == s[0].data));
+   bool multi_direct = ns > 1 && !o.dev_in && o.direct_h2d;
+   for (int i = 0; i < ns && multi_direct; i++) if (s[i].hist_len && s[i].hist + s[i].hist_len != s[i].data) multi_direct = false;
    uint8_t *stage = 0;
-   if (!o.dev_in && !single_direct) {
+   if (!o.dev_in && !single_direct && !multi_direct) {
       p.hin.need(in_bytes + 16);
       stage = p.hin.p;
+      if (!stage || zb_failed()) return -3;
       std::vector<size_t> offs(ns + 1, 0);
       for (int i = 0; i < ns; i++) offs[i + 1] = offs[i] + s[i].hist_len + s[i].n;
       const int nth = in_bytes > ((size_t)8 << 20) ? 4 : 1;
@@ -99,6 +107,7 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
       memset(&so[i], 0, sizeof(ZbStreamOut));
       so[i].first_win = (uint32_t)wins.size();
       so[i].in_bits = s[i].in_bits;
+      if (o.dev_in && o.dev_offsets) off = s[i].dev_off;
       ck_off[i] = off + s[i].hist_len; ck_len[i] = s[i].n;
       size_t done = 0; uint32_t k = 0;
       while (done < s[i].n) {
@@ -120,27 +129,49 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
    for (int i = 0; i < ns; i++) res[i].checksum = s[i].checksum;
    if (wins.empty()) { out.clear(); return 0; }
    p.setup(wins, o.dev_in ? o.dev_in : (single_direct ? s[0].data - s[0].hist_len : stage), in_bytes, o.dev_in != 0);
+   if (multi_direct && !zb_failed()) {      /* setup allocated the device input (no source given): one DMA per stream */
+      size_t at = 0;
+      for (int i = 0; i < ns; i++) { zb_h2d(p.st, p.in.p + at, s[i].data - s[i].hist_len, s[i].hist_len + s[i].n); at += s[i].hist_len + s[i].n; }
+   }
    zb_sync(p.st); o.ms[0] = tm.lap(); o.t_abs[0] = zb_now_ms();
+   if (zb_failed()) return -3;      /* allocation or copy failed: nothing has been launched on missing buffers */
    p.stage_sa();
    zb_sync(p.st); o.ms[1] = tm.lap(); o.t_abs[1] = zb_now_ms();
+   if (zb_failed()) return -3;
    if (o.stop_after >= 2) {
       p.stage_match(o.tile_main ? o.tile_main : zb_pick_tile(total_block));
       zb_sync(p.st); o.ms[2] = tm.lap(); o.t_abs[2] = zb_now_ms();
+      if (zb_failed()) return -3;
    }
    if (o.stop_after >= 3) {
       p.stage_greedy();
+      if (zb_failed()) return -3;
       p.stage_split();
       zb_sync(p.st); o.ms[3] = tm.lap(); o.t_abs[3] = zb_now_ms();
+      if (zb_failed()) return -3;
       p.stage_parse();
       zb_sync(p.st); o.ms[4] = tm.lap(); o.t_abs[4] = zb_now_ms();
+      if (zb_failed()) return -3;
       p.stage_emit_prepare();
-      if (o.phase == 1) {   /* shard: report the size for every entering phase and wait for zb_finish_shard */
-         if (o.checksum_kind) { std::vector<uint32_t> sums; p.stage_checksum(o.checksum_kind, ck_off, ck_len, sums, s[0].checksum); res[0].checksum = sums[0]; }
-         p.phase_map(0, (uint32_t)wins.size(), o.phase_bits);
+      if (zb_failed()) return -3;
+      if (o.phase == 1) {   /* shard(s): report the size for every entering phase and wait for zb_finish_shard / zb_finish_chunks */
+         if (o.checksum_kind) {
+            std::vector<uint32_t> sums;
+            if (ns == 1) { p.stage_checksum(o.checksum_kind, ck_off, ck_len, sums, s[0].checksum); res[0].checksum = sums[0]; }
+            else {      /* every stream from the initial value; the caller folds them with zultra_cuda_checksum_combine */
+               p.stage_checksum(o.checksum_kind, ck_off, ck_len, sums, 0);
+               for (int i = 0; i < ns; i++) res[i].checksum = sums[i];
+            }
+         }
+         p.plan = so;
+         o.phase_maps.assign((size_t)ns * 8, 0);
+         p.phase_maps(so, o.phase_maps.data());
+         memcpy(o.phase_bits, o.phase_maps.data(), sizeof(o.phase_bits));
          zb_sync(p.st); o.ms[5] = tm.lap(); o.ms[7] = tot.lap(); o.t_abs[5] = zb_now_ms();
-         return 0;
+         return zb_failed() ? -3 : 0;
       }
       p.stage_emit_finish(so);
+      if (zb_failed()) return -3;
       if (o.checksum_kind) {
          std::vector<uint32_t> sums;
          if (ns == 1) { p.stage_checksum(o.checksum_kind, ck_off, ck_len, sums, s[0].checksum); res[0].checksum = sums[0]; }
@@ -170,6 +201,7 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
             out.resize(ob);
          } else {
             p.hout.need(total_words * 4 + 16);
+            if (!p.hout.p || zb_failed()) return -3;
             zb_d2h(p.st, p.hout.p, p.out.p, total_words * 4);
             zb_sync(p.st);
             if (o.want_out_ptr) {   /* the caller copies each stream out of the page-locked buffer itself */
@@ -211,6 +243,17 @@ static inline int zb_finish_shard(ZbPipe &p, uint32_t in_bits, uint8_t *dev_out,
    zb_d2d(p.st, dev_out, p.out.p + p.h_sout[0].out_word_off, nb);
    zb_sync(p.st);
    *total_bits = p.h_sout[0].total_bits;
+   return 0;
+}
+/* second half for several chunks prepared in one call: in_bits[i] = entering phase of chunk i; the bitstreams stay in the
+   pipe's output buffer, chunk i at byte offset out_off[i] (word aligned), bits[i] = its bits including the entering ones */
+static inline int zb_finish_chunks(ZbPipe &p, const unsigned *in_bits, size_t *out_off, unsigned long long *bits) {
+   std::vector<ZbStreamOut> so = p.plan;
+   for (size_t i = 0; i < so.size(); i++) so[i].in_bits = in_bits[i];
+   p.stage_emit_finish(so);
+   zb_sync(p.st);
+   if (zb_failed()) return -3;
+   for (size_t i = 0; i < so.size(); i++) { out_off[i] = (size_t)p.h_sout[i].out_word_off * 4; bits[i] = p.h_sout[i].total_bits; }
    return 0;
 }
 /* lane of a stream that shares one output buffer with the other lanes: abs_bits = absolute bit offset of the lane's first

@@ -153,7 +153,8 @@ struct ZbPipe {
    /* stitch scan for the entering phase, then emission.  ext_words != 0: write into that zeroed word buffer, every stream's
       in_bits being its ABSOLUTE bit offset there (lanes of one stream sharing one output, zb_capi.cu) */
    void stage_emit_finish(const std::vector<ZbStreamOut> &streams, uint32_t *ext_words = 0);
-   void phase_map(uint32_t first_win, uint32_t nwin, unsigned long long bits_out[8]);   /* total bits for each entering phase 0..7 */
+   void phase_maps(const std::vector<ZbStreamOut> &streams, unsigned long long *bits_out);   /* per stream: total bits for each entering phase 0..7 */
+   std::vector<ZbStreamOut> plan;   /* streams of a prepared (phase 1) batch, for the emit call that follows */
    /* checksum partials of byte ranges of the device input: kind 1 = Adler-32, 2 = CRC-32 */
    ZbBuf<uint32_t> ck_tab, ck_part; ZbBuf<uint64_t> ck_rng; bool ck_tab_ready = false;
    void stage_checksum(int kind, const std::vector<uint64_t> &range_off, const std::vector<uint64_t> &range_len, std::vector<uint32_t> &sums, uint32_t init_first);
@@ -171,12 +172,13 @@ inline void ZbPipe::setup(const std::vector<ZbWinDesc> &wins, const uint8_t *h_i
    h_wbase.assign(nwin + 1, 0);
    for (int w = 0; w < nwin; w++) h_wbase[w + 1] = h_wbase[w] + wins[w].len;
    P = h_wbase[nwin];
-   win.need(nwin); wbase.need(nwin + 1);
+   win.need(nwin); wbase.need(nwin + 1); counters.need(64);
+   if (!in_is_device) in.need(in_bytes + 16);
+   if (zb_failed()) return;
    zb_h2d(st, win.p, h_win.data(), sizeof(ZbWinDesc) * nwin);
    zb_h2d(st, wbase.p, h_wbase.data(), 4 * (nwin + 1));
    if (in_is_device) in_ptr = h_in;
-   else { in.need(in_bytes + 16); zb_h2d(st, in.p, h_in, in_bytes); in_ptr = in.p; }
-   counters.need(64);
+   else { if (h_in) zb_h2d(st, in.p, h_in, in_bytes); in_ptr = in.p; }
 }
 
 /* ============================================================ suffix array + LCP ============================================================
@@ -190,6 +192,7 @@ inline void ZbPipe::stage_sa() {
    keyA.need(n); keyB.need(n); valA.need(n); valB.need(n); rank.need(n); sa.need(n); actA.need(n); actB.need(n); tmpA.need(n + 1); tmpB.need(n + 1);
    sa_lcp.need(n);
    scratch.need(zb_sort_scratch_words(n) + zb_scan_scratch_words(n) + 64);
+   if (zb_failed()) return;      /* fail fast: no launch ever sees a missing buffer (zb_run_batch reports the error) */
    int wb = 0; while ((1L << wb) < nwin) wb++;
    int nbytes = (64 - wb) / 8; if (nbytes > 7) nbytes = 7;
    const uint8_t *T = in_ptr; const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const int nw = nwin;
@@ -613,6 +616,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    zb_h2d(st, units.p, hu.data(), sizeof(ZbTileDesc) * nunit);
    zb_h2d(st, tiles.p, ht.data(), sizeof(ZbTileDesc) * ntile);
    match.need((size_t)P * ZB_NMATCH); glen.need(P); goff.need(P);
+   if (zb_failed()) return;
    unit_words.need((size_t)nunit * (2 * ZB_MAX_OFFSET)); unit_cnt.need(nunit);
    auto segs_for = [](size_t n) { size_t k = (n + 8191) / 8192; return (int)(k < 1 ? 1 : (k > 64 ? 64 : k)); };
    const int wave_tiles = std::min(ntile, 16384);
@@ -643,6 +647,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    const size_t smem_txt = (stride + ZB_MAX_MATCH + 7) & ~(size_t)3;
    const ZbWinDesc *wdp = win.p; const uint8_t *Tp = in_ptr;
    tile_q.need(nw_tiles);
+   if (zb_failed()) return;
    uint32_t *tq = tile_q.p;
    {  /* the limit is a per-function global: always the largest configuration, so concurrent host threads cannot undercut each other */
       const size_t smax = ((size_t)ZB_MAX_OFFSET + ZB_MF_TILE_MAX + 2) * 4 + (size_t)ZB_MF_TILE_MAX * 2;
@@ -844,11 +849,14 @@ inline void ZbPipe::stage_greedy() {
 #endif
    gentry.need(nch + 1); gtokcnt.need(nch + 1); gtokbase.need(nch + 1); tokpos.need(P);
    wtokbase.need(nwin + 1); wintbase.need(nwin + 1);
+#ifndef ZB_EMU
+   exitc.need((size_t)(nch + 1) * ZB_EXROW);
+#endif
+   if (zb_failed()) return;
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p, *gcf = gchunk_first.p; const int nw = nwin;
    uint32_t *gcw = gchunk_win.p; uint16_t *ex = exitoff.p; const uint16_t *gl = glen.p;
    uint32_t *ent = gentry.p, *tcnt = gtokcnt.p, *tbase = gtokbase.p, *tp = tokpos.p;
 #ifndef ZB_EMU
-   exitc.need((size_t)(nch + 1) * ZB_EXROW);
    if (nch > 0) {
       if (g_zb_prof_on) { zb_tag("path_sweep"); zb_prof_begin(0, st); }
       zb_sweep_k<0><<<(unsigned)((nch + ZB_SW_THREADS - 1) / ZB_SW_THREADS), ZB_SW_THREADS, 0, st>>>(nch, wd, wbs, gcf, nw, gcw, gl, 0, 0, -1, 0, exitc.p);
@@ -918,6 +926,7 @@ inline void ZbPipe::stage_greedy() {
    zb_d2h(st, h_wib.data(), wib, 4 * (nwin + 1)); zb_sync(st);
    const long nint = h_wib[nwin];
    ph.need((size_t)nint * ZB_NH);
+   if (zb_failed()) return;
    int *PH = ph.p; const uint8_t *T = in_ptr; const uint16_t *go = goff.p;
    /* per-interval histograms: row k+1 of a window = histogram of tokens [k*ZB_TOKI, (k+1)*ZB_TOKI) */
    zb_launch(st, nint, ZB_LAMBDA(long r) {
@@ -1068,6 +1077,8 @@ inline void ZbPipe::stage_split() {
    const int maxnodes = nwin * 32;
    nodesA.need(maxnodes); nodesB.need(maxnodes); nodehist.need((size_t)maxnodes * ZB_NH);
    wsplit.need((size_t)nwin * ZB_MAXSB); wnsplit.need(nwin);
+   sub.need((size_t)nwin * ZB_MAXSB); tabs.need((size_t)nwin * ZB_MAXSB); wsubcnt.need(nwin + 1); wsubbase.need(nwin + 1);
+   if (zb_failed()) return;
    zb_memset(st, wnsplit.p, 0, 4 * nwin);
    ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in_ptr, win.p};
    const ZbWinDesc *wd = win.p; const uint32_t *wtb = wtokbase.p;
@@ -1117,6 +1128,7 @@ inline void ZbPipe::stage_split() {
       int nnext = 0;
       if (nchk > 0) {
          chk_stat.need((size_t)nchk * 18); chk_flag.need(nchk); chk_delta.need(2 * (size_t)nchk); chk_node.need(nchk);
+         if (zb_failed()) return;
          uint16_t *cs = chk_stat.p; uint8_t *cf = chk_flag.p; int *cdl = chk_delta.p; uint32_t *cnode = chk_node.p;
          zb_launch(st, ncur, ZB_LAMBDA(long x) { for (uint32_t k = 0; k < cur[x].nchk; k++) cnode[cur[x].chk_base + k] = (uint32_t)x; });
          /* S2: 18-bin statistics of each check interval (blockdeflate.c:686-703) */
@@ -1221,11 +1233,9 @@ inline void ZbPipe::stage_split() {
       ncur = nnext;
    }
    /* sub-block list, in stream order */
-   sub.need((size_t)nwin * ZB_MAXSB); tabs.need((size_t)nwin * ZB_MAXSB);
    ZbSub *sb = sub.p; uint32_t *wsp = wsplit.p, *wns = wnsplit.p;
    /* per window: sort its split offsets and count its sub-blocks; exclusive sum -> first sub-block of every window; per
       window again: fill its sub-blocks (windows are independent, only the numbering runs through them) */
-   wsubcnt.need(nwin + 1); wsubbase.need(nwin + 1);
    uint32_t *wsc = wsubcnt.p, *wsbase = wsubbase.p;
    zb_launch(st, nw, ZB_LAMBDA(long w) {
       uint32_t *sp = wsp + (size_t)w * ZB_MAXSB;
@@ -1891,6 +1901,7 @@ inline void ZbPipe::stage_parse() {
    exitc.need((size_t)(npch + 1) * ZB_EXROW);
    dpfar.need((size_t)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS) * (size_t)(CD + WU + 8) * ZB_DP_THREADS + 64);   /* + 8: per-lane rows of the decoupled-lane kernel are padded to 8 steps */
 #endif
+   if (zb_failed()) return;
    uint32_t *dcs = dchunk_sub.p, *pcs = pchunk_sub.p;
    zb_launch(st, ns, ZB_LAMBDA(long x) {
       for (uint32_t k = 0; k < sb[x].ndchunk; k++) dcs[sb[x].dchunk_base + k] = (uint32_t)x;
@@ -2355,21 +2366,28 @@ inline void ZbPipe::stage_emit_prepare() {
 
 /* The stitch arithmetic of libzultra.c:327-398 on the host, for all 8 entering bit phases (multi-GPU: a shard learns its
    phase from the shards before it; everything up to here is phase independent). */
-inline void ZbPipe::phase_map(uint32_t first_win, uint32_t nw, unsigned long long bits_out[8]) {
+inline void ZbPipe::phase_maps(const std::vector<ZbStreamOut> &streams, unsigned long long *bits_out) {
    std::vector<ZbSub> hs(nsub);
    zb_d2h(st, hs.data(), sub.p, sizeof(ZbSub) * nsub); zb_sync(st);
-   for (int ph = 0; ph < 8; ph++) {
-      unsigned long long bit = (unsigned long long)ph;
-      for (int x = 0; x < nsub; x++) {
-         const ZbSub &s = hs[x];
-         if (s.win < first_win || s.win >= first_win + nw) continue;
-         const uint32_t size = s.pe - s.ps;
-         bool stored = s.body_bits < 0;
-         if (!stored) { const unsigned long long a = (bit + 3) >> 3, b = (bit + 3 + (unsigned long long)s.body_bits) >> 3; if (b - a > size) stored = true; }
-         if (!stored) bit += 3 + (unsigned long long)s.body_bits;
-         else { uint32_t rem = size; while (rem) { uint32_t n = rem > 65535 ? 65535 : rem; bit += 3; bit = (bit + 7) & ~7ull; bit += 32 + 8ull * n; rem -= n; } }
+   int x0 = 0;      /* sub-blocks are in window order and streams own consecutive windows */
+   for (size_t q = 0; q < streams.size(); q++) {
+      const uint32_t first_win = streams[q].first_win, nw = streams[q].nwin;
+      while (x0 < nsub && hs[x0].win < first_win) x0++;
+      int x1 = x0;
+      while (x1 < nsub && hs[x1].win < first_win + nw) x1++;
+      for (int ph = 0; ph < 8; ph++) {
+         unsigned long long bit = (unsigned long long)ph;
+         for (int x = x0; x < x1; x++) {
+            const ZbSub &s = hs[x];
+            const uint32_t size = s.pe - s.ps;
+            bool stored = s.body_bits < 0;
+            if (!stored) { const unsigned long long a = (bit + 3) >> 3, b = (bit + 3 + (unsigned long long)s.body_bits) >> 3; if (b - a > size) stored = true; }
+            if (!stored) bit += 3 + (unsigned long long)s.body_bits;
+            else { uint32_t rem = size; while (rem) { uint32_t n = rem > 65535 ? 65535 : rem; bit += 3; bit = (bit + 7) & ~7ull; bit += 32 + 8ull * n; rem -= n; } }
+         }
+         bits_out[8 * q + ph] = bit;
       }
-      bits_out[ph] = bit;
+      x0 = x1;
    }
 }
 
@@ -2387,6 +2405,7 @@ inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams, u
    const int nstr = (int)streams.size();
    h_sout = streams; nstream = nstr;
    sout.need(nstr);
+   if (zb_failed()) return;
    zb_h2d(st, sout.p, h_sout.data(), sizeof(ZbStreamOut) * nstr);
    ZbStreamOut *so = sout.p;
    /* sub-blocks are in window order; find each stream's first sub-block by scanning (serial, small) */
@@ -2431,6 +2450,7 @@ inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams, u
       uint64_t w = 0;
       for (int q = 0; q < nstr; q++) { h_sout[q].out_word_off = w; w += (h_sout[q].total_bits + 31) / 32 + 2; }
       out.need(w + 4);
+      if (zb_failed()) return;
       zb_memset(st, out.p, 0, (w + 4) * 4);
       zb_h2d(st, so, h_sout.data(), sizeof(ZbStreamOut) * nstr);
    }

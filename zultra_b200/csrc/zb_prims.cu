@@ -10,11 +10,12 @@
 
 void zb_cuda_fail(cudaError_t e) {
    (void)e;
-   /* no CPU fallback: a CUDA failure is fatal for the engine call; the C-ABI layer catches this flag */
-   extern int g_zb_cuda_error;
+   /* no CPU fallback: a CUDA failure is fatal for the engine call; the pipeline stops at the next stage boundary
+      (zb_failed) and the C-ABI layer reports it.  The flag belongs to the calling host thread: concurrent streams / lanes
+      cannot clear or read each other's errors. */
    g_zb_cuda_error = 1;
 }
-int g_zb_cuda_error = 0;
+thread_local int g_zb_cuda_error = 0;
 long long g_zb_launches = 0;
 
 /* ---- per-kernel timing ---- */

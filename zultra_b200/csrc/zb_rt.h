@@ -36,6 +36,7 @@ static inline unsigned zb_atomic_add(unsigned *p, unsigned v) { unsigned o = *p;
 static inline int zb_atomic_max(int *p, int v) { int o = *p; if (v > o) *p = v; return o; }
 static inline unsigned zb_atomic_or(unsigned *p, unsigned v) { unsigned o = *p; *p |= v; return o; }
 static inline int zb_sm_count() { return 148; }
+static inline bool zb_failed() { return false; }
 #else
 /* ---------------- CUDA ---------------- */
 #include <cuda_runtime.h>
@@ -44,6 +45,8 @@ typedef cudaStream_t zb_stream_t;
 #define ZB_DEV __device__
 #define ZB_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "zultra-b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); zb_cuda_fail(e_); } } while (0)
 void zb_cuda_fail(cudaError_t e);
+extern thread_local int g_zb_cuda_error;   /* set by a failed CUDA call / allocation on this host thread (zb_prims.cu) */
+static inline bool zb_failed() { return g_zb_cuda_error != 0; }
 extern long long g_zb_launches;   /* kernels launched by this library (bench.py reports it); several host threads count */
 static inline void zb_count_launch(int n) { __atomic_fetch_add(&g_zb_launches, (long long)n, __ATOMIC_RELAXED); }
 template <class F> __global__ void zb_task_kernel(long n, F f) {

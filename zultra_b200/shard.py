@@ -14,6 +14,20 @@ def plan_shards(n, block, world):
     return [(min(n, r * per * block), min(n, (r + 1) * per * block)) for r in range(world)]
 
 
+def chunk_blocks(nblocks, world):
+    """Max-blocks per chunk (same rule as multi_chunk_blocks, zb_capi.cu): at least ~4 chunks per device, at most 8 blocks."""
+    return max(1, min(8, nblocks // (world * 4)))
+
+
+def plan_chunks(n, block, world, g=None):
+    """Chunks of g max-blocks dealt round-robin to the ranks: [(lo, hi, rank)] in stream order.  Every rank gets a sample of
+    the whole stream, so a stream whose cost per byte varies along its length still loads all ranks evenly."""
+    nblocks = (n + block - 1) // block
+    g = g or chunk_blocks(nblocks, world)
+    nchunk = (nblocks + g - 1) // g
+    return [(j * g * block, min(n, (j + 1) * g * block), j % world) for j in range(nchunk)]
+
+
 def compose(maps):
     """maps[r][p] = bits of shard r when entered at phase p, INCLUDING the p pending bits.  Returns (offsets, nbits, total):
     absolute bit offset and produced bits of every shard."""
