@@ -75,14 +75,3 @@ long emu_compress(const uint8_t *data, long n, const uint8_t *hist, int hist_len
 }
 
 
-/* ZbCostRowBuf (zb_core.h): rows of every length up to 70 steps come out as the sequence that was put in */
-extern "C" int emu_selftest_rowbuf(void) {
-   for (int n = 0; n < 70; n++) {
-      std::vector<uint16_t> row(((n + 7) & ~7) + 8, 0xeeee), want(n);
-      ZbCostRowBuf b; b.init();
-      for (int t = 0; t < n; t++) { want[t] = (uint16_t)(t * 257 + 3); b.put(row.data(), t, want[t]); }
-      b.finish(row.data(), n);
-      for (int t = 0; t < n; t++) if (row[t] != want[t]) return 1 + n;
-   }
-   return 0;
-}

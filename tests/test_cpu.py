@@ -154,24 +154,20 @@ def test_oracle_multi_block_dictionary_and_errors(ref):
     assert oracle_py.compress(big, 0, 262144) == ref.compress(big, flags=0, block=262144)
 
 
-@pytest.mark.parametrize("name", ["js48k", "moz300k", "zeros100k", "period7", "lz_a96_p0.99", "rows1000", "utf16"])
-def test_emulated_lane_state_machine_vs_golden(emu, name, monkeypatch):
-    """The decoupled-lane form of the parse recurrence (zb_dpsm_open / _kstep / _close, zb_core.h), run chunk by chunk in
-    the host build: same deflate stream as the golden vector."""
-    monkeypatch.setenv("ZB_EMU_DP_SM", "1")
+@pytest.mark.parametrize("name", ["js48k", "moz300k", "zeros100k", "period7", "lz_a96_p0.99", "lz_a2_p0.9", "rows1000", "utf16", "alpha2"])
+def test_emulated_compact_candidate_records_vs_golden(emu, name, monkeypatch):
+    """The compact candidate records of the parse kernel (zb_cand_pack / zb_dp_eval, zb_core.h: leave-alone matches first,
+    short matches shortest-first, one shared prefix-minimum sweep, choice words resolved through the match list), run chunk
+    by chunk in the host build: same deflate stream as the golden vector."""
+    monkeypatch.setenv("ZB_EMU_DP_LEAN", "1")
     data = cases.small_cases()[name]
     out, bits, d = emu.compress(data)
     assert _gold_ok("%s/deflate" % name, out)
 
 
-def test_emulated_lane_state_machine_multi_block(emu, ref, monkeypatch):
+def test_emulated_compact_candidate_records_multi_block(emu, ref, monkeypatch):
     """Same, over several max-blocks with history, sub-block splits and clamped matches at sub-block ends."""
-    monkeypatch.setenv("ZB_EMU_DP_SM", "1")
+    monkeypatch.setenv("ZB_EMU_DP_LEAN", "1")
     for name, data, block in cases.multi_block_cases()[1:3]:
         out, bits, _ = emu.compress(data, block=block or (1 << 20))
         assert out == ref.compress(data, flags=0, block=block), name
-
-
-def test_cost_row_buffer_selftest(emu):
-    """ZbCostRowBuf: the 8-steps-at-a-time cost row of the decoupled-lane parse kernel."""
-    assert emu.lib.emu_selftest_rowbuf() == 0

@@ -607,124 +607,93 @@ struct ZbRingStrided {
 };
 
 /* ------------------------------------------------------------------------------------------------------------------------
- * The recurrence of zb_parse_range as a per-lane STATE MACHINE (experimental: the thread-per-chunk kernel spends half of its
- * instructions in candidate-length loops that only ~5 of a warp's 32 lanes are in; with the work of a position cut into
- * "open" (decode the record, queue the short matches), "k-step" (one candidate length) and "close" (leave-alone matches,
- * choice, write-back), a warp can run k-steps for whichever lanes have some and open/close positions for the others in
- * batches, so that no lane waits for the longest loop of the current position - lanes simply drift apart in position).
- * The functions below are the single-lane logic, shared by the host build (which runs them one chunk at a time to check them
- * against the golden vectors) and the device kernel; they make the same choices as zb_parse_range (blockdeflate.c:254-323).
+ * Compact candidate records for the parse kernel (zb_parse_dp_k).  The match list of a position does not change over the four
+ * parse passes (blockdeflate.c:871-920 only changes the code lengths), so everything about it that the recurrence needs is
+ * worked out ONCE per batch and packed into 16 bytes - half the traffic of the 32-byte match record in each of the four
+ * passes, and no offset -> symbol arithmetic, clamping or validity tests left on the recurrence's serial chain.
  *
- * MEM supplies: cost(tt) = cost written at step tt (0 for tt < 0: the zero guess above the start), put(t, c), best(i, w).
- * Steps count positions from the start of the chunk's walk: position i is step t, position i + k is step t - k.
- * Short matches (< 40) are queued as 14-bit entries {clamped length 6 | offset cost 5 | index 3}, shortest first (highest
- * index first), 4 per 64-bit word; an entry is finished when the shared prefix minimum over the lengths reaches its length.
+ * A record is up to eight 16-bit entries in PROCESSING order, terminated by a zero entry:
+ *   first the leave-alone matches (original length >= 40: tried at their full clamped length only, blockdeflate.c:286),
+ *   in list order (m = 0, 1, ..):        1 . | ml : 9 (bits 13..5, clamped to the sub-block end, may be 1 or 2: SURVEY A-3) | sym : 5
+ *   then the short matches, SHORTEST first (descending m), those clamped below 3 dropped:
+ *                                          0 1 | m : 3 (bits 13..11) | ml : 6 (bits 10..5) | sym : 5
+ * sym = distance symbol of the match's offset.  Candidate order of the reference (literal; m = 0.. longest first; lengths
+ * descending; strict '<' to replace) = minimal cost, ties to the smallest m, then to the largest length: leave-alone matches
+ * (the smallest m's) are compared in list order with '<', the short ones shortest first with '<=' over a shared prefix
+ * minimum of lencost(k) + cost[i + k], and a short match beats the best leave-alone match only when strictly cheaper.
+ *
+ * The kernel's choice word: k | sym << 9 | m << 14 (0 = literal); zb_choice_k turns the final pass's choices into {length,
+ * offset} by fetching the one offset from the match list.
  */
-struct ZbDpLane {
-   int i, t;                 /* open position and its step */
-   uint32_t cprev;           /* cost of position i + 1 */
-   int k, bnd, curk, mcur;   /* next length to try; length at which the current entry ends (0: no entry left); argmin; entry's match */
-   uint32_t curmin, offc;    /* prefix minimum of lencost(k) + cost[i + k]; offset cost of the current entry */
-   uint32_t bt; int bk, bm;  /* best match candidate so far: total, length, match index */
-   uint64_t q0, q1;          /* queued entries */
-   ZbMatchRec rec; uint32_t lit;
-};
+struct ZbCand { uint32_t w[4]; };
 
-ZB_HD void zb_dpsm_pop(ZbDpLane &S) {
-   const uint32_t e = (uint32_t)(S.q0 & 0x3fffu);
-   S.q0 = (S.q0 >> 14) | ((S.q1 & 0x3fffu) << 42);
-   S.q1 >>= 14;
-   S.bnd = (int)(e & 63u); S.offc = (e >> 6) & 31u; S.mcur = (int)(e >> 11);
-}
-
-/* open position i (record and literal already in S.rec / S.lit): queue its short matches */
-template <class OFFC>
-ZB_HD void zb_dpsm_open(ZbDpLane &S, int end, const OFFC &offcost) {
-   S.q0 = 0; S.q1 = 0;
-   S.k = ZB_MIN_MATCH; S.curmin = 0x7fffffffu; S.curk = 0; S.bt = 0x7fffffffu; S.bk = 0; S.bm = 0;
-   const int rem = end - S.i;
+ZB_HD ZbCand zb_cand_pack(const ZbMatchRec &rec, int rem /* sub-block end - position */) {
+   uint64_t lo = 0, hi = 0;
+   int n = 0, M = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-   for (int m = 0; m < ZB_NMATCH; m++) {        /* ascending index = descending length; pushed at the low end, so popped shortest first */
-      const int len0 = (int)(S.rec.w[m] & 0xffffu);
-      if (len0 >= ZB_MIN_MATCH && len0 < ZB_LEAVE_ALONE) {
+   for (int m = 0; m < ZB_NMATCH; m++) if (M == m && (rec.w[m] & 0xffffu) >= ZB_MIN_MATCH) M = m + 1;
+#define ZB_CAND_PUSH(e_) do { const uint64_t e__ = (uint64_t)(e_); if (n < 4) lo |= e__ << (16 * n); else hi |= e__ << (16 * (n - 4)); n++; } while (0)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+   for (int m = 0; m < ZB_NMATCH; m++) {
+      const int len0 = (int)(rec.w[m] & 0xffffu);
+      if (m < M && len0 >= ZB_LEAVE_ALONE) {
          const int ml = len0 < rem ? len0 : rem;
-         if (ml >= ZB_MIN_MATCH) {
-            const uint64_t e = (uint64_t)((uint32_t)ml | (offcost(S.rec.w[m] >> 16) << 6) | ((uint32_t)m << 11));
-            S.q1 = (S.q1 << 14) | ((S.q0 >> 42) & 0x3fffu);
-            S.q0 = ((S.q0 << 14) | e) & 0x00ffffffffffffffull;
+         ZB_CAND_PUSH(0x8000u | ((uint32_t)ml << 5) | (uint32_t)zb_off_sym(rec.w[m] >> 16));
+      }
+   }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+   for (int m = ZB_NMATCH - 1; m >= 0; m--) {
+      const int len0 = (int)(rec.w[m] & 0xffffu);
+      if (m < M && len0 < ZB_LEAVE_ALONE) {
+         const int ml = len0 < rem ? len0 : rem;
+         if (ml >= ZB_MIN_MATCH) ZB_CAND_PUSH(0x4000u | ((uint32_t)m << 11) | ((uint32_t)ml << 5) | (uint32_t)zb_off_sym(rec.w[m] >> 16));
+      }
+   }
+#undef ZB_CAND_PUSH
+   ZbCand c;
+   c.w[0] = (uint32_t)lo; c.w[1] = (uint32_t)(lo >> 32); c.w[2] = (uint32_t)hi; c.w[3] = (uint32_t)(hi >> 32);
+   return c;
+}
+
+/* One position of the recurrence from its compact record, written for clarity: the host build runs it (ZB_EMU_DP_LEAN) to pin
+   the record format and the tie-breaking against the golden vectors; the CUDA kernel implements the same arithmetic on its
+   shared-memory ring.  cost(k) = cost of position i + k (0 above the chunk's start).  Returns cost[i]; *choice as above. */
+template <class COSTAT>
+ZB_HD uint32_t zb_dp_eval(const ZbCand &c, uint32_t lit_cost, uint32_t cprev, const ZbCostTab &tab, const COSTAT &cost, uint32_t *choice) {
+   uint32_t btla = 0xffffffffu, bwla = 0, bts = 0xffffffffu, bws = 0, curmin = 0xffffffffu;
+   int k = ZB_MIN_MATCH, mla = 0;
+   for (int j = 0; j < 8; j++) {
+      const uint32_t e = (c.w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+      if (!e) break;
+      const uint32_t sym = e & 31u;
+      if (e & 0x8000u) {
+         const int ml = (int)((e >> 5) & 511u);
+         const int lidx = ml >= ZB_MIN_MATCH ? ml - ZB_MIN_MATCH : 255;
+         const uint32_t total = (uint32_t)tab.len[lidx] + tab.off[sym] + cost(ml);
+         if (total < btla) { btla = total; bwla = (uint32_t)ml | (sym << 9) | ((uint32_t)mla << 14); }
+         mla++;
+      } else {
+         const int ml = (int)((e >> 5) & 63u);
+         for (; k <= ml; k++) {
+            const uint32_t key = ((cost(k) + tab.len[k - ZB_MIN_MATCH]) << 6) | (uint32_t)(63 - k);
+            if (key < curmin) curmin = key;
          }
+         const uint32_t total = (curmin >> 6) + tab.off[sym];
+         if (total <= bts) { bts = total; bws = (63u - (curmin & 63u)) | (sym << 9) | (((e >> 11) & 7u) << 14); }
       }
    }
-   zb_dpsm_pop(S);
+   uint32_t bt = btla, bw = bwla;
+   if (bts < btla) { bt = bts; bw = bws; }
+   uint32_t bestc = cprev + lit_cost;
+   *choice = 0;
+   if (bt < bestc) { bestc = bt; *choice = bw; }
+   return bestc;
 }
-
-/* one candidate length of the open position (only while S.bnd != 0) */
-template <class MEM>
-ZB_HD void zb_dpsm_kstep(ZbDpLane &S, const MEM &mem, const uint8_t *plen) {
-   const uint32_t c = (uint32_t)plen[S.k - ZB_MIN_MATCH] + mem.cost(S.t - S.k);
-   if (c <= S.curmin) { S.curmin = c; S.curk = S.k; }
-   while (S.bnd == S.k) {               /* entries ending here (several only where the sub-block end clamps them) */
-      const uint32_t total = S.curmin + S.offc;
-      if (total <= S.bt) { S.bt = total; S.bk = S.curk; S.bm = S.mcur; }
-      zb_dpsm_pop(S);
-   }
-   S.k++;
-}
-
-/* close the open position: leave-alone matches, the choice, write-back; moves to position i - 1 */
-template <class MEM, class OFFC>
-ZB_HD void zb_dpsm_close(ZbDpLane &S, MEM &mem, int end, const uint8_t *plit, const uint8_t *plen, const OFFC &offcost, bool keep) {
-   uint32_t bw = 0;
-   if (S.bt != 0x7fffffffu) {
-      uint32_t off = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int m = 0; m < ZB_NMATCH; m++) if (m == S.bm) off = S.rec.w[m] >> 16;
-      bw = (uint32_t)S.bk | (off << 16);
-   }
-   const int rem = end - S.i;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-   for (int m = ZB_NMATCH - 1; m >= 0; m--) {    /* >= 40: only the full (clamped) length, after the shorter matches, longest last */
-      const int len0 = (int)(S.rec.w[m] & 0xffffu);
-      if (len0 >= ZB_LEAVE_ALONE) {
-         const int ml = len0 < rem ? len0 : rem;
-         int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
-         const uint32_t total = (uint32_t)plen[lidx] + offcost(S.rec.w[m] >> 16) + mem.cost(S.t - ml);
-         if (total <= S.bt) { S.bt = total; bw = (uint32_t)ml | (S.rec.w[m] & 0xffff0000u); }
-      }
-   }
-   uint32_t bestc = S.cprev + plit[S.lit], bestw = 0;
-   if (S.bt < bestc) { bestc = S.bt; bestw = bw; }
-   mem.put(S.t, bestc);
-   if (keep) mem.best(S.i, bestw);
-   S.cprev = bestc;
-   S.i--; S.t++;
-}
-
-/* Cost row of one decoupled lane (zb_parse_dp_sm_k): lanes drift apart in step, so a [step][thread] row would be written one
-   2-byte store per lane and line.  Instead every lane owns a contiguous row and writes it 8 steps (16 bytes) at a time out of
-   a 128-bit shift register; a step is readable from the row once its group of 8 has been flushed, which is always the case
-   for the far reads (>= 64 steps back) and for the signatures (taken after finish()). */
-struct ZbCostRowBuf {
-   uint32_t b0, b1, b2, b3;
-   ZB_HD void init() { b0 = b1 = b2 = b3 = 0; }
-   /* append the cost of step t (t = 0, 1, 2, ...); flushes the group when it is complete */
-   ZB_HD void put(uint16_t *row, int t, uint32_t c) {
-      b0 = (b0 >> 16) | (b1 << 16); b1 = (b1 >> 16) | (b2 << 16); b2 = (b2 >> 16) | (b3 << 16); b3 = (b3 >> 16) | (c << 16);
-      if ((t & 7) == 7) { uint32_t *d = (uint32_t *)(row + (t - 7)); d[0] = b0; d[1] = b1; d[2] = b2; d[3] = b3; }
-   }
-   /* after the last put (nsteps steps in total): write the incomplete last group */
-   ZB_HD void finish(uint16_t *row, int nsteps) {
-      const int rem = nsteps & 7;
-      if (!rem) return;
-      for (int j = rem; j < 8; j++) { b0 = (b0 >> 16) | (b1 << 16); b1 = (b1 >> 16) | (b2 << 16); b2 = (b2 >> 16) | (b3 << 16); b3 >>= 16; }
-      uint32_t *d = (uint32_t *)(row + (nsteps - rem)); d[0] = b0; d[1] = b1; d[2] = b2; d[3] = b3;
-   }
-};
 
 #endif /* ZB_CORE_H */

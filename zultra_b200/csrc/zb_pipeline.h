@@ -129,7 +129,7 @@ struct ZbPipe {
    /* sub-blocks */
    ZbBuf<ZbSub> sub; ZbBuf<ZbSubTabs> tabs; ZbBuf<uint32_t> dchunk_sub, pchunk_sub;
    ZbBuf<zb_match_t> best; ZbBuf<int16_t> sig_true, sig_warm, sig_new; ZbBuf<uint8_t> dok; ZbBuf<uint32_t> dbad;
-   ZbBuf<uint32_t> pentry, pbits; ZbBuf<uint16_t> dpfar;   /* dpfar: cost rows of the thread-per-chunk parse kernel */
+   ZbBuf<uint32_t> pentry, pbits, cand /* 16-byte candidate records, zb_cand_pack */; ZbBuf<uint16_t> dpfar;   /* dpfar: cost rows of the thread-per-chunk parse kernel */
    /* output */
    ZbBuf<uint32_t> out; ZbBuf<ZbStreamOut> sout;
    std::vector<ZbStreamOut> h_sout;
@@ -708,7 +708,8 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
  * all the hop needs.  Sweep: one thread per chunk, backwards; the exit offsets of the positions behind (<= 258) sit in a
  * shared-memory ring ([slot][thread]: conflict-free), lengths are read 16 bytes at a time.  MODE 0: greedy path, lengths
  * from glen (u16), chunks per window.  MODE 1: chosen path, lengths from best[] (< 3 counts as a literal), chunks per
- * sub-block; pass >= 0 skips static sub-blocks after the first pass. */
+ * sub-block; pass >= 0 skips static sub-blocks after the first pass.  The length is the low 9 bits of the word in both the parse
+ * kernel's choice format (k | sym << 9 | m << 14) and the final {length, offset} format. */
 #define ZB_SW_THREADS 64
 #define ZB_SW_RING 288
 #define ZB_EXROW 264          /* u16 per chunk row: 258 used, 528 bytes = 33 x 16 */
@@ -765,10 +766,10 @@ __global__ void __launch_bounds__(ZB_SW_THREADS) zb_sweep_k(long nchunk, const Z
 #undef ZB_SW_PROC0
       while (p > lo) ZB_SW_STEP(gl[gb + p - 1]);
    } else {
-      while (p > lo && ((gb + p) & 3u)) ZB_SW_STEP(bm[gb + p - 1].length);
+      while (p > lo && ((gb + p) & 3u)) ZB_SW_STEP(bm[gb + p - 1].length & 0x1ffu);
       const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
 #define ZB_SW_LD1(k_) (p >= lo + (k_) ? *(const uint4 *)(bm + gb + p - (k_)) : z4)
-#define ZB_SW_PROC1(v) do { ZB_SW_STEP((v).w & 0xffffu); ZB_SW_STEP((v).z & 0xffffu); ZB_SW_STEP((v).y & 0xffffu); ZB_SW_STEP((v).x & 0xffffu); } while (0)
+#define ZB_SW_PROC1(v) do { ZB_SW_STEP((v).w & 0x1ffu); ZB_SW_STEP((v).z & 0x1ffu); ZB_SW_STEP((v).y & 0x1ffu); ZB_SW_STEP((v).x & 0x1ffu); } while (0)
       uint4 va = ZB_SW_LD1(4), vb = ZB_SW_LD1(8), vc = ZB_SW_LD1(12);
       for (;;) {
          if (p < lo + 4) break; ZB_SW_PROC1(va); va = ZB_SW_LD1(12);
@@ -777,7 +778,7 @@ __global__ void __launch_bounds__(ZB_SW_THREADS) zb_sweep_k(long nchunk, const Z
       }
 #undef ZB_SW_LD1
 #undef ZB_SW_PROC1
-      while (p > lo) ZB_SW_STEP(bm[gb + p - 1].length);
+      while (p > lo) ZB_SW_STEP(bm[gb + p - 1].length & 0x1ffu);
    }
 #undef ZB_SW_STEP
 }
@@ -1278,95 +1279,52 @@ ZB_HD void zb_walk_best(const zb_match_t *best, uint32_t entry, uint32_t hi, F &
 }
 
 #ifndef ZB_EMU
+/* ---- candidate records: once per batch, one thread per position of every sub-block (zb_cand_pack, zb_core.h) ---- */
+__global__ void __launch_bounds__(256) zb_cand_k(long npch, const ZbSub *sb, const uint32_t *pcs, const uint32_t *wbs, const zb_match_t *mt, uint4 *cand) {
+   const long c = blockIdx.x;
+   if (c >= npch) return;
+   const ZbSub s = sb[pcs[c]];
+   const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
+   const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+   for (uint32_t p = lo + threadIdx.x; p < hi; p += 256) {
+      const ZbMatchRec rec = zb_load_rec(mt + ((size_t)gb << 3), (int)p);
+      const ZbCand cd = zb_cand_pack(rec, (int)(s.pe - p));
+      cand[gb + p] = make_uint4(cd.w[0], cd.w[1], cd.w[2], cd.w[3]);
+   }
+}
+
+/* after the last pass: choice words -> {length, offset} (private.h:59), the offset fetched from the match list */
+__global__ void __launch_bounds__(256) zb_choice_k(long npch, const ZbSub *sb, const uint32_t *pcs, const uint32_t *wbs, const zb_match_t *mt, uint32_t *bm) {
+   const long c = blockIdx.x;
+   if (c >= npch) return;
+   const ZbSub s = sb[pcs[c]];
+   const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
+   const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+   for (uint32_t p = lo + threadIdx.x; p < hi; p += 256) {
+      const uint32_t w = bm[gb + p];
+      uint32_t v = 0;
+      if (w) v = (w & 511u) | ((uint32_t)mt[((size_t)(gb + p) << 3) + (w >> 14)].offset << 16);
+      bm[gb + p] = v;
+   }
+}
+
 /* ---- chunked backward recurrence, one thread per parse chunk (32 independent chunks per warp) ----
- * Occupancy is what this kernel lives on (every thread is one long dependent chain), so the per-thread state is kept small:
- * the costs of the last 64 positions sit in a shared-memory ring ([slot][thread]: a warp's accesses fall into distinct banks
- * up to the 2-way u16 pairing) - short matches (< 40) only look 39 positions ahead - and every cost is also streamed to a
- * global scratch row ([step][thread], so a warp's store is one 64-byte line) from which the rare far reads of leave-alone
- * matches (>= 40: one cost, up to 258 ahead) and the two 259-entry signatures are taken.  A chunk starts from cost 0 and a
- * step adds at most 15 bits, so with CD + WU <= 4368 steps the u16 costs never wrap and are compared as plain integers.
- * The bit costs come from a per-warp shared-memory copy of the table of the warp's first sub-block; a lane whose chunk
- * belongs to a later sub-block (one warp per sub-block boundary) reads its table from global memory instead.  Match records
- * are fetched one position ahead. */
+ * Every thread is one long dependent chain, so the kernel lives on instruction count and occupancy.  Per position a thread
+ * reads a 16-byte candidate record (zb_cand_pack) and the literal byte, both fetched a position ahead; the costs of the last
+ * 64 positions sit in a shared-memory ring ([slot][thread] u16: a warp's accesses fall into distinct banks up to the 2-way
+ * u16 pairing) - short matches (< 40) only look 39 positions ahead - and every cost is also streamed to a global scratch row
+ * ([step][thread], so a warp's store is one 64-byte line) from which the rare far reads of leave-alone matches (>= 40: one
+ * cost, up to 258 ahead) and the two 259-entry signatures are taken.  A chunk starts from cost 0 and a step adds at most 15
+ * bits, so with CD + WU <= 4368 steps the u16 costs never wrap and are compared as plain integers.
+ * The candidate lengths of all short matches of a position share ONE prefix-minimum sweep: key = (cost[i + k] + lencost(k))
+ * << 6 | 63 - k, one multiply-add and one minimum per length (the length cost and the tie-break come pre-combined out of a
+ * per-sub-block table), the sweep pausing at every match's length to price that match.
+ * Bit-cost tables: the CTA's 128 chunks belong to consecutive sub-blocks; their tables are copied to shared memory, one slot
+ * each (the host sizes the dynamic shared memory by the largest number of sub-blocks any CTA spans - batches of small streams
+ * span a dozen), and every lane uses the slot of its own sub-block. */
 #define ZB_DP_THREADS 128
 #define ZB_NR 64              /* near ring entries */
-#define ZB_DP_INF 0x7fffffffu
-
-/* cost of an offset: OT = the warp's 512-entry table indexed like the reference's g_nOffsetSymbol (blockdeflate.c:45,150:
-   o - 1 for o <= 256, else 256 + ((o - 257) >> 7)); otherwise the symbol is computed and looked up in the sub-block's table */
-template <bool OT>
-__device__ __forceinline__ uint32_t zb_dp_offcost(const uint8_t *__restrict__ poff, uint32_t off) {
-   if (OT) { const uint32_t d = off - 1u; return poff[d < 256u ? d : 256u + ((d - 256u) >> 7)]; }
-   return poff[zb_off_sym(off)];
-}
-
-template <bool OT>
-__device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const zb_match_t *__restrict__ match, const uint8_t *__restrict__ plit,
-                                            const uint8_t *__restrict__ plen, const uint8_t *__restrict__ poff, int lo, int from, int end,
-                                            zb_match_t *__restrict__ best, uint16_t *ring0, uint16_t *far0, int &t_io, uint32_t &cprev_io, const bool KEEP) {
-   const int NT = ZB_DP_THREADS;
-   if (from - 1 < lo) return;
-   int t = t_io;
-   uint32_t cprev = cprev_io;                 /* cost of position i + 1 */
-   ZbMatchRec nxt = zb_load_rec(match, from - 1);
-   uint32_t nlit = T[from - 1];
-   for (int i = from - 1; i >= lo; i--, t++) {
-      const ZbMatchRec rec = nxt;
-      const uint32_t lit = nlit;
-      if (i - 1 >= lo) { nxt = zb_load_rec(match, i - 1); nlit = T[i - 1]; }
-      uint32_t bestc = cprev + plit[lit];
-      uint32_t bestw = 0;
-      int M = 0;
-#pragma unroll
-      for (int m = 0; m < ZB_NMATCH; m++) if (M == m && (rec.w[m] & 0xffffu) >= ZB_MIN_MATCH) M = m + 1;
-      if (M) {
-         uint32_t bt = ZB_DP_INF, bw = 0;
-         int k = ZB_MIN_MATCH, curk = 0;
-         uint32_t curmin = ZB_DP_INF;
-         const int q = (t - ZB_MIN_MATCH) & (ZB_NR - 1);          /* slot of i+3 (a slot not written yet reads as the zero guess) */
-         const uint16_t *pr = ring0 + q * NT;                       /* slot of i+k, moving down by NT per k */
-         int kw = k + q + 1;                                        /* first k whose slot wraps */
-#pragma unroll
-         for (int m = ZB_NMATCH - 1; m >= 0; m--) {
-            if (m < M) {
-               const int mlen0 = (int)(rec.w[m] & 0xffffu), moff = (int)(rec.w[m] >> 16);
-               const uint32_t offc = zb_dp_offcost<OT>(poff, (uint32_t)moff);
-               int ml = mlen0;
-               if (i + ml > end) ml = end - i;
-               uint32_t total; int kk;
-               if (mlen0 >= ZB_LEAVE_ALONE) {
-                  int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255;
-                  const int tt = t - ml;                             /* step at which position i + ml was done */
-                  uint32_t cv;
-                  if (ml < ZB_NR) cv = ring0[(tt & (ZB_NR - 1)) * NT];
-                  else cv = tt >= 0 ? (uint32_t)far0[(size_t)tt * NT] : 0u;
-                  total = plen[lidx] + offc + cv;
-                  kk = ml;
-               } else {
-                  while (k <= ml) {
-                     const int kstop = ml < kw - 1 ? ml : kw - 1;
-#pragma unroll 4
-                     for (; k <= kstop; k++, pr -= NT) {
-                        const uint32_t c = (uint32_t)plen[k - ZB_MIN_MATCH] + (uint32_t)*pr;
-                        if (c <= curmin) { curmin = c; curk = k; }
-                     }
-                     if (k == kw) { pr += ZB_NR * NT; kw += ZB_NR; }
-                  }
-                  total = curk ? curmin + offc : ZB_DP_INF;
-                  kk = curk;
-               }
-               if (total <= bt && total != ZB_DP_INF) { bt = total; bw = (uint32_t)kk | ((uint32_t)moff << 16); }
-            }
-         }
-         if (bt < bestc) { bestc = bt; bestw = bw; }
-      }
-      ring0[(t & (ZB_NR - 1)) * NT] = (uint16_t)bestc;
-      far0[(size_t)t * NT] = (uint16_t)bestc;
-      cprev = bestc;
-      if (KEEP) ((uint32_t *)best)[i] = bestw;
-   }
-   t_io = t; cprev_io = cprev;
-}
+struct ZbDpTab { uint8_t lit[256]; uint8_t len[256]; uint8_t off[32]; uint32_t lenkey[40]; };   /* lenkey[k - 3] = lencost(k) << 6 | 63 - k */
 
 /* the 259 relative costs at `pos0` (the signature two neighbouring chunks are compared by), read back from the scratch row:
    position p was done at step from - 1 - p; positions at and above `from` are the zero guess */
@@ -1386,39 +1344,105 @@ __device__ __forceinline__ void zb_dp_signature(int16_t *__restrict__ dst, size_
    }
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
-                                                               const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw,
-                                                               size_t SS, uint16_t *far, int CD, int WU) {
-   __shared__ uint16_t ring_s[ZB_NR * ZB_DP_THREADS];
-   __shared__ ZbCostTab tab_s[ZB_DP_THREADS / 32];
-   __shared__ uint8_t offtab_s[ZB_DP_THREADS / 32][512];
-   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-   const long cw = (long)blockIdx.x * ZB_DP_THREADS + wi * 32;
-   if (cw >= ndch) return;                /* the whole warp */
-   const long c = cw + lane;
-   const uint32_t x0 = dcs[cw];
-   {
-      const uint32_t *src = (const uint32_t *)&tb[x0].cost; uint32_t *dstw = (uint32_t *)&tab_s[wi];
-      for (int e = lane; e < (int)(sizeof(ZbCostTab) / 4); e += 32) dstw[e] = src[e];
+/* positions [lo, from) of one chunk, descending; t = step of position from - 1 on entry.  All per-step addresses are running
+   pointers (the cost row advances by one row, the records / text / choices retreat by one element, the ring slot by one slot
+   modulo 64): the loop is instruction bound, and 64-bit address arithmetic from the position index was a fifth of it. */
+__device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const uint4 *__restrict__ cand, const ZbDpTab *__restrict__ tab, int lo, int from,
+                                            uint32_t *__restrict__ choice, uint16_t *ring0, uint16_t *far0, int &t_io, uint32_t &cprev_io, const bool KEEP) {
+   const int NT = ZB_DP_THREADS;
+   if (from - 1 < lo) return;
+   int t = t_io;
+   uint32_t cprev = cprev_io;                 /* cost of position i + 1 */
+   const uint4 *pc = cand + (from - 1);
+   const uint8_t *pt = T + (from - 1);
+   uint32_t *pch = choice + (from - 1);
+   uint16_t *pf = far0 + (size_t)t * NT;
+   uint4 nxt = __ldg(pc);
+   uint32_t nlit = *pt;
+   const uint32_t *lenkey = tab->lenkey;
+   uint32_t slot = (uint32_t)t & (ZB_NR - 1);  /* ring slot of the position being done */
+   for (int n = from - lo; n > 0; n--, t++, pf += NT, pch--) {
+      uint4 rec = nxt;
+      const uint32_t lit = nlit;
+      pc--; pt--;
+      if (n > 1) { nxt = __ldg(pc); nlit = *pt; }
+      uint32_t bestc = cprev + tab->lit[lit];
+      uint32_t bestw = 0;
+      if (rec.x) {
+         uint32_t btla = 0xffffffffu, bwla = 0, bts = 0xffffffffu, bws = 0, curmin = 0xffffffffu, mla = 0;
+         int k = ZB_MIN_MATCH;
+         const int q = (int)((slot - ZB_MIN_MATCH) & (ZB_NR - 1));   /* slot of i + 3 (a slot not written yet reads as the zero guess) */
+         const uint16_t *pr = ring0 + q * NT;                       /* slot of i + k, moving down by NT per k */
+         int kw = k + q + 1;                                        /* first k whose slot wraps */
+         uint32_t e = rec.x & 0xffffu;
+#pragma unroll 1
+         do {
+            const uint32_t offc = tab->off[e & 31u];
+            if (e & 0x8000u) {      /* leave-alone match: its one length */
+               const int ml = (int)((e >> 5) & 511u);
+               const int lidx = ml >= ZB_MIN_MATCH ? ml - ZB_MIN_MATCH : 255;
+               uint32_t cv;
+               if (ml < ZB_NR) cv = ring0[((slot - (uint32_t)ml) & (ZB_NR - 1)) * NT];
+               else cv = t >= ml ? (uint32_t)*(pf - (size_t)ml * NT) : 0u;      /* the row of step t - ml */
+               const uint32_t total = (uint32_t)tab->len[lidx] + offc + cv;
+               if (total < btla) { btla = total; bwla = (uint32_t)ml | ((e & 31u) << 9) | (mla << 14); }
+               mla++;
+            } else {                /* short match: extend the shared sweep to its length, then price it */
+               const int ml = (int)((e >> 5) & 63u);
+               while (k <= ml) {
+                  const int kstop = ml < kw - 1 ? ml : kw - 1;
+#pragma unroll 4
+                  for (; k <= kstop; k++, pr -= NT) {
+                     const uint32_t key = ((uint32_t)*pr << 6) + lenkey[k - ZB_MIN_MATCH];
+                     curmin = key < curmin ? key : curmin;
+                  }
+                  if (k == kw) { pr += ZB_NR * NT; kw += ZB_NR; }
+               }
+               const uint32_t total = (curmin >> 6) + offc;
+               if (total <= bts) { bts = total; bws = (63u - (curmin & 63u)) | ((e & 31u) << 9) | (((e >> 11) & 7u) << 14); }
+            }
+            /* next entry: the record shifts down by 16 bits */
+            rec.x = __funnelshift_r(rec.x, rec.y, 16); rec.y = __funnelshift_r(rec.y, rec.z, 16); rec.z = __funnelshift_r(rec.z, rec.w, 16); rec.w >>= 16;
+            e = rec.x & 0xffffu;
+         } while (e);
+         if (bts < btla) { btla = bts; bwla = bws; }
+         if (btla < bestc) { bestc = btla; bestw = bwla; }
+      }
+      ring0[slot * NT] = (uint16_t)bestc;
+      *pf = (uint16_t)bestc;
+      slot = (slot + 1) & (ZB_NR - 1);
+      cprev = bestc;
+      if (KEEP) *pch = bestw;
+   }
+   t_io = t; cprev_io = cprev;
+}
+
+__global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
+                                                               const uint32_t *wbs, const uint8_t *T, const uint4 *cand, uint32_t *bm, int16_t *sgt, int16_t *sgw,
+                                                               size_t SS, uint16_t *far, int CD, int WU, int nslot) {
+   extern __shared__ __align__(16) uint8_t zb_dp_sm[];
+   uint16_t *ring_s = (uint16_t *)zb_dp_sm;                                   /* [ZB_NR][ZB_DP_THREADS] */
+   ZbDpTab *tab_s = (ZbDpTab *)(zb_dp_sm + ZB_NR * ZB_DP_THREADS * 2);        /* [nslot] */
+   const long c0 = (long)blockIdx.x * ZB_DP_THREADS, c = c0 + threadIdx.x;
+   const long clast = (c0 + ZB_DP_THREADS < ndch ? c0 + ZB_DP_THREADS : ndch) - 1;
+   const uint32_t x0 = dcs[c0], x1 = dcs[clast];
+   int ns = (int)(x1 - x0) + 1; if (ns > nslot) ns = nslot;                   /* never more than nslot (the host sized it by the maximum) */
+   for (int sl = 0; sl < ns; sl++) {
+      const uint32_t *src = (const uint32_t *)&tb[x0 + sl].cost; uint32_t *dstw = (uint32_t *)&tab_s[sl];
+      for (int e = threadIdx.x; e < (int)(sizeof(ZbCostTab) / 4); e += ZB_DP_THREADS) dstw[e] = src[e];
+      if (threadIdx.x < 40) { const int k = ZB_MIN_MATCH + threadIdx.x; tab_s[sl].lenkey[threadIdx.x] = ((uint32_t)tb[x0 + sl].cost.len[threadIdx.x] << 6) | (uint32_t)(63 - (k < 63 ? k : 63)); }
    }
    uint16_t *ring0 = ring_s + threadIdx.x;
    for (int e = 0; e < ZB_NR; e++) ring0[e * ZB_DP_THREADS] = 0;
-   __syncwarp();
-   for (int e = lane; e < 512; e += 32) offtab_s[wi][e] = tab_s[wi].off[zb_off_sym(e < 256 ? (uint32_t)e + 1u : 257u + ((uint32_t)(e - 256) << 7))];
-   __syncwarp();
-   /* a warp whose chunks span several sub-blocks (batches of small streams: ~10 chunks per sub-block) takes the global-table
-      path as a whole: one code path for the warp instead of the two instantiations run one after the other */
-   const bool uniform = __all_sync(0xffffffffu, (c < ndch ? dcs[c] : x0) == x0);
+   __syncthreads();
    if (c >= ndch) return;
    const uint32_t x = dcs[c];
    const ZbSub s = sb[x];
    if (pass > 0 && !s.is_dyn) return;
+   const ZbDpTab *tab = &tab_s[x - x0];
    const uint32_t k = (uint32_t)c - s.dchunk_base;
    const uint32_t gb = wbs[s.win];
    const uint8_t *t = T + wd[s.win].in_off;
-   const zb_match_t *m0 = mt + ((size_t)gb << 3);
-   zb_match_t *b0 = bm + gb;
    const int lo = (int)(s.ps + k * CD);
    const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
    const int end = (int)s.pe;
@@ -1426,124 +1450,13 @@ __global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub
    uint16_t *far0 = far + (size_t)blockIdx.x * (size_t)(CD + WU) * ZB_DP_THREADS + threadIdx.x;
    int16_t *sw = sgw + (size_t)c, *sg = sgt + (size_t)c;
    int step = 0; uint32_t cprev = 0;
-   /* warm-up [hi, from) then the chunk [lo, hi): ONE copy of the recurrence per table path (the two phases as iterations of
-      a loop that is not unrolled) - the kernel is instruction-issue bound and its code should stay inside the I-cache */
-   if (uniform) {
-      const uint8_t *plit = tab_s[wi].lit, *plen = tab_s[wi].len, *poff = offtab_s[wi];
+   /* warm-up [hi, from) then the chunk [lo, hi): ONE copy of the recurrence (the two phases as iterations of a loop that is
+      not unrolled) - the kernel is instruction-issue bound and its code should stay inside the I-cache */
 #pragma unroll 1
-      for (int phase = 0; phase < 2; phase++) {
-         zb_dp_range<true>(t, m0, plit, plen, poff, phase ? lo : hi, phase ? hi : from, end, b0, ring0, far0, step, cprev, phase != 0);
-         zb_dp_signature(phase ? sg : sw, SS, far0, phase ? lo : hi, from, end, step, cprev, phase == 0);
-      }
-   } else {
-      const uint8_t *plit = tb[x].cost.lit, *plen = tb[x].cost.len, *poff = tb[x].cost.off;
-#pragma unroll 1
-      for (int phase = 0; phase < 2; phase++) {
-         zb_dp_range<false>(t, m0, plit, plen, poff, phase ? lo : hi, phase ? hi : from, end, b0, ring0, far0, step, cprev, phase != 0);
-         zb_dp_signature(phase ? sg : sw, SS, far0, phase ? lo : hi, from, end, step, cprev, phase == 0);
-      }
+   for (int phase = 0; phase < 2; phase++) {
+      zb_dp_range(t, cand + gb, tab, phase ? lo : hi, phase ? hi : from, bm + gb, ring0, far0, step, cprev, phase != 0);
+      zb_dp_signature(phase ? sg : sw, SS, far0, phase ? lo : hi, from, end, step, cprev, phase == 0);
    }
-}
-
-/* ---- EXPERIMENTAL (ZULTRA_CUDA_DP_SM=1; logic checked on the host against the golden vectors, kernel not yet measured):
- * the same chunks, one thread each, but the lanes of a warp are decoupled: a lane is either inside the candidate-length loop
- * of its open position (k-steps) or between positions (close + open).  Every warp iteration runs k-steps for the lanes that
- * have some, unless at least ZB_SM_QUORUM lanes are waiting to close/open (or nobody has k-steps left), in which case those
- * lanes do that together.  No lane waits for the longest loop of "the current position": lanes drift apart in position. */
-#define ZB_SM_QUORUM 16
-template <bool OT>
-__device__ __forceinline__ void zb_dp_sm_chunk(bool active, const uint8_t *__restrict__ t, const zb_match_t *__restrict__ m0, const uint8_t *plit, const uint8_t *plen,
-                                               const uint8_t *poff, int lo, int hi, int from, int end, uint16_t *ring0, uint16_t *far0, uint32_t *best) {
-   /* far0 = this lane's own contiguous cost row (steps 0, 1, 2, ...), written 8 steps at a time (ZbCostRowBuf) */
-   struct Mem { uint16_t *ring0, *far0; uint32_t *bp; int t_now; ZbCostRowBuf rb;
-      __device__ __forceinline__ uint32_t cost(int tt) const {
-         if (tt < 0) return 0u;
-         return (t_now - tt < ZB_NR) ? (uint32_t)ring0[(tt & (ZB_NR - 1)) * ZB_DP_THREADS] : (uint32_t)far0[tt];
-      }
-      __device__ __forceinline__ void put(int tt, uint32_t c) { ring0[(tt & (ZB_NR - 1)) * ZB_DP_THREADS] = (uint16_t)c; rb.put(far0, tt, c); }
-      __device__ __forceinline__ void best(int i, uint32_t w) { bp[i] = w; }
-   } mem;
-   mem.ring0 = ring0; mem.far0 = far0; mem.bp = best; mem.t_now = 0; mem.rb.init();
-   auto offcost = [&](uint32_t off) -> uint32_t { return zb_dp_offcost<OT>(poff, off); };
-   ZbDpLane S;
-   S.i = from - 1; S.t = 0; S.cprev = 0; S.bnd = 0; S.q0 = 0; S.q1 = 0; S.k = ZB_MIN_MATCH; S.curk = 0; S.mcur = 0; S.curmin = 0; S.offc = 0; S.bt = 0; S.bk = 0; S.bm = 0; S.lit = 0;
-   bool finished = !active || S.i < lo, open = false;
-   ZbMatchRec nxt; uint32_t nlit = 0;
-#pragma unroll
-   for (int m = 0; m < ZB_NMATCH; m++) nxt.w[m] = 0;
-   if (!finished) { nxt = zb_load_rec(m0, S.i); nlit = t[S.i]; }
-   for (;;) {
-      const bool want_k = !finished && open && S.bnd != 0;
-      const bool want_adv = !finished && !want_k;
-      const uint32_t mk = __ballot_sync(0xffffffffu, want_k), ma = __ballot_sync(0xffffffffu, want_adv);
-      if (!(mk | ma)) break;
-      if (__popc(ma) >= ZB_SM_QUORUM || !mk) {
-         if (want_adv) {
-            if (open) {
-               mem.t_now = S.t;
-               zb_dpsm_close(S, mem, end, plit, plen, offcost, S.i < hi);
-               open = false;
-               if (S.i < lo) finished = true;
-            }
-            if (!finished) {
-               S.rec = nxt; S.lit = nlit;
-               if (S.i - 1 >= lo) { nxt = zb_load_rec(m0, S.i - 1); nlit = t[S.i - 1]; }
-               zb_dpsm_open(S, end, offcost);
-               open = true;
-            }
-         }
-      } else {
-         if (want_k) { mem.t_now = S.t; zb_dpsm_kstep(S, mem, plen); }
-         if (want_k && S.bnd != 0) zb_dpsm_kstep(S, mem, plen);
-      }
-   }
-   if (active) mem.rb.finish(far0, S.t);
-}
-
-__global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_sm_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
-                                                                  const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm, int16_t *sgt, int16_t *sgw,
-                                                                  size_t SS, uint16_t *far, int CD, int WU) {
-   __shared__ uint16_t ring_s[ZB_NR * ZB_DP_THREADS];
-   __shared__ ZbCostTab tab_s[ZB_DP_THREADS / 32];
-   __shared__ uint8_t offtab_s[ZB_DP_THREADS / 32][512];
-   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-   const long cw = (long)blockIdx.x * ZB_DP_THREADS + wi * 32;
-   if (cw >= ndch) return;                /* the whole warp */
-   const long c = cw + lane;
-   const uint32_t x0 = dcs[cw];
-   {
-      const uint32_t *src = (const uint32_t *)&tb[x0].cost; uint32_t *dstw = (uint32_t *)&tab_s[wi];
-      for (int e = lane; e < (int)(sizeof(ZbCostTab) / 4); e += 32) dstw[e] = src[e];
-   }
-   uint16_t *ring0 = ring_s + threadIdx.x;
-   for (int e = 0; e < ZB_NR; e++) ring0[e * ZB_DP_THREADS] = 0;
-   __syncwarp();
-   for (int e = lane; e < 512; e += 32) offtab_s[wi][e] = tab_s[wi].off[zb_off_sym(e < 256 ? (uint32_t)e + 1u : 257u + ((uint32_t)(e - 256) << 7))];
-   __syncwarp();
-   const bool uniform = __all_sync(0xffffffffu, (c < ndch ? dcs[c] : x0) == x0);
-   /* every lane stays in the warp loop (it votes); lanes without a chunk are inactive */
-   bool active = c < ndch;
-   const uint32_t x = active ? dcs[c] : x0;
-   const ZbSub s = sb[x];
-   if (pass > 0 && !s.is_dyn) active = false;
-   const uint32_t k = active ? (uint32_t)c - s.dchunk_base : 0u;
-   const uint32_t gb = wbs[s.win];
-   const uint8_t *t = T + wd[s.win].in_off;
-   const zb_match_t *m0 = mt + ((size_t)gb << 3);
-   const int lo = (int)(s.ps + k * CD);
-   const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
-   const int end = (int)s.pe;
-   int from = hi + WU; if (from > end) from = end;
-   const size_t rstride = (size_t)((CD + WU + 7) & ~7);      /* u16 per lane row: a multiple of 8, so the 16-byte groups are aligned */
-   uint16_t *far0 = far + ((size_t)blockIdx.x * ZB_DP_THREADS + threadIdx.x) * rstride;
-   if (uniform) zb_dp_sm_chunk<true>(active, t, m0, tab_s[wi].lit, tab_s[wi].len, offtab_s[wi], lo, hi, from, end, ring0, far0, (uint32_t *)(bm + gb));
-   else zb_dp_sm_chunk<false>(active, t, m0, tb[x].cost.lit, tb[x].cost.len, tb[x].cost.off, lo, hi, from, end, ring0, far0, (uint32_t *)(bm + gb));
-   if (!active) return;
-   /* both signatures out of the cost row (position p was done at step from - 1 - p) */
-   const int tw = from - hi, tall = from - lo;
-   const uint32_t cw_ = tw > 0 ? (uint32_t)far0[tw - 1] : 0u, ct_ = tall > 0 ? (uint32_t)far0[tall - 1] : 0u;
-   zb_dp_signature(sgw + (size_t)c, SS, far0, hi, from, end, tw, cw_, true, 1);
-   zb_dp_signature(sgt + (size_t)c, SS, far0, lo, from, end, tall, ct_, false, 1);
 }
 
 /* ---- repair of wrong chunks: the same recurrence, ONE WARP per chain ----
@@ -1605,15 +1518,16 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
                M = m + 1;
                const int ml = len0 < rem ? len0 : rem;
                const bool lg = len0 >= ZB_LEAVE_ALONE;
-               int fixed = (int)tab.off[zb_off_sym((uint32_t)off0)];
+               const uint32_t osym = (uint32_t)zb_off_sym((uint32_t)off0);
+               int fixed = (int)tab.off[osym];
                if (lg) { int lidx = ml - ZB_MIN_MATCH; if (lidx < 0 || lidx > 255) lidx = 255; fixed += (int)tab.len[lidx]; }
                else if (ml > K) K = ml;
-               inf = (uint32_t)ml | ((lg ? 1u : 0u) << 9) | ((uint32_t)fixed << 10) | ((uint32_t)off0 << 16);
+               inf = (uint32_t)ml | ((lg ? 1u : 0u) << 9) | ((uint32_t)fixed << 10) | (osym << 16) | ((uint32_t)m << 21);      /* bits 16..: what the choice word needs */
                /* far candidate: a leave-alone match that lands past the block's top position is already final */
                if (lg && ml > lane) {
                   int idx = s - (ml - 1 - lane); if (idx < 0) idx += ZB_RING;
                   const int total = fixed + (int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base);
-                  if (total < farE) { farE = total; farw = (uint32_t)ml | ((uint32_t)off0 << 16); }
+                  if (total < farE) { farE = total; farw = (uint32_t)ml | (osym << 9) | ((uint32_t)m << 14); }
                } else far_ok = false;
             }
             sh.info[lane][m] = inf;
@@ -1701,7 +1615,7 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
          }
          base = (base + (uint32_t)bestc) & 0xffffu;
          if (lane == 0) ring[s] = (uint16_t)base;
-         if (lane == x) outw = (uint32_t)bl | ((uint32_t)bo << 16);
+         if (lane == x) outw = bl ? ((uint32_t)bl | (((uint32_t)bo & 31u) << 9) | (((uint32_t)bo >> 5) << 14)) : 0u;      /* choice word, as zb_parse_dp_k writes it */
          __syncwarp();
       }
       if (lane < nb_pos) ((uint32_t *)best)[i0 - lane] = outw;
@@ -1817,8 +1731,8 @@ __global__ void __launch_bounds__(ZB_PH_THREADS) zb_path_hist_k(long npch, const
             return w;
          };
 #define ZB_PH_LD(k_) (g + (k_) < hi_i ? *(const uint4 *)(bw + g + (k_)) : make_uint4(0u, 0u, 0u, 0u))
-#define ZB_PH_ONE(w_, j_, tw_) do { const int pp_ = g + (j_); if (pp_ == next && pp_ < hi_i) { const uint32_t ln_ = (w_) & 0xffffu; \
-            if (ln_ >= ZB_MIN_MATCH) { atomicAdd(lc + zb_len_sym(ln_ - ZB_MIN_MATCH), 1); atomicAdd(oc + zb_off_sym((w_) >> 16), 1); next += (int)ln_; } \
+#define ZB_PH_ONE(w_, j_, tw_) do { const int pp_ = g + (j_); if (pp_ == next && pp_ < hi_i) { const uint32_t ln_ = (w_) & 0x1ffu;      /* choice word: k | sym << 9 | m << 14 */ \
+            if (ln_ >= ZB_MIN_MATCH) { atomicAdd(lc + zb_len_sym(ln_ - ZB_MIN_MATCH), 1); atomicAdd(oc + (((w_) >> 9) & 31u), 1); next += (int)ln_; } \
             else { atomicAdd(lc + (((tw_) >> (8 * (j_))) & 0xffu), 1); next++; } } } while (0)
 #define ZB_PH_PROC(v, tw_) do { ZB_PH_ONE((v).x, 0, tw_); ZB_PH_ONE((v).y, 1, tw_); ZB_PH_ONE((v).z, 2, tw_); ZB_PH_ONE((v).w, 3, tw_); g += 4; } while (0)
          uint4 va = ZB_PH_LD(0), vb = ZB_PH_LD(4), vc = ZB_PH_LD(8);
@@ -1884,22 +1798,34 @@ inline void ZbPipe::stage_parse() {
    /* chunk lists */
    zb_launch(st, 1, ZB_LAMBDA(long) {
       uint32_t d = 0, p = 0;
+      uint32_t curg = 0xffffffffu, cnt = 0, mx = 1;      /* most sub-blocks any group of 128 parse chunks (one CTA of zb_parse_dp_k) touches */
       for (int x = 0; x < ns; x++) {
          uint32_t size = sb[x].pe - sb[x].ps;
-         sb[x].dchunk_base = d; sb[x].ndchunk = (size + CD - 1) / CD; d += sb[x].ndchunk;
+         const uint32_t nd = (size + CD - 1) / CD;
+         sb[x].dchunk_base = d; sb[x].ndchunk = nd;
+         if (nd) {
+            const uint32_t g0 = d >> 7, g1 = (d + nd - 1) >> 7;
+            if (g0 == curg) cnt++; else { curg = g0; cnt = 1; }
+            if (cnt > mx) mx = cnt;
+            if (g1 != g0) { curg = g1; cnt = 1; }
+         }
+         d += nd;
          sb[x].pchunk_base = p; sb[x].npchunk = (size + ZB_CP - 1) / ZB_CP; p += sb[x].npchunk;
       }
-      cn[4] = d; cn[5] = p;
+      cn[4] = d; cn[5] = p; cn[6] = mx;
    });
-   uint32_t hc[2];
-   zb_d2h(st, hc, cn + 4, 8); zb_sync(st);
+   uint32_t hc[3];
+   zb_d2h(st, hc, cn + 4, 12); zb_sync(st);
    const long ndch = hc[0], npch = hc[1];
    dchunk_sub.need(ndch + 1); pchunk_sub.need(npch + 1); best.need(P);
+#ifndef ZB_EMU
+   cand.need((size_t)P * 4);
+#endif
    sig_true.need((size_t)(ndch + 1) * 260); sig_warm.need((size_t)(ndch + 1) * 260); sig_new.need((size_t)(ndch + 1) * 260); dok.need(ndch + 1); dbad.need(ndch + 1);
    pentry.need(npch + 1); pbits.need(npch + 1);
 #ifndef ZB_EMU
    exitc.need((size_t)(npch + 1) * ZB_EXROW);
-   dpfar.need((size_t)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS) * (size_t)(CD + WU + 8) * ZB_DP_THREADS + 64);   /* + 8: per-lane rows of the decoupled-lane kernel are padded to 8 steps */
+   dpfar.need((size_t)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS) * (size_t)(CD + WU + 8) * ZB_DP_THREADS + 64);   
 #endif
    if (zb_failed()) return;
    uint32_t *dcs = dchunk_sub.p, *pcs = pchunk_sub.p;
@@ -1909,6 +1835,22 @@ inline void ZbPipe::stage_parse() {
    });
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
    const zb_match_t *mt = match.p; zb_match_t *bm = best.p;
+#ifndef ZB_EMU
+   /* candidate records (once: the match lists do not change over the passes) and the parse kernel's shared memory */
+   const int dp_nslot = (int)(hc[2] < 1 ? 1 : (hc[2] > ZB_DP_THREADS ? ZB_DP_THREADS : hc[2]));
+   const size_t dp_smem = (size_t)ZB_NR * ZB_DP_THREADS * 2 + (size_t)dp_nslot * sizeof(ZbDpTab);
+   {  /* the limit is a per-function global: always the largest configuration, so concurrent host threads cannot undercut each other */
+      const size_t smax = (size_t)ZB_NR * ZB_DP_THREADS * 2 + (size_t)ZB_DP_THREADS * sizeof(ZbDpTab);
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+   }
+   if (npch > 0) {
+      if (g_zb_prof_on) { zb_tag("parse_cand"); zb_prof_begin(0, st); }
+      zb_cand_k<<<(unsigned)npch, 256, 0, st>>>(npch, sb, pcs, wbs, mt, (uint4 *)cand.p);
+      if (g_zb_prof_on) zb_prof_end(st);
+      zb_count_launch(1);
+      ZB_CUDA_CHECK(cudaGetLastError());
+   }
+#endif
    const size_t SS = (size_t)ndch + 1;   /* signatures are stored [entry][chunk]: neighbouring chunks' accesses coalesce */
    int16_t *sgt = sig_true.p, *sgw = sig_warm.p, *sgn = sig_new.p; uint8_t *ok = dok.p; uint32_t *bad = dbad.p; (void)sgn;
    uint16_t *ex = exitoff.p; uint32_t *pen = pentry.p;
@@ -1921,17 +1863,8 @@ inline void ZbPipe::stage_parse() {
       if (ndch > 0) {
          if (g_zb_prof_on) { zb_tag("parse_dp"); zb_prof_begin(0, st); }
          {
-            /* register budget variants (ZULTRA_CUDA_DP_MINB = 8/7/6 asks for that many CTAs per SM: 64/72/72 registers; default:
-               the compiler's 56).  Measured on enwik100m: 0 and 8 equal (18.6 ms), 7 slower (21.5 ms), 10 CTAs at 48
-               registers slower still (25.6 ms). */
-            static const int minb = getenv("ZULTRA_CUDA_DP_MINB") ? atoi(getenv("ZULTRA_CUDA_DP_MINB")) : 0;
-            static const int use_sm = getenv("ZULTRA_CUDA_DP_SM") ? atoi(getenv("ZULTRA_CUDA_DP_SM")) : 0;
             const unsigned grid = (unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS);
-            if (use_sm) zb_parse_dp_sm_k<<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
-            else if (minb == 6) zb_parse_dp_k<6><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
-            else if (minb == 7) zb_parse_dp_k<7><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
-            else if (minb == 8) zb_parse_dp_k<8><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
-            else zb_parse_dp_k<0><<<grid, ZB_DP_THREADS, 0, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, mt, bm, sgt, sgw, SS, dpfar.p, CD, WU);
+            zb_parse_dp_k<<<grid, ZB_DP_THREADS, dp_smem, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, (const uint4 *)cand.p, (uint32_t *)bm, sgt, sgw, SS, dpfar.p, CD, WU, dp_nslot);
          }
          if (g_zb_prof_on) zb_prof_end(st);
          zb_count_launch(1);
@@ -1939,12 +1872,12 @@ inline void ZbPipe::stage_parse() {
       }
 #else
       zb_tag("parse_dp");
-      const bool emu_sm = getenv("ZB_EMU_DP_SM") != 0;    /* host build only: run the chunks through the lane state machine (zb_dpsm_*) */
+      const bool emu_lean = getenv("ZB_EMU_DP_LEAN") != 0;    /* host build only: run the chunks through the compact candidate records (zb_cand_pack / zb_dp_eval), as zb_parse_dp_k does */
       zb_launch(st, ndch, ZB_LAMBDA(long c) {
          const ZbSub s = sb[dcs[c]];
          if (pass > 0 && !s.is_dyn) return;
-         if (emu_sm) {
-            if (c == 0 && pass == 0 && getenv("ZB_EMU_DP_SM")[0] == '2') fprintf(stderr, "parse: lane state machine path\n");
+         if (emu_lean) {
+            if (c == 0 && pass == 0 && getenv("ZB_EMU_DP_LEAN")[0] == '2') fprintf(stderr, "parse: compact candidate record path\n");
             const uint32_t kc = (uint32_t)c - s.dchunk_base;
             const uint32_t gb = wbs[s.win];
             const uint8_t *t = T + wd[s.win].in_off;
@@ -1954,28 +1887,28 @@ inline void ZbPipe::stage_parse() {
             const int end = (int)s.pe;
             int from = hi + WU; if (from > end) from = end;
             const ZbCostTab &ct = tb[dcs[c]].cost;
-            struct Mem {
-               std::vector<uint32_t> v; zb_match_t *bp;
-               uint32_t cost(int tt) const { return tt >= 0 ? v[(size_t)tt] : 0u; }
-               void put(int t, uint32_t x) { if (x > 0xffffu) { fprintf(stderr, "dp cost overflow\n"); abort(); } v[(size_t)t] = x; }
-               void best(int i, uint32_t w) { bp[i].length = (uint16_t)(w & 0xffffu); bp[i].offset = (uint16_t)(w >> 16); }
-            } mem;
-            mem.v.assign((size_t)(from - lo) + 1, 0u); mem.bp = bm + gb;
-            auto offcost = [&](uint32_t off) -> uint32_t { return ct.off[zb_off_sym(off)]; };
-            ZbDpLane S; memset(&S, 0, sizeof(S));
-            S.i = from - 1; S.t = 0; S.cprev = 0;
-            while (S.i >= lo) {
-               S.rec = zb_load_rec(m0, S.i); S.lit = t[S.i];
-               zb_dpsm_open(S, end, offcost);
-               while (S.bnd) zb_dpsm_kstep(S, mem, ct.len);
-               zb_dpsm_close(S, mem, end, ct.lit, ct.len, offcost, S.i < hi);
+            std::vector<uint32_t> v((size_t)(from - lo) + 1, 0u);      /* cost of step tt (position from - 1 - tt) */
+            uint32_t cprev = 0;
+            int tt = 0;
+            for (int i = from - 1; i >= lo; i--, tt++) {
+               const ZbCand cd = zb_cand_pack(zb_load_rec(m0, i), end - i);
+               auto costat = [&](int k) -> uint32_t { const int q = tt - k; return q >= 0 ? v[(size_t)q] : 0u; };
+               uint32_t ch = 0;
+               const uint32_t cc = zb_dp_eval(cd, ct.lit[t[i]], cprev, ct, costat, &ch);
+               if (cc > 0xffffu) { fprintf(stderr, "dp cost overflow\n"); abort(); }
+               v[(size_t)tt] = cc; cprev = cc;
+               if (i < hi) {      /* the choice word, resolved the way zb_choice_k does */
+                  zb_match_t b; b.length = 0; b.offset = 0;
+                  if (ch) { b.length = (uint16_t)(ch & 511u); b.offset = m0[((size_t)i << 3) + (ch >> 14)].offset;
+                            if ((uint32_t)zb_off_sym(b.offset) != ((ch >> 9) & 31u)) { fprintf(stderr, "choice symbol mismatch\n"); abort(); } }
+                  bm[gb + i] = b;
+               }
             }
-            /* signatures from the cost row, as zb_dp_signature does on the device */
             const int tw = from - hi, tall = from - lo;
-            const uint32_t bw_ = tw > 0 ? mem.v[(size_t)tw - 1] : 0u, bt_ = tall > 0 ? mem.v[(size_t)tall - 1] : 0u;
+            const uint32_t bw_ = tw > 0 ? v[(size_t)tw - 1] : 0u, bt_ = tall > 0 ? v[(size_t)tall - 1] : 0u;
             int16_t *sw = sgw + (size_t)c, *sg = sgt + (size_t)c;
             for (int q = 0; q <= ZB_MAX_MATCH; q++) {
-               const uint32_t vw = mem.cost(tw - 1 - q), vt = mem.cost(tall - 1 - q);
+               const uint32_t vw = tw - 1 - q >= 0 ? v[(size_t)(tw - 1 - q)] : 0u, vt = tall - 1 - q >= 0 ? v[(size_t)(tall - 1 - q)] : 0u;
                sw[(size_t)q * SS] = (hi + q <= end && hi + q <= from) ? (int16_t)(uint16_t)(vw - bw_) : (int16_t)0;
                sg[(size_t)q * SS] = (lo + q <= end) ? (int16_t)(uint16_t)(vt - bt_) : (int16_t)0;
             }
@@ -2179,6 +2112,15 @@ inline void ZbPipe::stage_parse() {
          sb[x] = s;
       }, 64);
    }
+#ifndef ZB_EMU
+   if (npch > 0) {      /* choice words -> {length, offset} */
+      if (g_zb_prof_on) { zb_tag("parse_choice"); zb_prof_begin(0, st); }
+      zb_choice_k<<<(unsigned)npch, 256, 0, st>>>(npch, sb, pcs, wbs, mt, (uint32_t *)bm);
+      if (g_zb_prof_on) zb_prof_end(st);
+      zb_count_launch(1);
+      ZB_CUDA_CHECK(cudaGetLastError());
+   }
+#endif
    /* P7: matches that are cheaper as literals (blockdeflate.c:410-458), dynamic sub-blocks only */
    zb_launch(st, npch, ZB_LAMBDA(long c) {
       const uint32_t x = pcs[c];
@@ -2548,7 +2490,7 @@ inline void ZbPipe::release_all() {
    gtokcnt.release(); gtokbase.release(); tokpos.release(); wtok.release(); wtokbase.release(); wintbase.release(); ph.release();
    gchunk_first.release(); gchunk_win.release(); nodesA.release(); nodesB.release(); nodehist.release(); chk_stat.release(); chk_flag.release();
    chk_delta.release(); chk_node.release(); wsplit.release(); wnsplit.release(); sub.release(); tabs.release(); dchunk_sub.release(); pchunk_sub.release();
-   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); dbad.release(); pentry.release(); pbits.release(); dpfar.release(); hin.release(); hout.release(); wsubcnt.release(); wsubbase.release(); out.release(); sout.release();
+   best.release(); sig_true.release(); sig_warm.release(); sig_new.release(); dok.release(); dbad.release(); pentry.release(); pbits.release(); cand.release(); dpfar.release(); hin.release(); hout.release(); wsubcnt.release(); wsubbase.release(); out.release(); sout.release();
 }
 
 
