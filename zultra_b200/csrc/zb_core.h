@@ -476,7 +476,7 @@ ZB_HD int zb_mf_scan(const uint32_t *words, int n, int r, uint32_t i, const uint
       lvl = l; steps++;
       ZB_STAT(g_zb_rank_steps++);
       int p;
-      if (lL >= lR) {
+      if (lL > lR || (lL == lR && (steps & 1))) {      /* ties alternate: see zb_mf_scan_k */
          const uint32_t w = words[L];
          p = (int)(w & ZB_POS_MASK);
          const uint32_t wl = w >> ZB_POS_BITS;

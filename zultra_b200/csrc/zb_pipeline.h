@@ -387,29 +387,44 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
    if (threadIdx.x == 0) { next_m = 0; nq = 0; zb_smw[0] = 0; words[n] = 0; }
    __syncthreads();
    const uint32_t gbase = wbs[t.win];
+   const int lane = threadIdx.x & 31;
    bool busy = false, drained = false, moved = false;
-   uint32_t m = 0, lL = 0, lR = 0, lvl = 0, first_rec = 0, maxlen = 0;
-   int i = 0, L = 0, R = 0, best = -1, nm = 0, steps = 0;
+   uint32_t m = 0, lL = 0, lR = 0, lvl = 0, maxlen = 0, rec0 = 0, rec1 = 0;
+   int i = 0, L = 0, R = 0, best = -1, nm = 0, steps = 0, gap = 0, thr = 0;
    uint32_t *dst = 0;
-#define ZB_MF_EMIT(v_) do { uint32_t v__ = (v_); if ((v__ & 0xffffu) > maxlen) v__ = (v__ & 0xffff0000u) | maxlen; if (nm == 0) first_rec = v__; dst[nm++] = v__; } while (0)
+   /* the first two records of a position stay in registers (most positions have no more) and leave with one 8-byte store when
+      the walk ends; further records go straight to their slot */
+#define ZB_MF_EMIT(v_) do { uint32_t v__ = (v_); if ((v__ & 0xffffu) > maxlen) v__ = (v__ & 0xffff0000u) | maxlen; \
+      if (nm == 0) rec0 = v__; else if (nm == 1) rec1 = v__; else dst[nm] = v__; nm++; } while (0)
+   /* the rank walk hands over to the text walk (kernel B) once steps >= ts_min and gap = i - 1 - best <= ts_mul * steps; the
+      product is kept as a running sum (thr), the gap changes only when `best` moves */
    for (;;) {
-      if (!busy && !drained) {
-         m = atomicAdd(&next_m, 1u);
-         if (m >= nmain) drained = true;
-         else {
-            busy = true;
-            const int r = (int)rom[m];
-            i = (int)(nlook + m);
-            L = r - 1; R = r + 1;
-            lL = words[r] >> ZB_POS_BITS;     /* words[0] has LCP 0 */
-            lR = words[R] >> ZB_POS_BITS;     /* words[n] = 0 */
-            best = (i > ZB_MAX_OFFSET ? i - ZB_MAX_OFFSET : 0) - 1;   /* p > best also enforces the 32768 limit */
-            nm = 0; lvl = 0; moved = false; steps = 0; first_rec = 0;
-            maxlen = t.wlen - (t.m0 + m);     /* matchfinder.c:276-280 (LAST_LITERALS = 0) */
-            dst = (uint32_t *)(mt + ((size_t)(gbase + t.m0 + m) << 3));
+      {  /* positions are handed out warp by warp: one shared-memory atomic for all lanes that need one */
+         const uint32_t need = __ballot_sync(0xffffffffu, !busy && !drained);
+         if (need) {
+            uint32_t base = 0;
+            if (lane == __ffs((int)need) - 1) base = atomicAdd(&next_m, (uint32_t)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, __ffs((int)need) - 1);
+            if (!busy && !drained) {
+               m = base + (uint32_t)__popc(need & ((1u << lane) - 1u));
+               if (m >= nmain) drained = true;
+               else {
+                  busy = true;
+                  const int r = (int)rom[m];
+                  i = (int)(nlook + m);
+                  L = r - 1; R = r + 1;
+                  lL = words[r] >> ZB_POS_BITS;     /* words[0] has LCP 0 */
+                  lR = words[R] >> ZB_POS_BITS;     /* words[n] = 0 */
+                  best = (i > ZB_MAX_OFFSET ? i - ZB_MAX_OFFSET : 0) - 1;   /* p > best also enforces the 32768 limit */
+                  nm = 0; lvl = 0; moved = false; steps = 0; rec0 = 0; rec1 = 0;
+                  gap = i - 1 - best; thr = 0;
+                  maxlen = t.wlen - (t.m0 + m);     /* matchfinder.c:276-280 (LAST_LITERALS = 0) */
+                  dst = (uint32_t *)(mt + ((size_t)(gbase + t.m0 + m) << 3));
+               }
+            }
          }
       }
-      if (__all_sync(0xffffffffu, drained && !busy)) break;
+      if (__all_sync(0xffffffffu, !busy)) break;      /* every lane is drained */
       bool fin = false;
       if (busy) {
 #pragma unroll 1
@@ -421,19 +436,23 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
                if (nm == ZB_NMATCH) { fin = true; break; }
             }
             if (l < ZB_MIN_MATCH) { fin = true; break; }
-            if ((steps & 1) == 0 && steps >= ts_min && i - 1 - best <= ts_mul * steps) {   /* the rest is cheaper read from the text: kernel B */
+            if (steps >= ts_min && gap <= thr) {   /* the rest is cheaper read from the text: kernel B */
                const uint32_t at = atomicAdd(&nq, 1u);
+               if (nm == 1) dst[0] = rec0; else if (nm >= 2) *(uint2 *)dst = make_uint2(rec0, rec1);      /* kernel B fills the slots from nm on */
                queue[3 * at] = m | ((uint32_t)nm << 13) | ((moved ? 1u : 0u) << 17) | (lvl << 18);
                queue[3 * at + 1] = l | ((uint32_t)(i - 1 - best) << 9);
-               queue[3 * at + 2] = first_rec;
+               queue[3 * at + 2] = rec0;
                busy = false;
                break;
             }
-            lvl = l; steps++;
+            lvl = l; steps++; thr += ts_mul;
             /* one step to the side with the larger running LCP, without a branch (the two sides would split the warp): the
                left side's new LCP is in the word it consumes, the right side's in the word after it (never read past the
                list: with R at the end sentinel lR is 0 and the left side is taken) */
-            const bool goL = lL >= lR;
+            /* equal running LCPs (both clamped at 258 inside a long byte run or periodic stretch): alternate, so that the side
+               holding the EARLIER positions is reached at once - always preferring one side walked thousands of later
+               positions of the run before the text-walk hand-over (45 % of all rank steps on the mozilla-shaped config) */
+            const bool goL = lL > lR || (lL == lR && (steps & 1));
             const int at = goL ? L : R;
             const uint32_t w = words[at], w2 = words[at + 1];
             const uint32_t wl = (goL ? w : w2) >> ZB_POS_BITS;
@@ -445,15 +464,19 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
             if (p < i && p > best) {
                best = p; moved = true;
                if (best == i - 1) { ZB_MF_EMIT(lvl | (1u << 16)); fin = true; break; }
+               gap = i - 1 - best;
             }
          }
       }
       if (fin) {
-         for (int z = nm; z < ZB_NMATCH; z++) dst[z] = 0u;
+         /* slots 0 and 1 from the registers, the unused ones zeroed (matchfinder.c:271-274) */
+         *(uint2 *)dst = make_uint2(rec0, nm >= 2 ? rec1 : 0u);
+         if (nm <= 2) { *(uint2 *)(dst + 2) = make_uint2(0u, 0u); *(uint4 *)(dst + 4) = make_uint4(0u, 0u, 0u, 0u); }
+         else for (int z = nm; z < ZB_NMATCH; z++) dst[z] = 0u;
          const uint32_t p = t.m0 + m;
-         const uint32_t l0 = first_rec & 0xffffu;
+         const uint32_t l0 = rec0 & 0xffffu;
          gl[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)l0 : (uint16_t)1;
-         go[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)(first_rec >> 16) : (uint16_t)0;
+         go[gbase + p] = l0 >= ZB_MIN_MATCH ? (uint16_t)(rec0 >> 16) : (uint16_t)0;
          busy = false;
       }
    }
