@@ -84,7 +84,8 @@ int zultra_cuda_ctx_set_devices(zultra_cuda_ctx_t *pCtx, int nDevices);
  * checksum of the chunk's own bytes from the initial value, per chunk.  chunks_emit: entering phase per chunk (from the
  * composed maps of ALL ranks); leaves chunk i's bitstream at *ppDevOut + pnOutOffset[i] (device memory owned by the context,
  * valid until its next call), pnOutBits[i] bits including the entering ones.  stitch_device (the gathering rank): OR-merges
- * parts at their absolute bit offsets into a zeroed device buffer - the "shift and concatenate" of the stitch.
+ * parts at their absolute bit offsets into a zeroed device buffer - the "shift and concatenate" of the stitch; every source
+ * part must be followed by at least 8 readable zero bytes (the spans zultra_cuda_chunks_emit leaves are).
  */
 int zultra_cuda_chunks_prepare(zultra_cuda_ctx_t *pCtx, const void *pDevInData, int nChunks, const size_t *pnChunkOffset, const int *pnChunkHistory,
                                const size_t *pnChunkSize, const int *pnChunkFinalize, unsigned int nMaxBlockSize, unsigned int nFlags,

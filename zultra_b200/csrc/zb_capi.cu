@@ -82,7 +82,7 @@ int zultra_cuda_ctx_create(zultra_cuda_ctx_t **pp, int device) {
    zb_trace("ctx_create: stream created (primary context up)");
    {  /* tuning knobs (never change the output) */
       const char *e;
-      if ((e = getenv("ZULTRA_CUDA_PARSE_CD")) && atoi(e) >= 512) c->pipe.parse_cd = atoi(e);
+      if ((e = getenv("ZULTRA_CUDA_PARSE_CD")) && atoi(e) >= 64) c->pipe.parse_cd = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_PARSE_WU")) && atoi(e) >= 258) c->pipe.parse_wu = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_TILE")) && atoi(e) >= 256) c->tile = (unsigned)atoi(e);
       if ((e = getenv("ZULTRA_CUDA_TS_MIN")) && atoi(e) >= 1) c->pipe.mf_ts_min = atoi(e);
@@ -534,47 +534,52 @@ int zultra_cuda_chunks_emit(zultra_cuda_ctx_t *c, const unsigned int *in_bits, v
    return ctx_leave(c, rc ? ZULTRA_CUDA_ERR_CUDA : 0);
 }
 
-/* The stitch on one device: part i = src[i][0 .. ceil((phase_i + nbits_i) / 8)) bytes whose first bit sits at phase_i = dst_bit[i] & 7 of its
-   first byte (low bits zero) goes to byte dst_bit[i] >> 3 of dst; bytes two parts share are OR-merged.  dst must be zero where parts
-   meet: the caller clears it (cudaMemsetAsync) before the call.  One thread per aligned 4-byte word of the destination span of a part. */
-__global__ void zb_stitch_k(uint32_t *dst, int nparts, const uint8_t *const *src, const unsigned long long *dst_bit, const unsigned long long *nbits, const unsigned long long *word_base) {
-   const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-   int lo = 0, hi = nparts - 1;
-   if (g >= word_base[nparts]) return;
-   while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (word_base[mid] <= g) lo = mid; else hi = mid - 1; }
-   const unsigned long long b0 = dst_bit[lo] >> 3;                                   /* first destination byte of the part */
-   const unsigned long long nb = ((dst_bit[lo] & 7) + nbits[lo] + 7) >> 3;           /* bytes of the part */
-   const unsigned long long w = (b0 >> 2) + (g - word_base[lo]);                     /* destination word */
-   const long long s0 = (long long)(w << 2) - (long long)b0;                         /* source byte that lands in byte 0 of the word */
-   const uint8_t *sp = src[lo];
-   uint32_t v = 0;
+/* The stitch on one device: part i = src[i][0 .. ceil((phase_i + nbits_i) / 8)) bytes, its first bit at phase_i = dst_bit[i] & 7 of
+   its first byte (the bits below are zero), goes to byte dst_bit[i] >> 3 of dst; bytes two parts share are OR-merged.  dst must be
+   zero where parts meet: the caller clears it before the call.  Grid: y = part, x strides over the aligned 32-bit words of the
+   part's destination span; a word comes out of two aligned source words and a funnel shift, interior words are plain stores,
+   the first and last word of a part go through atomicOr.  Every source span is followed by >= 8 readable zero bytes (the
+   pipeline's output spans are; zultra_cuda.h states it for other callers). */
+struct ZbStitchPart { const uint8_t *src; unsigned long long dst_bit, nbits; };
+__global__ void __launch_bounds__(256) zb_stitch_k(uint32_t *dst, const ZbStitchPart *parts) {
+   const ZbStitchPart p = parts[blockIdx.y];
+   const unsigned long long b0 = p.dst_bit >> 3, nb = ((p.dst_bit & 7) + p.nbits + 7) >> 3;
+   if (!nb) return;
+   const unsigned long long w0 = b0 >> 2, nwords = ((b0 + nb + 3) >> 2) - w0;
+   for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < nwords; j += (unsigned long long)gridDim.x * blockDim.x) {
+      const long long s0 = (long long)((w0 + j) << 2) - (long long)b0;      /* source byte that lands in byte 0 of this word (< 0 only for j = 0) */
+      uint32_t v;
+      if (s0 >= 0 && (unsigned long long)s0 + 4 <= nb) {
+         const uintptr_t a = (uintptr_t)(p.src + s0);
+         const uint32_t *pa = (const uint32_t *)(a & ~(uintptr_t)3);
+         v = (a & 3) ? __funnelshift_r(pa[0], pa[1], (uint32_t)(a & 3) << 3) : pa[0];
+      } else {
+         v = 0;
 #pragma unroll
-   for (int k = 0; k < 4; k++) { const long long q = s0 + k; if (q >= 0 && (unsigned long long)q < nb) v |= (uint32_t)sp[q] << (8 * k); }
-   if (!v) return;
-   const bool edge = s0 < 1 || (unsigned long long)(s0 + 4) >= nb;                   /* may share bytes with a neighbouring part */
-   if (edge) atomicOr(dst + w, v); else dst[w] = v;
+         for (int k = 0; k < 4; k++) { const long long q = s0 + k; if (q >= 0 && (unsigned long long)q < nb) v |= (uint32_t)p.src[q] << (8 * k); }
+      }
+      if (!v) continue;
+      if (s0 < 1 || (unsigned long long)s0 + 4 >= nb) atomicOr(dst + w0 + j, v); else dst[w0 + j] = v;      /* an edge word may share bytes with a neighbouring part */
+   }
 }
 
 int zultra_cuda_stitch_device(zultra_cuda_ctx_t *c, void *dev_dst, int nparts, const void *const *dev_src, const unsigned long long *dst_bit, const unsigned long long *nbits) {
    int rc = ctx_enter(c);
    if (rc) return rc;
-   if (!dev_dst || nparts <= 0 || !dev_src || !dst_bit || !nbits || ((uintptr_t)dev_dst & 3)) return ZULTRA_CUDA_ERR_ARG;
-   std::vector<unsigned long long> h((size_t)4 * nparts + 1);
-   unsigned long long words = 0;
+   if (!dev_dst || nparts <= 0 || nparts > 65535 || !dev_src || !dst_bit || !nbits || ((uintptr_t)dev_dst & 3)) return ZULTRA_CUDA_ERR_ARG;
+   std::vector<ZbStitchPart> h((size_t)nparts);
+   unsigned long long maxwords = 0;
    for (int i = 0; i < nparts; i++) {
-      const unsigned long long b0 = dst_bit[i] >> 3, nb = ((dst_bit[i] & 7) + nbits[i] + 7) >> 3;
-      h[i] = (unsigned long long)(uintptr_t)dev_src[i]; h[nparts + i] = dst_bit[i]; h[2 * nparts + i] = nbits[i]; h[3 * nparts + i] = words;
-      words += nb ? ((b0 + nb + 3) >> 2) - (b0 >> 2) : 0;
+      h[i].src = (const uint8_t *)dev_src[i]; h[i].dst_bit = dst_bit[i]; h[i].nbits = nbits[i];
+      maxwords = std::max(maxwords, (((dst_bit[i] & 7) + nbits[i] + 7) >> 5) + 2);
    }
-   h[4 * (size_t)nparts] = words;
-   c->pipe.ck_rng.need(h.size());
+   c->pipe.ck_rng.need(((size_t)nparts * sizeof(ZbStitchPart) + 7) / 8);
    if (zb_failed()) return ctx_leave(c, ZULTRA_CUDA_ERR_CUDA);
-   zb_h2d(c->pipe.st, c->pipe.ck_rng.p, h.data(), h.size() * 8);
-   const unsigned long long *d = (const unsigned long long *)c->pipe.ck_rng.p;
-   if (words) {
-      zb_stitch_k<<<(unsigned)((words + 255) / 256), 256, 0, c->pipe.st>>>((uint32_t *)dev_dst, nparts, (const uint8_t *const *)d, d + nparts, d + 2 * nparts, d + 3 * nparts);
-      zb_count_launch(1);
-   }
+   zb_h2d(c->pipe.st, c->pipe.ck_rng.p, h.data(), h.size() * sizeof(ZbStitchPart));
+   const unsigned gx = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>((maxwords + 1023) / 1024, 1), 4096);
+   zb_stitch_k<<<dim3(gx, (unsigned)nparts), 256, 0, c->pipe.st>>>((uint32_t *)dev_dst, (const ZbStitchPart *)c->pipe.ck_rng.p);
+   zb_count_launch(1);
+   ZB_CUDA_CHECK(cudaGetLastError());
    zb_sync(c->pipe.st);
    return ctx_leave(c, 0);
 }

@@ -165,10 +165,22 @@ ZB_HD void zb_huff_lengths(const int *cnt, int nsym, int *len, uint32_t *key) {
 #undef ZB_SETW
 }
 
-/* order[] = symbols with len != 0 sorted by (len, index) ascending; returns count.  Lengths <= 287. */
+/* order[] = symbols with len != 0 sorted by (len, index) ascending; returns count.  Lengths <= 287.  Counting sort (one
+   pass to count, one to place): limited codes have <= 15 distinct lengths, the per-length rescans of a naive selection were a
+   fifth of a table build. */
 ZB_HD int zb_order_by_len(const int *len, int nsym, int16_t *order) {
-   int n = 0, maxl = 0;
+   int maxl = 0;
    for (int i = 0; i < nsym; i++) if (len[i] > maxl) maxl = len[i];
+   if (maxl <= 31) {
+      uint16_t start[32];
+      for (int l = 0; l <= maxl; l++) start[l] = 0;
+      for (int i = 0; i < nsym; i++) start[len[i]]++;
+      int run = 0;
+      for (int l = 1; l <= maxl; l++) { const int c = start[l]; start[l] = (uint16_t)run; run += c; }
+      for (int i = 0; i < nsym; i++) { const int l = len[i]; if (l) order[start[l]++] = (int16_t)i; }
+      return run;
+   }
+   int n = 0;
    for (int l = 1; l <= maxl; l++)
       for (int i = 0; i < nsym; i++)
          if (len[i] == l) order[n++] = (int16_t)i;
@@ -249,18 +261,23 @@ ZB_HD void zb_rle_scan(const uint8_t *cl, int n, unsigned mask, V &v) {
    while (i < n) {
       int run = 1;
       while (i + run < n && cl[i + run] == cl[i]) run++;
+      /* What the repeat codes leave of a run is re-scanned by the reference one symbol per round (huffencoder.c:450-453), and no
+         repeat code can apply to it any more (the loops below only stop once the remainder is too short for the codes the mask
+         allows): it comes out as plain symbols.  They are emitted here at once - same tokens, but linear instead of quadratic in
+         the run length when the mask disables a repeat code (a 128-long zero run under mask 0 cost 8 000 steps per scan). */
       if (cl[i] == 0) {
          if (run >= 3) {
             while (run >= 11 && (mask & 4)) { int m = run > 138 ? 138 : run; v.rep(18, m - 11, 7); run -= m; i += m; }
             while (run >= 3 && (mask & 2)) { int m = run > 10 ? 10 : run; v.rep(17, m - 3, 3); run -= m; i += m; }
-            if (run) { v.sym(0); i++; }
-         } else { v.sym(0); i++; }
+         }
+         for (; run > 0; run--) { v.sym(0); i++; }
       } else {
          int c = cl[i] > 15 ? 15 : cl[i];
          run--; v.sym(c); i++;
          if (run == 7 && (mask & 1) && !(mask & 8)) { v.rep(16, 1, 2); v.rep(16, 0, 2); run -= 7; i += 7; }
          else if (run == 8 && (mask & 1) && !(mask & 16)) { v.rep(16, 1, 2); v.rep(16, 1, 2); run -= 8; i += 8; }
          while (run >= 3 && (mask & 1)) { int m = run > 6 ? 6 : run; v.rep(16, m - 3, 2); run -= m; i += m; }
+         for (; run > 0; run--) { v.sym(c); i++; }
       }
    }
 }

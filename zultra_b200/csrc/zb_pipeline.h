@@ -1094,6 +1094,180 @@ __global__ void __launch_bounds__(128) zb_split_drift_k(const ZbNode *cur, int n
 }
 #endif
 
+#ifndef ZB_EMU
+#include "zb_warp.h"
+#define ZB_WT 128                 /* threads per CTA of the warp-per-task kernels: 4 tasks */
+
+/* splitter S1 (blockdeflate.c:646-667): one warp per node - greedy histogram of the node, its cost estimate, check-point layout */
+__global__ void __launch_bounds__(ZB_WT) zb_split_nodes_k(ZbNode *cur, int ncur, int *nh, ZbGreedyView gv) {
+   __shared__ ZbWarpScratch ws[ZB_WT / 32];
+   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+   const int x = blockIdx.x * (ZB_WT / 32) + wi;
+   if (x >= ncur) return;
+   ZbWarpScratch &s = ws[wi];
+   ZbNode nd = cur[x];
+   nd.nchk = 0; nd.best_tok = 0; nd.best_delta = 0; nd.t0 = 0;
+   if (nd.pe - nd.ps >= 8192) {
+      zbw_range_hist(gv, (int)nd.win, nd.ts, nd.te, s.h, lane);
+      if (lane == 0) s.h[ZB_EOB] += 1;
+      __syncwarp();
+      int *h = nh + (size_t)x * ZB_NH;
+      for (int i = lane; i < ZB_NH; i += 32) h[i] = s.h[i];
+      zbw_lengths(s.h, ZB_NLIT, s.llen, s, lane);
+      zbw_lengths(s.h + ZB_NLIT, ZB_NOFF, s.olen, s, lane);
+      nd.total_cost = zbw_dynamic_cost(s.h, s.llen, s.h + ZB_NLIT, s.olen, s, lane);
+      /* first check: >= 256 tokens and >= 512 bytes consumed (blockdeflate.c:705), then every 256 tokens */
+      const uint32_t ntok = nd.te - nd.ts;
+      const uint32_t *a = gv.tp + gv.wtb[nd.win] + nd.ts;
+      uint32_t t0 = 256;
+      while (t0 <= ntok) {
+         const uint32_t endpos = t0 < ntok ? a[t0] : nd.pe;
+         if (endpos - nd.ps >= 512) break;
+         t0++;
+      }
+      if (t0 <= ntok) { nd.t0 = t0; nd.nchk = (ntok - t0) / 256 + 1; }
+   }
+   if (lane == 0) cur[x] = nd;
+}
+
+/* splitter S4 (blockdeflate.c:724-757): one warp per side of a drift-flagged candidate */
+__global__ void __launch_bounds__(ZB_WT) zb_split_eval_k(const ZbNode *cur, long ntask, const uint8_t *cf, const uint32_t *cnode, const int *nh, int *cdl, ZbGreedyView gv) {
+   __shared__ ZbWarpScratch ws[ZB_WT / 32];
+   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+   const long y = (long)blockIdx.x * (ZB_WT / 32) + wi;
+   if (y >= ntask) return;
+   const long c = y >> 1; const int right_side = (int)(y & 1);
+   if (!cf[c]) { if (lane == 0) cdl[y] = -1; return; }
+   ZbWarpScratch &s = ws[wi];
+   const uint32_t x = cnode[c];
+   const ZbNode nd = cur[x];
+   const uint32_t k = (uint32_t)c - nd.chk_base;   /* k >= 1 here */
+   const uint32_t tsplit = nd.t0 + 256 * (k - 1);   /* tokens left of the split */
+   zbw_range_hist(gv, (int)nd.win, nd.ts, nd.ts + tsplit, s.h, lane);
+   if (right_side) {
+      const int *tot = nh + (size_t)x * ZB_NH;
+      for (int i = lane; i < ZB_NH; i += 32) s.h[i] = tot[i] - s.h[i];
+   }
+   __syncwarp();
+   if (lane == 0) s.h[ZB_EOB] = 1;
+   __syncwarp();
+   zbw_lengths(s.h, ZB_NLIT, s.llen, s, lane);
+   zbw_lengths(s.h + ZB_NLIT, ZB_NOFF, s.olen, s, lane);
+   const int cost = zbw_dynamic_cost(s.h, s.llen, s.h + ZB_NLIT, s.olen, s, lane);
+   if (lane == 0) cdl[y] = cost;
+}
+
+/* D1: greedy histogram, static-vs-dynamic decision (libzultra.c:317-324), first tables (blockdeflate.c:863-869): one warp per sub-block */
+__global__ void __launch_bounds__(ZB_WT) zb_sub_init_k(ZbSub *sb, ZbSubTabs *tb, int ns, ZbGreedyView gv) {
+   __shared__ ZbWarpScratch ws[ZB_WT / 32];
+   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+   const int x = blockIdx.x * (ZB_WT / 32) + wi;
+   if (x >= ns) return;
+   ZbWarpScratch &s = ws[wi];
+   ZbSub sub = sb[x]; ZbSubTabs &t = tb[x];
+   zbw_range_hist(gv, (int)sub.win, sub.ts, sub.te, s.h, lane);
+   if (lane == 0) s.h[ZB_EOB] += 1;
+   __syncwarp();
+   {  /* zb_static_cost */
+      int c = 0;
+      for (int i = lane; i < 286; i += 32) c += s.h[i] * (zb_static_lit_len(i) + (i >= 257 ? zb_lensym_extra(i - 257) : 0));
+      if (lane < ZB_NOFF) c += s.h[ZB_NLIT + lane] * (5 + zb_offsym_extra(lane));
+      sub.static_cost = zbw_sum(c) + 3;
+   }
+   zbw_lengths(s.h, ZB_NLIT, s.llen, s, lane);
+   zbw_lengths(s.h + ZB_NLIT, ZB_NOFF, s.olen, s, lane);
+   sub.dynamic_cost = zbw_dynamic_cost(s.h, s.llen, s.h + ZB_NLIT, s.olen, s, lane);
+   sub.is_dyn = sub.static_cost <= sub.dynamic_cost ? 0 : 1;
+   sub.ub_hit = 0;
+   if (sub.is_dyn) {
+      int ub = 0;
+      zbw_build(s.h, ZB_NLIT, 15, s.llen, s, &ub, lane);
+      zbw_build(s.h + ZB_NLIT, ZB_NOFF, 15, s.olen, s, &ub, lane);
+      sub.ub_hit = __shfl_sync(ZBW_FULL, ub, 0);
+      for (int i = lane; i < ZB_NLIT; i += 32) t.llen[i] = s.llen[i];
+      if (lane < ZB_NOFF) t.olen[lane] = s.olen[lane];
+      zbw_make_costtab(s.llen, s.olen, true, t.cost, lane);      /* blockdeflate.c:873-881 */
+   } else {
+      for (int i = lane; i < ZB_NLIT; i += 32) { t.llen[i] = zb_static_lit_len(i); s.llen[i] = zb_static_lit_len(i); }   /* blockdeflate.c:839-849 */
+      if (lane < ZB_NOFF) { t.olen[lane] = 5; s.olen[lane] = 5; }
+      __syncwarp();
+      zbw_make_costtab(s.llen, s.olen, false, t.cost, lane);
+   }
+   if (lane == 0) sb[x] = sub;
+}
+
+/* D7: rebuild the tables from the pass's histogram (blockdeflate.c:893-919): one warp per sub-block */
+__global__ void __launch_bounds__(ZB_WT) zb_sub_tables_k(ZbSub *sb, ZbSubTabs *tb, int ns, int pass) {
+   __shared__ ZbWarpScratch ws[ZB_WT / 32];
+   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+   const int x = blockIdx.x * (ZB_WT / 32) + wi;
+   if (x >= ns) return;
+   if (!sb[x].is_dyn) return;
+   ZbWarpScratch &s = ws[wi];
+   ZbSubTabs &t = tb[x];
+   if (pass == 3 && lane == 0) {   /* always describe at least two distance codes (blockdeflate.c:893-913) */
+      int nz = 0;
+      for (int i = 0; nz < 2 && i < ZB_NOFF - 2; i++) if (t.ocnt[i]) nz++;
+      if (nz == 0) t.ocnt[0] = t.ocnt[1] = 1;
+      else if (nz == 1) { if (t.ocnt[0]) t.ocnt[1] = 1; else t.ocnt[0] = 1; }
+   }
+   __syncwarp();
+   for (int i = lane; i < ZB_NLIT; i += 32) s.h[i] = t.lcnt[i];
+   if (lane < ZB_NOFF) s.h[ZB_NLIT + lane] = t.ocnt[lane];
+   __syncwarp();
+   int ub = 0;
+   zbw_build(s.h, ZB_NLIT, 15, s.llen, s, &ub, lane);
+   zbw_build(s.h + ZB_NLIT, ZB_NOFF, 15, s.olen, s, &ub, lane);
+   for (int i = lane; i < ZB_NLIT; i += 32) t.llen[i] = s.llen[i];
+   if (lane < ZB_NOFF) t.olen[lane] = s.olen[lane];
+   zbw_make_costtab(s.llen, s.olen, pass < 3, t.cost, lane);      /* final lengths as they are: the post-optimiser and the emitter use them */
+   if (lane == 0 && ub) sb[x].ub_hit = 1;
+}
+/* F1a: RLE smoothing trial (blockdeflate.c:926-945) and the code-length sequence to be described: one warp per sub-block */
+__global__ void __launch_bounds__(ZB_WT) zb_sub_smooth_k(ZbSub *sb, ZbSubTabs *tb, int ns) {
+   __shared__ ZbWarpScratch ws[ZB_WT / 32];
+   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+   const int x = blockIdx.x * (ZB_WT / 32) + wi;
+   if (x >= ns) return;
+   ZbWarpScratch &s = ws[wi];
+   ZbSub sub = sb[x]; ZbSubTabs &t = tb[x];
+   if (!sub.is_dyn) {
+      sub.nl = 288; sub.no = 32; sub.ncl = 0; sub.mask = 0; sub.hdr_bits = 0;
+      if (lane == 0) sb[x] = sub;
+      return;
+   }
+   for (int i = lane; i < ZB_NLIT; i += 32) { s.llen[i] = t.llen[i]; s.h[i] = t.lcnt[i]; s.olen[i] = i < ZB_NOFF ? t.olen[i] : 0; }
+   if (lane < ZB_NOFF) s.h[ZB_NLIT + lane] = t.ocnt[lane];
+   __syncwarp();
+   const int cur_cost = zbw_dynamic_cost(s.h, s.llen, s.h + ZB_NLIT, s.olen, s, lane);
+   if (lane == 0) {      /* zultra_huffman_encoder_optimize_for_rle: two short sequential scans */
+      zb_smooth_counts(ZB_NLIT, s.h, s.sc.cl);
+      zb_smooth_counts(ZB_NOFF, s.h + ZB_NLIT, s.sc.cl);
+   }
+   __syncwarp();
+   int ub = 0;
+   zbw_build(s.h, ZB_NLIT, 15, s.llen, s, &ub, lane);
+   zbw_build(s.h + ZB_NLIT, ZB_NOFF, 15, s.olen, s, &ub, lane);
+   const int opt_cost = zbw_dynamic_cost(s.h, s.llen, s.h + ZB_NLIT, s.olen, s, lane);
+   if (opt_cost < cur_cost) {      /* the smoothed counts stay in the encoder (SURVEY A-7) */
+      for (int i = lane; i < ZB_NLIT; i += 32) { t.lcnt[i] = s.h[i]; t.llen[i] = s.llen[i]; }
+      if (lane < ZB_NOFF) { t.ocnt[lane] = s.h[ZB_NLIT + lane]; t.olen[lane] = s.olen[lane]; }
+      if (__shfl_sync(ZBW_FULL, ub, 0)) sub.ub_hit = 1;
+   } else {
+      for (int i = lane; i < ZB_NLIT; i += 32) s.llen[i] = t.llen[i];
+      if (lane < ZB_NOFF) s.olen[lane] = t.olen[lane];
+   }
+   __syncwarp();
+   int nl = 257, no = 1;
+   { const int i = 256 + lane; const uint32_t mk = __ballot_sync(ZBW_FULL, i >= 257 && s.llen[i] != 0); if (mk) nl = 256 + 32 - __clz((int)mk); }
+   { const uint32_t mk = __ballot_sync(ZBW_FULL, lane >= 1 && s.olen[lane] != 0); if (mk) no = 32 - __clz((int)mk); }
+   sub.nl = nl; sub.no = no;
+   for (int i = lane; i < nl; i += 32) t.cl[i] = (uint8_t)s.llen[i];
+   for (int i = lane; i < no; i += 32) t.cl[nl + i] = (uint8_t)s.olen[i];
+   if (lane == 0) sb[x] = sub;
+}
+#endif
+
 /* ============================================================ block splitter ============================================================
  * zultra_compressor_split_subblock_recursive (blockdeflate.c:634-786), one recursion level per round.
  */
@@ -1117,6 +1291,13 @@ inline void ZbPipe::stage_split() {
    int ncur = nwin;
    for (int depth = 0; depth < 6 && ncur > 0; depth++) {
       /* S1: node totals, check-point layout */
+#ifndef ZB_EMU
+      if (g_zb_prof_on) { zb_tag("split_nodes"); zb_prof_begin(0, st); }
+      zb_split_nodes_k<<<(unsigned)((ncur + ZB_WT / 32 - 1) / (ZB_WT / 32)), ZB_WT, 0, st>>>(cur, ncur, nh, gv);
+      if (g_zb_prof_on) zb_prof_end(st);
+      zb_count_launch(1);
+      ZB_CUDA_CHECK(cudaGetLastError());
+#else
       zb_launch(st, ncur, ZB_LAMBDA(long x) {
          ZbNode nd = cur[x];
          nd.nchk = 0; nd.best_tok = 0; nd.best_delta = 0; nd.t0 = 0;
@@ -1141,6 +1322,7 @@ inline void ZbPipe::stage_split() {
          }
          cur[x] = nd;
       });
+#endif
       /* check record bases (serial, few nodes) */
       zb_launch(st, 1, ZB_LAMBDA(long) {
          uint32_t b = 0;
@@ -1201,6 +1383,13 @@ inline void ZbPipe::stage_split() {
          });
 #endif
          /* S4: cost delta of splitting at the PREVIOUS check point (blockdeflate.c:724-757) */
+#ifndef ZB_EMU
+         if (g_zb_prof_on) { zb_tag("split_eval"); zb_prof_begin(0, st); }
+         zb_split_eval_k<<<(unsigned)((2L * nchk + ZB_WT / 32 - 1) / (ZB_WT / 32)), ZB_WT, 0, st>>>(cur, 2L * nchk, cf, cnode, nh, cdl, gv);
+         if (g_zb_prof_on) zb_prof_end(st);
+         zb_count_launch(1);
+         ZB_CUDA_CHECK(cudaGetLastError());
+#else
          zb_tag("split_eval");
          zb_launch(st, 2L * nchk, ZB_LAMBDA(long y) {      /* one task per side of a candidate: the two are independent */
             const long c = y >> 1; const int right_side = (int)(y & 1);
@@ -1222,6 +1411,7 @@ inline void ZbPipe::stage_split() {
             zb_huff_lengths(h + ZB_NLIT, ZB_NOFF, olen, s.key);
             cdl[y] = zb_dynamic_cost(h, llen, h + ZB_NLIT, olen, s);
          }, 64);
+#endif
          /* S5: best candidate per node (first maximum, delta >= 0), emit children */
          zb_memset(st, cn + 2, 0, 4);
          uint32_t *wsp = wsplit.p, *wns = wnsplit.p;
@@ -1370,6 +1560,7 @@ __device__ __forceinline__ void zb_dp_signature(int16_t *__restrict__ dst, size_
 /* positions [lo, from) of one chunk, descending; t = step of position from - 1 on entry.  All per-step addresses are running
    pointers (the cost row advances by one row, the records / text / choices retreat by one element, the ring slot by one slot
    modulo 64): the loop is instruction bound, and 64-bit address arithmetic from the position index was a fifth of it. */
+template <int UNR>
 __device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const uint4 *__restrict__ cand, const ZbDpTab *__restrict__ tab, int lo, int from,
                                             uint32_t *__restrict__ choice, uint16_t *ring0, uint16_t *far0, int &t_io, uint32_t &cprev_io, const bool KEEP) {
    const int NT = ZB_DP_THREADS;
@@ -1414,7 +1605,7 @@ __device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const
                const int ml = (int)((e >> 5) & 63u);
                while (k <= ml) {
                   const int kstop = ml < kw - 1 ? ml : kw - 1;
-#pragma unroll 4
+#pragma unroll UNR
                   for (; k <= kstop; k++, pr -= NT) {
                      const uint32_t key = ((uint32_t)*pr << 6) + lenkey[k - ZB_MIN_MATCH];
                      curmin = key < curmin ? key : curmin;
@@ -1440,7 +1631,8 @@ __device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const
    t_io = t; cprev_io = cprev;
 }
 
-__global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
+template <int UNR, int MINB>
+__global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
                                                                const uint32_t *wbs, const uint8_t *T, const uint4 *cand, uint32_t *bm, int16_t *sgt, int16_t *sgw,
                                                                size_t SS, uint16_t *far, int CD, int WU, int nslot) {
    extern __shared__ __align__(16) uint8_t zb_dp_sm[];
@@ -1477,7 +1669,7 @@ __global__ void __launch_bounds__(ZB_DP_THREADS) zb_parse_dp_k(const ZbSub *sb, 
       not unrolled) - the kernel is instruction-issue bound and its code should stay inside the I-cache */
 #pragma unroll 1
    for (int phase = 0; phase < 2; phase++) {
-      zb_dp_range(t, cand + gb, tab, phase ? lo : hi, phase ? hi : from, bm + gb, ring0, far0, step, cprev, phase != 0);
+      zb_dp_range<UNR>(t, cand + gb, tab, phase ? lo : hi, phase ? hi : from, bm + gb, ring0, far0, step, cprev, phase != 0);
       zb_dp_signature(phase ? sg : sw, SS, far0, phase ? lo : hi, from, end, step, cprev, phase == 0);
    }
 }
@@ -1782,7 +1974,7 @@ inline void ZbPipe::stage_parse() {
       shorter chunks (more warm-up overhead, shorter serial chains) for small batches such as one GPU's shard of a stream. */
    /* (the thread-per-chunk kernel keeps ~1024 chunks resident per SM: aim at one full wave, within [512, ZB_CD]) */
    int cd_auto = (int)(((long)P / ((long)zb_sm_count() * 1024) + 63) / 64 * 64);
-   if (cd_auto < 512) cd_auto = 512;
+   if (cd_auto < 128) cd_auto = 128;      /* small inputs (one 48 KB stream, a GPU's share of a strongly scaled 51 MB): short chunks = short serial chains, the warm-up then dominates a chunk */
    if (cd_auto > ZB_CD) cd_auto = ZB_CD;
    int WU = parse_wu; if (WU > 2048) WU = 2048;
    int CD = parse_cd ? parse_cd : cd_auto; if (CD > 2048) CD = 2048;      /* CD + WU <= 4368: u16 costs cannot wrap (zb_parse_dp_k) */
@@ -1790,6 +1982,15 @@ inline void ZbPipe::stage_parse() {
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
    ZbGreedyView gv = {ph.p, wintbase.p, wtokbase.p, tokpos.p, wbase.p, glen.p, goff.p, in_ptr, win.p};
    /* D1: greedy histogram, static-vs-dynamic decision (libzultra.c:317-324), first tables (blockdeflate.c:863-869) */
+#ifndef ZB_EMU
+   if (ns > 0) {
+      if (g_zb_prof_on) { zb_tag("sub_init"); zb_prof_begin(0, st); }
+      zb_sub_init_k<<<(unsigned)((ns + ZB_WT / 32 - 1) / (ZB_WT / 32)), ZB_WT, 0, st>>>(sb, tb, ns, gv);
+      if (g_zb_prof_on) zb_prof_end(st);
+      zb_count_launch(1);
+      ZB_CUDA_CHECK(cudaGetLastError());
+   }
+#else
    zb_launch(st, ns, ZB_LAMBDA(long x) {
       ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
       int h[ZB_NH];
@@ -1818,6 +2019,7 @@ inline void ZbPipe::stage_parse() {
       }
       sb[x] = s;
    }, 64);
+#endif
    /* chunk lists */
    zb_launch(st, 1, ZB_LAMBDA(long) {
       uint32_t d = 0, p = 0;
@@ -1864,7 +2066,13 @@ inline void ZbPipe::stage_parse() {
    const size_t dp_smem = (size_t)ZB_NR * ZB_DP_THREADS * 2 + (size_t)dp_nslot * sizeof(ZbDpTab);
    {  /* the limit is a per-function global: always the largest configuration, so concurrent host threads cannot undercut each other */
       const size_t smax = (size_t)ZB_NR * ZB_DP_THREADS * 2 + (size_t)ZB_DP_THREADS * sizeof(ZbDpTab);
-      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<4, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<1, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<2, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<4, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<1, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
    }
    if (npch > 0) {
       if (g_zb_prof_on) { zb_tag("parse_cand"); zb_prof_begin(0, st); }
@@ -1887,7 +2095,12 @@ inline void ZbPipe::stage_parse() {
          if (g_zb_prof_on) { zb_tag("parse_dp"); zb_prof_begin(0, st); }
          {
             const unsigned grid = (unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS);
-            zb_parse_dp_k<<<grid, ZB_DP_THREADS, dp_smem, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, (const uint4 *)cand.p, (uint32_t *)bm, sgt, sgw, SS, dpfar.p, CD, WU, dp_nslot);
+            /* development variants (ZULTRA_CUDA_DP_VAR): k-loop unroll factor x CTAs per SM asked of the compiler */
+            static const int var = getenv("ZULTRA_CUDA_DP_VAR") ? atoi(getenv("ZULTRA_CUDA_DP_VAR")) : 0;
+#define ZB_DP_LAUNCH(U_, B_) zb_parse_dp_k<U_, B_><<<grid, ZB_DP_THREADS, dp_smem, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, (const uint4 *)cand.p, (uint32_t *)bm, sgt, sgw, SS, dpfar.p, CD, WU, dp_nslot)
+            if (var == 1) ZB_DP_LAUNCH(1, 9); else if (var == 2) ZB_DP_LAUNCH(2, 9); else if (var == 3) ZB_DP_LAUNCH(4, 10); else if (var == 4) ZB_DP_LAUNCH(2, 10); else if (var == 5) ZB_DP_LAUNCH(1, 10);
+            else if (var == 6) ZB_DP_LAUNCH(2, 12); else ZB_DP_LAUNCH(4, 9);
+#undef ZB_DP_LAUNCH
          }
          if (g_zb_prof_on) zb_prof_end(st);
          zb_count_launch(1);
@@ -2110,6 +2323,15 @@ inline void ZbPipe::stage_parse() {
       });
 #endif
       /* D7: rebuild tables (blockdeflate.c:893-919) */
+#ifndef ZB_EMU
+      if (ns > 0) {
+         if (g_zb_prof_on) { zb_tag("sub_tables"); zb_prof_begin(0, st); }
+         zb_sub_tables_k<<<(unsigned)((ns + ZB_WT / 32 - 1) / (ZB_WT / 32)), ZB_WT, 0, st>>>(sb, tb, ns, pass);
+         if (g_zb_prof_on) zb_prof_end(st);
+         zb_count_launch(1);
+         ZB_CUDA_CHECK(cudaGetLastError());
+      }
+#else
       zb_launch(st, ns, ZB_LAMBDA(long x) {
          ZbSub s = sb[x];
          if (!s.is_dyn) return;
@@ -2134,6 +2356,7 @@ inline void ZbPipe::stage_parse() {
          }
          sb[x] = s;
       }, 64);
+#endif
    }
 #ifndef ZB_EMU
    if (npch > 0) {      /* choice words -> {length, offset} */
@@ -2169,6 +2392,15 @@ inline void ZbPipe::stage_parse() {
       }
    });
    /* F1a: RLE smoothing trial (blockdeflate.c:926-945); the code-length sequence to be described */
+#ifndef ZB_EMU
+   if (ns > 0) {
+      if (g_zb_prof_on) { zb_tag("sub_smooth"); zb_prof_begin(0, st); }
+      zb_sub_smooth_k<<<(unsigned)((ns + ZB_WT / 32 - 1) / (ZB_WT / 32)), ZB_WT, 0, st>>>(sb, tb, ns);
+      if (g_zb_prof_on) zb_prof_end(st);
+      zb_count_launch(1);
+      ZB_CUDA_CHECK(cudaGetLastError());
+   }
+#else
    zb_launch(st, ns, ZB_LAMBDA(long x) {
       ZbSub s = sb[x]; ZbSubTabs &t = tb[x];
       ZbScratch sc;
@@ -2200,6 +2432,7 @@ inline void ZbPipe::stage_parse() {
       }
       sb[x] = s;
    }, 64);
+#endif
    /* F1b: the 20 RLE masks {0..7, 9, 11, .., 31} in parallel (blockdeflate.c:958-974) */
    zb_launch(st, (long)ns * 20, ZB_LAMBDA(long y) {
       const long x = y / 20; const int mi = (int)(y % 20);
