@@ -48,6 +48,7 @@ long emu_compress(const uint8_t *data, long n, const uint8_t *hist, int hist_len
                   /* optional dumps, sized by caller: */ uint32_t *sa_lcp, uint16_t *match, int *nsub, int *sub_info /* 8 ints per sub */,
                   int *lit_len, int *off_len, uint16_t *best, unsigned *crc) {
    ZbPipe p; p.st = 0;
+   if (getenv("ZB_EMU_PARSE_CD")) p.parse_cd = atoi(getenv("ZB_EMU_PARSE_CD"));      /* analysis aid: force the parse chunk length */
    ZbStreamIn s = {data, (size_t)n, hist, (uint32_t)hist_len, finalize, (uint32_t)in_bits, 0};
    std::vector<uint8_t> o; std::vector<ZbStreamRes> r; ZbDump d;
    ZbRunOpts opt; opt.tile_main = tile_main; opt.dump = &d; opt.checksum_kind = 2;

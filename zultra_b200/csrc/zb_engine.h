@@ -47,7 +47,7 @@ struct ZbRunOpts {
 /* main positions per match-finder tile: as large as shared memory allows (amortises the 32768 look-back entries every
    tile loads) while still giving every SM several tiles */
 static inline uint32_t zb_pick_tile(size_t total) {
-   uint32_t t = 8192;
+   uint32_t t = 16384;
    while (t > 512 && total / t < 600) t >>= 1;
    return t;
 }
@@ -76,6 +76,7 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
    bool multi_direct = ns > 1 && !o.dev_in && o.direct_h2d;
    for (int i = 0; i < ns && multi_direct; i++) if (s[i].hist_len && s[i].hist + s[i].hist_len != s[i].data) multi_direct = false;
    uint8_t *stage = 0;
+   bool staged_to_device = false, pipe_fail = false;      /* the gather threads already sent the staged input to p.in */
    if (!o.dev_in && !single_direct && !multi_direct) {
       p.hin.need(in_bytes + 16);
       stage = p.hin.p;
@@ -83,20 +84,39 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
       std::vector<size_t> offs(ns + 1, 0);
       for (int i = 0; i < ns; i++) offs[i + 1] = offs[i] + s[i].hist_len + s[i].n;
       const int nth = in_bytes > ((size_t)8 << 20) ? 4 : 1;
-      auto gather = [&](int a, int b) {
+#ifndef ZB_EMU
+      /* large batches: every gathering thread sends what it has gathered to the device in 4 MiB pieces on its own stream, so the
+         DMA runs under the remaining memcpys instead of after them (347 MB of small streams: 25 ms of gather + DMA -> the longer of the two) */
+      const bool piped = nth > 1 && p.stager.init();
+      if (piped) { p.in.need(in_bytes + 16); if (zb_failed()) return -3; staged_to_device = true; }
+#else
+      const bool piped = false;
+#endif
+      auto gather = [&](int a, int b, int lane) {
+         size_t sent = a < ns ? offs[a] : in_bytes;
          for (int i = a; i < b; i++) {
             if (s[i].hist_len) memcpy(stage + offs[i], s[i].hist, s[i].hist_len);
             memcpy(stage + offs[i] + s[i].hist_len, s[i].data, s[i].n);
+#ifndef ZB_EMU
+            if (piped && (offs[i + 1] - sent >= ((size_t)4 << 20) || i + 1 == b)) {
+               cudaMemcpyAsync(p.in.p + sent, stage + sent, offs[i + 1] - sent, cudaMemcpyHostToDevice, p.stager.st[lane]);
+               sent = offs[i + 1];
+            }
+#endif
          }
+#ifndef ZB_EMU
+         if (piped) { cudaSetDevice(p.device); if (cudaStreamSynchronize(p.stager.st[lane]) != cudaSuccess) pipe_fail = true; }
+#endif
+         (void)lane; (void)sent;
       };
-      if (nth == 1) gather(0, ns);
+      if (nth == 1) gather(0, ns, 0);
       else {
          std::vector<std::thread> th;
          int a = 0;
          for (int k = 0; k < nth; k++) {   /* equal byte shares */
             int b = a;
             while (b < ns && (k == nth - 1 || offs[b] < in_bytes / nth * (k + 1))) b++;
-            th.emplace_back(gather, a, b);
+            th.emplace_back(gather, a, b, k);
             a = b;
          }
          for (auto &t : th) t.join();
@@ -128,7 +148,8 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
    res.assign(ns, ZbStreamRes());
    for (int i = 0; i < ns; i++) res[i].checksum = s[i].checksum;
    if (wins.empty()) { out.clear(); return 0; }
-   p.setup(wins, o.dev_in ? o.dev_in : (single_direct ? s[0].data - s[0].hist_len : stage), in_bytes, o.dev_in != 0);
+   if (pipe_fail) return -3;
+   p.setup(wins, o.dev_in ? o.dev_in : (single_direct ? s[0].data - s[0].hist_len : (staged_to_device ? (const uint8_t *)0 : stage)), in_bytes, o.dev_in != 0);
    if (multi_direct && !zb_failed()) {      /* setup allocated the device input (no source given): one DMA per stream */
       size_t at = 0;
       for (int i = 0; i < ns; i++) { zb_h2d(p.st, p.in.p + at, s[i].data - s[i].hist_len, s[i].hist_len + s[i].n); at += s[i].hist_len + s[i].n; }
@@ -191,6 +212,10 @@ static inline int zb_run_batch(ZbPipe &p, const ZbStreamIn *s, int ns, uint32_t 
          for (int i = 0; i < ns; i++) total_words = std::max<size_t>(total_words, p.h_sout[i].out_word_off + (p.h_sout[i].total_bits + 31) / 32);
          if (ns == 1 && o.host_out) {   /* straight into the caller's buffer */
             if (ob > o.host_out_cap) return -2;
+#ifndef ZB_EMU
+            if (ob >= ((size_t)8 << 20) && ZbStager::pageable(o.host_out)) { zb_sync(p.st); if (!p.stager.copy(1, p.out.p, o.host_out, ob, p.device)) return -3; }
+            else
+#endif
             zb_d2h(p.st, o.host_out, p.out.p, ob);
             zb_sync(p.st);
             out.clear();

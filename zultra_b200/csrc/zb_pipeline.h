@@ -26,7 +26,7 @@
 #define ZB_NH 320         /* 288 lit/len + 32 distance counters */
 #define ZB_MAXSB 64       /* sub-blocks per window */
 #define ZB_MAXNODES 64    /* splitter nodes per window per level (<= 32 used) */
-#define ZB_MF_TILE_MAX 8192   /* main positions per match-finder tile: words + ranks + text of 32768 + 8192 positions fill the 227 KB of shared memory */
+#define ZB_MF_TILE_MAX 16384  /* main positions per match-finder tile: the list of 32768 + 16384 suffixes (4 bytes each) + the rank of every main position (2 bytes) = 224 KB of the 227 KB of shared memory */
 
 struct ZbWinDesc {
    uint32_t in_off;   /* offset of the window's first byte (history start) in the device input */
@@ -101,9 +101,74 @@ struct ZbHostBuf {   /* grow-only page-locked host buffer */
    void release() { zb_host_free(p); p = 0; cap = 0; }
 };
 
+#ifndef ZB_EMU
+/* Host <-> device copies of PAGEABLE caller memory.  cudaMemcpyAsync on unregistered memory goes through the driver's own
+   bounce buffers on the calling thread: ~11 GB/s up and ~4.4 GB/s down on the B200 box, i.e. 9 + 11 ms of a 100 MB one-shot
+   call whose device work is 73 ms.  Here the range is cut into 4 lanes, each with its own host thread, CUDA stream and a pair
+   of page-locked 4 MiB buffers: memcpy and DMA of consecutive pieces overlap inside a lane, and the lanes' memcpys run side
+   by side.  Page-locked (or registered) caller memory is copied directly, as before. */
+#include <thread>
+struct ZbStager {
+   enum { LANES = 4, PIECE = 4 << 20 };
+   uint8_t *buf = 0; cudaStream_t st[LANES]; cudaEvent_t ev[LANES][2]; bool ready = false;
+   bool init() {
+      if (ready) return true;
+      if (cudaHostAlloc((void **)&buf, (size_t)LANES * 2 * PIECE, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); buf = 0; return false; }
+      for (int l = 0; l < LANES; l++) { cudaStreamCreateWithFlags(&st[l], cudaStreamNonBlocking); cudaEventCreateWithFlags(&ev[l][0], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev[l][1], cudaEventDisableTiming); }
+      ready = true;
+      return true;
+   }
+   void release() { if (!ready) return; for (int l = 0; l < LANES; l++) { cudaStreamDestroy(st[l]); cudaEventDestroy(ev[l][0]); cudaEventDestroy(ev[l][1]); } cudaFreeHost(buf); buf = 0; ready = false; }
+   static bool pageable(const void *p) {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+      return a.type == cudaMemoryTypeUnregistered;
+   }
+   /* dir 0: host -> device, 1: device -> host.  Synchronous: returns when all bytes have arrived.  Returns false on a CUDA error. */
+   bool copy(int dir, void *dev, void *host, size_t n, int device) {
+      if (!init()) return false;
+      bool ok[LANES];
+      auto lane = [&](int l) {
+         ok[l] = true;
+         if (cudaSetDevice(device) != cudaSuccess) { ok[l] = false; return; }
+         const size_t per = ((n + LANES - 1) / LANES + 255) & ~(size_t)255, lo = std::min(n, (size_t)l * per), hi = std::min(n, lo + per);
+         uint8_t *b[2] = {buf + (size_t)(2 * l) * PIECE, buf + (size_t)(2 * l + 1) * PIECE};
+         size_t pend_off[2] = {0, 0}, pend_len[2] = {0, 0};
+         int k = 0;
+         for (size_t off = lo; off < hi; off += PIECE, k ^= 1) {
+            const size_t len = std::min((size_t)PIECE, hi - off);
+            if (dir == 0) {
+               if (cudaEventSynchronize(ev[l][k]) != cudaSuccess) ok[l] = false;      /* the DMA that last read this buffer */
+               memcpy(b[k], (const uint8_t *)host + off, len);
+               if (cudaMemcpyAsync((uint8_t *)dev + off, b[k], len, cudaMemcpyHostToDevice, st[l]) != cudaSuccess) ok[l] = false;
+               cudaEventRecord(ev[l][k], st[l]);
+            } else {
+               if (pend_len[k]) { if (cudaEventSynchronize(ev[l][k]) != cudaSuccess) ok[l] = false; memcpy((uint8_t *)host + pend_off[k], b[k], pend_len[k]); }
+               if (cudaMemcpyAsync(b[k], (const uint8_t *)dev + off, len, cudaMemcpyDeviceToHost, st[l]) != cudaSuccess) ok[l] = false;
+               cudaEventRecord(ev[l][k], st[l]);
+               pend_off[k] = off; pend_len[k] = len;
+            }
+         }
+         if (dir == 1) for (int q = 0; q < 2; q++, k ^= 1) if (pend_len[k]) { if (cudaEventSynchronize(ev[l][k]) != cudaSuccess) ok[l] = false; memcpy((uint8_t *)host + pend_off[k], b[k], pend_len[k]); pend_len[k] = 0; }
+         if (cudaStreamSynchronize(st[l]) != cudaSuccess) ok[l] = false;
+      };
+      std::thread th[LANES - 1];
+      for (int l = 1; l < LANES; l++) th[l - 1] = std::thread(lane, l);
+      lane(0);
+      for (int l = 1; l < LANES; l++) th[l - 1].join();
+      for (int l = 0; l < LANES; l++) if (!ok[l]) { cudaGetLastError(); return false; }
+      return true;
+   }
+};
+#endif
+
 struct ZbPipe {
    zb_stream_t st;
    ZbHostBuf hin, hout;         /* staging of multi-stream batches */
+#ifndef ZB_EMU
+   ZbStager stager;             /* pageable caller memory: multi-lane staged copies */
+   int device = 0;
+#endif
    /* batch description */
    int nwin = 0, nstream = 0;
    uint32_t P = 0;              /* total window positions */
@@ -178,7 +243,16 @@ inline void ZbPipe::setup(const std::vector<ZbWinDesc> &wins, const uint8_t *h_i
    zb_h2d(st, win.p, h_win.data(), sizeof(ZbWinDesc) * nwin);
    zb_h2d(st, wbase.p, h_wbase.data(), 4 * (nwin + 1));
    if (in_is_device) in_ptr = h_in;
-   else { if (h_in) zb_h2d(st, in.p, h_in, in_bytes); in_ptr = in.p; }
+   else {
+      if (h_in) {
+#ifndef ZB_EMU
+         if (in_bytes >= ((size_t)8 << 20) && ZbStager::pageable(h_in)) { zb_sync(st); if (!stager.copy(0, in.p, (void *)h_in, in_bytes, device)) zb_cuda_fail(cudaErrorUnknown); }
+         else
+#endif
+         zb_h2d(st, in.p, h_in, in_bytes);
+      }
+      in_ptr = in.p;
+   }
 }
 
 /* ============================================================ suffix array + LCP ============================================================
@@ -305,7 +379,7 @@ inline void ZbPipe::stage_sa() {
    main position from a shared counter and all 32 lanes keep stepping (same arithmetic as the rank walk of zb_mf_scan, kept
    as a resumable state).  Records go straight to global memory as they are found.  A position whose walk reaches the
    text-walk condition is handed to kernel B through a per-tile queue in global memory: three words
-   {m | nm << 13 | moved << 17 | lvl << 18, bound | (i - 1 - best) << 9, first record}. */
+   {m | nm << 14 | moved << 18 | lvl << 19, bound | (i - 1 - best) << 9, first record}. */
 #define ZB_MF_THREADS 1024
 __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *td, int first, const uint32_t *unit_words, const uint32_t *unit_cnt, uint32_t *queues, size_t qstride,
                                                               size_t stride, uint32_t *qcnt, zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, uint32_t tile_main,
@@ -439,7 +513,7 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
             if (steps >= ts_min && gap <= thr) {   /* the rest is cheaper read from the text: kernel B */
                const uint32_t at = atomicAdd(&nq, 1u);
                if (nm == 1) dst[0] = rec0; else if (nm >= 2) *(uint2 *)dst = make_uint2(rec0, rec1);      /* kernel B fills the slots from nm on */
-               queue[3 * at] = m | ((uint32_t)nm << 13) | ((moved ? 1u : 0u) << 17) | (lvl << 18);
+               queue[3 * at] = m | ((uint32_t)nm << 14) | ((moved ? 1u : 0u) << 18) | (lvl << 19);
                queue[3 * at + 1] = l | ((uint32_t)(i - 1 - best) << 9);
                queue[3 * at + 2] = rec0;
                busy = false;
@@ -532,9 +606,9 @@ __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *
       if ((uint32_t)lane < nhere) { const uint32_t *qe = queue + 3 * (size_t)(e0 + lane); r0 = __ldg(qe); r1 = __ldg(qe + 1); r2 = __ldg(qe + 2); }
       for (uint32_t tix = 0; tix < nhere; tix++) {
       const uint32_t c0 = __shfl_sync(0xffffffffu, r0, (int)tix), c1 = __shfl_sync(0xffffffffu, r1, (int)tix), c2 = __shfl_sync(0xffffffffu, r2, (int)tix);
-      const uint32_t m = c0 & 0x1fffu, lvl = c0 >> 18, bound = c1 & 0x1ffu;
-      const int nm = (int)((c0 >> 13) & 15u);
-      const bool moved = (c0 >> 17) & 1u;
+      const uint32_t m = c0 & 0x3fffu, lvl = c0 >> 19, bound = c1 & 0x1ffu;
+      const int nm = (int)((c0 >> 14) & 15u);
+      const bool moved = (c0 >> 18) & 1u;
       const int i = (int)(nlook + m);
       const int best = i - 1 - (int)(c1 >> 9);
       const uint32_t k3 = (uint32_t)txt[i] | ((uint32_t)txt[i + 1] << 8) | ((uint32_t)txt[i + 2] << 16);
@@ -645,6 +719,25 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    const int wave_tiles = std::min(ntile, 16384);
    const int seg_g = segs_for(maxlen), seg_u = segs_for(use_groups ? gstride : maxlen), seg_t = segs_for(2 * ZB_MAX_OFFSET);
    filt_seg.need(2 * std::max((size_t)ngroup * seg_g, std::max((size_t)nunit * seg_u, (size_t)wave_tiles * seg_t)) + 64);
+#ifndef ZB_EMU
+   {  /* window lists -> unit lists: one stable partition per window (zb_unit_distribute) */
+      std::vector<ZbDistWin> hd(nwin);
+      uint32_t ub = 0, sb2 = 0, numax = 1;
+      for (int w = 0; w < nwin; w++) {
+         const ZbWinDesc &d = h_win[w];
+         ZbDistWin x; memset(&x, 0, sizeof(x));
+         x.sa_base = h_wbase[w]; x.len = d.len; x.hist = d.hist; x.unit_base = ub; x.seg_base = sb2;
+         x.nu = (d.len - d.hist + ZB_MAX_OFFSET - 1) / ZB_MAX_OFFSET;
+         ub += x.nu; sb2 += (d.len + 4095) / 4096; numax = std::max(numax, x.nu);
+         hd[w] = x;
+      }
+      groups.need((sizeof(ZbDistWin) * (size_t)nwin + sizeof(ZbTileDesc) - 1) / sizeof(ZbTileDesc) + 1);      /* (the group descriptors' buffer, unused in this build) */
+      filt_seg.need(2 * (size_t)sb2 * numax + 64);
+      if (zb_failed() || (int)ub != nunit) { if ((int)ub != nunit) zb_cuda_fail(cudaErrorUnknown); return; }
+      zb_h2d(st, groups.p, hd.data(), sizeof(ZbDistWin) * nwin);
+      zb_unit_distribute(st, sa_lcp.p, (const ZbDistWin *)groups.p, nwin, (int)sb2, nunit, (int)numax, filt_seg.p, unit_words.p, unit_cnt.p);
+   }
+#else
    if (use_groups) {
       groups.need(ngroup); group_words.need((size_t)ngroup * gstride); group_cnt.need(ngroup);
       zb_h2d(st, groups.p, hg.data(), sizeof(ZbTileDesc) * ngroup);
@@ -653,6 +746,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    } else {
       zb_tile_filter(st, sa_lcp.p, 0, units.p, nunit, 0, unit_words.p, 2 * ZB_MAX_OFFSET, unit_cnt.p, seg_u, filt_seg.p);
    }
+#endif
    const size_t stride = ZB_MAX_OFFSET + tile_main;
    const int wave = 16384;
    const int nw_tiles = std::min(ntile, wave);
@@ -675,6 +769,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    {  /* the limit is a per-function global: always the largest configuration, so concurrent host threads cannot undercut each other */
       const size_t smax = ((size_t)ZB_MAX_OFFSET + ZB_MF_TILE_MAX + 2) * 4 + (size_t)ZB_MF_TILE_MAX * 2;
       ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_mf_scan_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_mf_text_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)ZB_MAX_OFFSET + ZB_MF_TILE_MAX + ZB_MAX_MATCH + 7) & ~(size_t)3)));
    }
 #else
    tile_pd.need((size_t)nw_tiles * tile_main);
@@ -1688,8 +1783,9 @@ __global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub
 #define ZB_DW_INF 0x7fffffffu
 #define ZB_DW_FAR_INF 0x3fffffff
 
+#define ZB_DW_RING 576         /* costs of the last 576 positions: 259 for the recurrence, 517 + a block for the run shortcut below */
 struct ZbDwShared {            /* per warp */
-   uint16_t ring[ZB_RING];
+   uint16_t ring[ZB_DW_RING];
    uint32_t info[32][ZB_NMATCH + 1];  /* decoded matches of the 32 positions of the current block (+1: bank spread) */
    uint32_t meta[32];                 /* M | K << 4 | literal cost << 16 */
    ZbCostTab tab;                     /* the sub-block's bit costs */
@@ -1700,8 +1796,17 @@ struct ZbDwShared {            /* per warp */
    {clamped length (9 bits) | leave-alone flag | fixed cost (6 bits: offset cost, plus the length cost for a leave-alone
    match) | offset (16 bits)}.  What stays serial per position is: ring reads, one redux per short match, a few compares,
    one ring write. */
+/* Byte runs.  Inside a long run every position has the same match record and the same literal, so the recurrence is a fixed map
+   applied over and over: once the 259 relative costs at a position equal those 258 positions above it (the length of the run's
+   one match), every choice below repeats the choice 258 above and every cost is that cost plus a constant, for as long as the
+   records stay the same.  The walker tracks the stretch of identical records it is in (whole blocks of 32), tests that
+   periodicity once the stretch is 517 positions long, and from then on copies 32 choices per step instead of scanning them -
+   a 64 KiB run of a mozilla-shaped input is one serial chain of 128 chunks, and this chain is what the repair's time is. */
+struct ZbDwUni { uint4 ra, rb; uint32_t rl, delta; int len, top; bool periodic; int n_copy, n_scan, n_slow; /* positions done by each path (ZULTRA_CUDA_FIX_DEBUG) */ };
+
 __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const zb_match_t *__restrict__ match, int lo, int from, int end,
-                                          zb_match_t *__restrict__ best, ZbDwShared &sh, int &slot, const int lane) {
+                                          zb_match_t *__restrict__ best, ZbDwShared &sh, int &slot, ZbDwUni &U, const int lane,
+                                          const int pf_lo /* first position of the sub-block: L2 prefetches may run ahead of this chunk into the next ones of the chain */) {
    int s = slot;
    if (from <= lo) return;
    uint16_t *ring = sh.ring;
@@ -1717,8 +1822,104 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
    }
    uint32_t base = ring[s];       /* cost of the position above the next one to do: carried in a register */
    bool far_ok = true; int farE = ZB_DW_FAR_INF, lita = 0; uint32_t farw = 0u;
-   for (int i0 = from - 1; i0 >= lo; i0 -= 32) {
+   /* after a block done the long way: count it into the stretch of identical records and, once the stretch spans 517 positions
+      (none of them clamped by the sub-block end), test whether the cost window has become 258-periodic: cost[ib + q] -
+      cost[ib + 258 + q] the same for q = 0..258, ib = the block's lowest position (slot s) */
+#define ZB_DW_STRETCH() do { \
+      if (cont || (U.len == 0 && U.top == i0)) U.len += nb_pos; \
+      if (U.len >= 2 * ZB_MAX_MATCH + 1 && !U.periodic && end - U.top >= ZB_MAX_MATCH) { \
+         __syncwarp(); \
+         int s258_ = s - ZB_MAX_MATCH; if (s258_ < 0) s258_ += ZB_DW_RING; \
+         const uint32_t d_ = ((uint32_t)ring[s] - (uint32_t)ring[s258_]) & 0xffffu; \
+         bool ok_ = true; \
+         for (int q_ = lane; q_ <= ZB_MAX_MATCH; q_ += 32) { \
+            int x_ = s - q_; if (x_ < 0) x_ += ZB_DW_RING; \
+            int y_ = x_ - ZB_MAX_MATCH; if (y_ < 0) y_ += ZB_DW_RING; \
+            if ((((uint32_t)ring[x_] - (uint32_t)ring[y_]) & 0xffffu) != d_) ok_ = false; \
+         } \
+         if (__all_sync(0xffffffffu, ok_)) { U.periodic = true; U.delta = d_; } \
+      } \
+   } while (0)
+   for (int i0 = from - 1; i0 >= lo;) {      /* every path below steps i0 itself */
       __syncwarp();
+      const int nb_pos = i0 - lo + 1 < 32 ? i0 - lo + 1 : 32;
+      bool cont;      /* this block consists of copies of ONE record, the same as the stretch before it */
+      {
+         const uint4 a0 = make_uint4(__shfl_sync(0xffffffffu, na.x, 0), __shfl_sync(0xffffffffu, na.y, 0), __shfl_sync(0xffffffffu, na.z, 0), __shfl_sync(0xffffffffu, na.w, 0));
+         const uint4 b0 = make_uint4(__shfl_sync(0xffffffffu, nb.x, 0), __shfl_sync(0xffffffffu, nb.y, 0), __shfl_sync(0xffffffffu, nb.z, 0), __shfl_sync(0xffffffffu, nb.w, 0));
+         const uint32_t l0 = __shfl_sync(0xffffffffu, nl, 0);
+         const bool mine = lane >= nb_pos || (na.x == a0.x && na.y == a0.y && na.z == a0.z && na.w == a0.w && nb.x == b0.x && nb.y == b0.y && nb.z == b0.z && nb.w == b0.w && nl == l0);
+         const bool uniform = __all_sync(0xffffffffu, mine);
+         cont = uniform && U.len > 0 && a0.x == U.ra.x && a0.y == U.ra.y && a0.z == U.ra.z && a0.w == U.ra.w && b0.x == U.rb.x && b0.y == U.rb.y && b0.z == U.rb.z && b0.w == U.rb.w && l0 == U.rl;
+         if (!uniform) { U.len = 0; U.periodic = false; }
+         else if (!cont) { U.ra = a0; U.rb = b0; U.rl = l0; U.len = 0; U.top = i0; U.periodic = false; }
+      }
+      if (U.periodic && cont) {
+         /* The run shortcut, four blocks at a time while the chunk has them: one record per lane and block, all loads of a
+            round in flight together (a block a round exposed a full memory round trip per 32 positions: 52 cycles a position,
+            no better than the scan), the records of the next kilobyte pulled into L2 meanwhile. */
+         bool wide = false;
+         while (i0 - 127 >= lo) {
+            uint4 xa[3], xb[3]; uint32_t xl[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+               const int p = i0 - 32 * (k + 1) - lane;
+               const uint4 *q = (const uint4 *)(match + ((size_t)p << 3));
+               xa[k] = __ldg(q); xb[k] = __ldg(q + 1); xl[k] = t[p];
+            }
+            uint32_t cw[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) cw[k] = ((const uint32_t *)best)[i0 - 32 * k - lane + ZB_MAX_MATCH];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+               const int pf = i0 - 1024 - 32 * k - lane;
+               if (pf >= pf_lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(match + ((size_t)pf << 3)));
+            }
+            bool okb = na.x == U.ra.x && na.y == U.ra.y && na.z == U.ra.z && na.w == U.ra.w && nb.x == U.rb.x && nb.y == U.rb.y && nb.z == U.rb.z && nb.w == U.rb.w && nl == U.rl;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+               okb = okb && xa[k].x == U.ra.x && xa[k].y == U.ra.y && xa[k].z == U.ra.z && xa[k].w == U.ra.w && xb[k].x == U.rb.x && xb[k].y == U.rb.y && xb[k].z == U.rb.z && xb[k].w == U.rb.w && xl[k] == U.rl;
+            if (!__all_sync(0xffffffffu, okb)) break;      /* the single-block logic below takes it from here (this block is still `cont`) */
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+               int sl = s + 1 + 32 * k + lane; if (sl >= ZB_DW_RING) sl -= ZB_DW_RING;
+               int sh258 = sl - ZB_MAX_MATCH; if (sh258 < 0) sh258 += ZB_DW_RING;
+               ring[sl] = (uint16_t)((uint32_t)ring[sh258] + U.delta);
+               ((uint32_t *)best)[i0 - 32 * k - lane] = cw[k];
+            }
+            wide = true;
+            i0 -= 128;
+            s += 128; if (s >= ZB_DW_RING) s -= ZB_DW_RING;
+            U.len += 128; U.n_copy += 128;
+            {
+               const int p = i0 - lane;
+               if (p >= lo) { const uint4 *q = (const uint4 *)(match + ((size_t)p << 3)); na = __ldg(q); nb = __ldg(q + 1); nl = t[p]; }
+            }
+            __syncwarp();
+            base = ring[s];
+         }
+         if (wide) continue;      /* a fresh look at the block now at i0 (its records are loaded) */
+      }
+      if (U.periodic && cont) {
+         /* the run shortcut: choice and cost of position i = those of position i + 258 (+ delta) */
+         if (lane < nb_pos) {
+            const int i = i0 - lane;
+            int sl = s + 1 + lane; if (sl >= ZB_DW_RING) sl -= ZB_DW_RING;
+            int sh258 = sl - ZB_MAX_MATCH; if (sh258 < 0) sh258 += ZB_DW_RING;
+            ring[sl] = (uint16_t)((uint32_t)ring[sh258] + U.delta);
+            ((uint32_t *)best)[i] = ((const uint32_t *)best)[i + ZB_MAX_MATCH];
+         }
+         {
+            const int p = i0 - 32 - lane;
+            if (p >= lo) { const uint4 *q = (const uint4 *)(match + ((size_t)p << 3)); na = __ldg(q); nb = __ldg(q + 1); nl = t[p]; }
+         }
+         s += nb_pos; if (s >= ZB_DW_RING) s -= ZB_DW_RING;
+         __syncwarp();
+         base = ring[s];
+         U.len += nb_pos; U.n_copy += nb_pos;
+         i0 -= 32;
+         continue;
+      }
       {  /* decode position i0 - lane */
          const int i = i0 - lane;
          const uint32_t w[ZB_NMATCH] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
@@ -1740,7 +1941,7 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
                inf = (uint32_t)ml | ((lg ? 1u : 0u) << 9) | ((uint32_t)fixed << 10) | (osym << 16) | ((uint32_t)m << 21);      /* bits 16..: what the choice word needs */
                /* far candidate: a leave-alone match that lands past the block's top position is already final */
                if (lg && ml > lane) {
-                  int idx = s - (ml - 1 - lane); if (idx < 0) idx += ZB_RING;
+                  int idx = s - (ml - 1 - lane); if (idx < 0) idx += ZB_DW_RING;
                   const int total = fixed + (int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base);
                   if (total < farE) { farE = total; farw = (uint32_t)ml | (osym << 9) | ((uint32_t)m << 14); }
                } else far_ok = false;
@@ -1757,11 +1958,10 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
          /* a scan block is over long before a DRAM round trip: the records of the blocks further ahead are pulled into L2 now,
             so that the register prefetch above only ever waits for L2 */
          const int pf = i0 - 32 * 6 - lane;
-         if (pf >= lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(match + ((size_t)pf << 3)));
-         if (lane == 0 && pf >= lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(t + pf - 31));
+         if (pf >= pf_lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(match + ((size_t)pf << 3)));
+         if (lane == 0 && pf >= pf_lo + 31) asm volatile("prefetch.global.L2 [%0];" :: "l"(t + pf - 31));
       }
       __syncwarp();
-      const int nb_pos = i0 - lo + 1 < 32 ? i0 - lo + 1 : 32;
       uint32_t outw = 0;      /* lane x keeps the choice of position i0 - x: one coalesced store per block */
       if (__all_sync(0xffffffffu, far_ok)) {
          /* Every candidate of every position of the block is either its literal or a leave-alone match landing above the
@@ -1778,31 +1978,34 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
          int cin = __shfl_up_sync(0xffffffffu, r, 1); if (lane == 0) cin = 0;
          if (farE < cin + lita) outw = farw;             /* literal first, a match only on strictly lower cost */
          if (lane < nb_pos) {
-            int sl = s + 1 + lane; if (sl >= ZB_RING) sl -= ZB_RING;
+            int sl = s + 1 + lane; if (sl >= ZB_DW_RING) sl -= ZB_DW_RING;
             ring[sl] = (uint16_t)(base + (uint32_t)r);
             ((uint32_t *)best)[i0 - lane] = outw;
          }
          base = (base + (uint32_t)__shfl_sync(0xffffffffu, r, nb_pos - 1)) & 0xffffu;
-         s += nb_pos; if (s >= ZB_RING) s -= ZB_RING;
+         s += nb_pos; if (s >= ZB_DW_RING) s -= ZB_DW_RING;
+         U.n_scan += nb_pos;
+         ZB_DW_STRETCH();
+         i0 -= 32;
          continue;
       }
       for (int x = 0; x < nb_pos; x++) {
          const uint32_t meta = sh.meta[x];
          const int M = (int)(meta & 15u), K = (int)((meta >> 4) & 0xfffu);
          const int s1 = s;                           /* slot of i+1 */
-         s = s1 + 1; if (s >= ZB_RING) s -= ZB_RING;
+         s = s1 + 1; if (s >= ZB_DW_RING) s -= ZB_DW_RING;
          int bestc = (int)(meta >> 16), bl = 0, bo = 0;
          if (M) {
             uint32_t keyA = ZB_DW_INF, keyB = ZB_DW_INF;
             if (K >= ZB_MIN_MATCH) {
                const int k = ZB_MIN_MATCH + lane;
                if (k <= K) {
-                  int idx = s1 - (k - 1); if (idx < 0) idx += ZB_RING;
+                  int idx = s1 - (k - 1); if (idx < 0) idx += ZB_DW_RING;
                   keyA = ((uint32_t)((int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base) + lcA + 8192) << 6) | (uint32_t)(63 - k);
                }
                const int k2 = k + 32;
                if (k2 <= K) {
-                  int idx = s1 - (k2 - 1); if (idx < 0) idx += ZB_RING;
+                  int idx = s1 - (k2 - 1); if (idx < 0) idx += ZB_DW_RING;
                   keyB = ((uint32_t)((int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base) + lcB + 8192) << 6) | (uint32_t)(63 - k2);
                }
             }
@@ -1813,7 +2016,7 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
                   const int mlm = (int)(inf & 511u), fixed = (int)((inf >> 10) & 63u);
                   int total = 0x7fffffff, kk = 0;
                   if ((inf >> 9) & 1u) {   /* >= 40: only the full (clamped) length, even below 3 (SURVEY A-3) */
-                     int idx = s1 - (mlm - 1); if (idx < 0) idx += ZB_RING;
+                     int idx = s1 - (mlm - 1); if (idx < 0) idx += ZB_DW_RING;
                      const uint32_t cv = mlm == 1 ? base : (uint32_t)ring[idx];     /* cost[i+1] is the register copy */
                      total = fixed + (int)(int16_t)(uint16_t)(cv - base);
                      kk = mlm;
@@ -1834,7 +2037,11 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
          __syncwarp();
       }
       if (lane < nb_pos) ((uint32_t *)best)[i0 - lane] = outw;
+      U.n_slow += nb_pos;
+      ZB_DW_STRETCH();
+      i0 -= 32;
    }
+#undef ZB_DW_STRETCH
    slot = s;
 }
 
@@ -1844,7 +2051,7 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
    verifies again afterwards, so a race with a neighbouring run costs a round, never correctness. */
 __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, const uint32_t *badlist, int nbad, const uint8_t *ok,
                                                                 const ZbWinDesc *wd, const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm,
-                                                                int16_t *sgt, int16_t *sgw, size_t SS, int CD) {
+                                                                int16_t *sgt, int16_t *sgw, size_t SS, int CD, long long *dbg) {
    __shared__ ZbDwShared sh_all[ZB_DW_WARPS];
    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
    const long g = (long)blockIdx.x * ZB_DW_WARPS + wi;
@@ -1861,45 +2068,56 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
    zb_match_t *b0 = bm + gb;
    const int end = (int)s.pe;
    int slot = 0;
+   ZbDwUni U; U.ra = make_uint4(0u, 0u, 0u, 0u); U.rb = U.ra; U.rl = 0; U.delta = 0; U.len = 0; U.top = -1; U.periodic = false; U.n_copy = U.n_scan = U.n_slow = 0;
+   const long long clk0 = clock64();
    {
       const uint32_t *src = (const uint32_t *)&tb[x].cost; uint32_t *dstw = (uint32_t *)&sh.tab;
       for (int e = lane; e < (int)(sizeof(ZbCostTab) / 4); e += 32) dstw[e] = src[e];
       const int16_t *b = sgt + (size_t)(c + 1);
       int16_t *sw = sgw + (size_t)c;
-      for (int e = lane; e < ZB_RING; e += 32) ring[e] = 0;
+      for (int e = lane; e < ZB_DW_RING; e += 32) ring[e] = 0;
       __syncwarp();
-      for (int e = lane; e <= ZB_MAX_MATCH; e += 32) { int sl = slot - e; if (sl < 0) sl += ZB_RING; const int16_t v = b[(size_t)e * SS]; ring[sl] = (uint16_t)v; sw[(size_t)e * SS] = v; }
+      for (int e = lane; e <= ZB_MAX_MATCH; e += 32) { int sl = slot - e; if (sl < 0) sl += ZB_DW_RING; const int16_t v = b[(size_t)e * SS]; ring[sl] = (uint16_t)v; sw[(size_t)e * SS] = v; }
    }
    __syncwarp();
    for (;;) {
       const int lo = (int)(s.ps + ((uint32_t)c - s.dchunk_base) * CD), hi = lo + CD;
-      zb_dw_run(t, m0, lo, hi, end, b0, sh, slot, lane);
+      zb_dw_run(t, m0, lo, hi, end, b0, sh, slot, U, lane, (int)s.ps);
       /* this chunk's true costs at its start */
       const uint16_t b = ring[slot];
       int16_t *sg = sgt + (size_t)c;
       for (int e = lane; e <= ZB_MAX_MATCH; e += 32) {
-         int sl = slot - e; if (sl < 0) sl += ZB_RING;
+         int sl = slot - e; if (sl < 0) sl += ZB_DW_RING;
          sg[(size_t)e * SS] = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
       }
       if ((uint32_t)c == s.dchunk_base) break;
       const long nx = c - 1;
       if (!ok[nx] && ok[c]) break;   /* c had been right, so nx heads a run of its own: another warp owns it */
       int16_t *sw = sgw + (size_t)nx;
-      bool same = true;
-      for (int e = lane; e <= ZB_MAX_MATCH; e += 32) {
-         int sl = slot - e; if (sl < 0) sl += ZB_RING;
-         const int16_t v = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
-         if (sw[(size_t)e * SS] != v) same = false;
+      if (ok[nx]) {      /* (inside a run of wrong chunks nx is redone whatever it had assumed: no reason to wait for its 259 loads) */
+         bool same = true;
+         int16_t got[(ZB_MAX_MATCH + 32) / 32];
+#pragma unroll
+         for (int j = 0; j < (ZB_MAX_MATCH + 32) / 32; j++) { const int e = lane + 32 * j; got[j] = e <= ZB_MAX_MATCH ? sw[(size_t)e * SS] : (int16_t)0; }      /* all in flight together */
+#pragma unroll
+         for (int j = 0; j < (ZB_MAX_MATCH + 32) / 32; j++) {
+            const int e = lane + 32 * j;
+            if (e <= ZB_MAX_MATCH) {
+               int sl = slot - e; if (sl < 0) sl += ZB_DW_RING;
+               const int16_t v = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
+               if (got[j] != v) same = false;
+            }
+         }
+         if (__all_sync(0xffffffffu, same)) break;      /* nx was computed from exactly these costs: the run ends here */
       }
-      same = __all_sync(0xffffffffu, same);
-      if (ok[nx] && same) break;      /* nx was computed from exactly these costs: the run ends here */
       for (int e = lane; e <= ZB_MAX_MATCH; e += 32) {   /* what chunk nx is now computed from */
-         int sl = slot - e; if (sl < 0) sl += ZB_RING;
+         int sl = slot - e; if (sl < 0) sl += ZB_DW_RING;
          sw[(size_t)e * SS] = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
       }
       c = nx;
       __syncwarp();
    }
+   if (dbg && lane == 0) { long long *d = dbg + 5 * g; d[0] = U.n_copy; d[1] = U.n_scan; d[2] = U.n_slow; d[3] = clock64() - clk0; d[4] = badlist[g]; }
 }
 #endif
 
@@ -2099,7 +2317,7 @@ inline void ZbPipe::stage_parse() {
             static const int var = getenv("ZULTRA_CUDA_DP_VAR") ? atoi(getenv("ZULTRA_CUDA_DP_VAR")) : 0;
 #define ZB_DP_LAUNCH(U_, B_) zb_parse_dp_k<U_, B_><<<grid, ZB_DP_THREADS, dp_smem, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, (const uint4 *)cand.p, (uint32_t *)bm, sgt, sgw, SS, dpfar.p, CD, WU, dp_nslot)
             if (var == 1) ZB_DP_LAUNCH(1, 9); else if (var == 2) ZB_DP_LAUNCH(2, 9); else if (var == 3) ZB_DP_LAUNCH(4, 10); else if (var == 4) ZB_DP_LAUNCH(2, 10); else if (var == 5) ZB_DP_LAUNCH(1, 10);
-            else if (var == 6) ZB_DP_LAUNCH(2, 12); else ZB_DP_LAUNCH(4, 9);
+            else if (var == 6) ZB_DP_LAUNCH(2, 12); else if (var == 7) ZB_DP_LAUNCH(4, 9); else ZB_DP_LAUNCH(2, 9);      /* measured on B200: unroll 2 at 55 registers is the fastest of these */
 #undef ZB_DP_LAUNCH
          }
          if (g_zb_prof_on) zb_prof_end(st);
@@ -2216,7 +2434,20 @@ inline void ZbPipe::stage_parse() {
 #endif
 #ifndef ZB_EMU
          if (g_zb_prof_on) { zb_tag("parse_repair"); zb_prof_begin(0, st); }
-         zb_parse_fix_k<<<(unsigned)((nbad + ZB_DW_WARPS - 1) / ZB_DW_WARPS), ZB_DW_THREADS, 0, st>>>(sb, tb, dcs, bad, (int)nbad, ok, wd, wbs, T, mt, bm, sgt, sgw, SS, CD);
+         static const int fix_dbg = getenv("ZULTRA_CUDA_FIX_DEBUG") ? atoi(getenv("ZULTRA_CUDA_FIX_DEBUG")) : 0;
+         long long *dbgp = 0;
+         if (fix_dbg) { scratch.need((size_t)nbad * 10 + 64); dbgp = (long long *)scratch.p; zb_memset(st, dbgp, 0, (size_t)nbad * 40); }
+         zb_parse_fix_k<<<(unsigned)((nbad + ZB_DW_WARPS - 1) / ZB_DW_WARPS), ZB_DW_THREADS, 0, st>>>(sb, tb, dcs, bad, (int)nbad, ok, wd, wbs, T, mt, bm, sgt, sgw, SS, CD, dbgp);
+         if (fix_dbg) {
+            std::vector<long long> hd((size_t)nbad * 5);
+            zb_d2h(st, hd.data(), dbgp, hd.size() * 8); zb_sync(st);
+            std::vector<int> idx; for (int e = 0; e < (int)nbad; e++) if (hd[5 * (size_t)e + 3]) idx.push_back(e);
+            std::sort(idx.begin(), idx.end(), [&](int a, int b) { return hd[5 * (size_t)a + 3] > hd[5 * (size_t)b + 3]; });
+            long long tc = 0, tn = 0, ts = 0; for (int e : idx) { tc += hd[5 * (size_t)e]; tn += hd[5 * (size_t)e + 1]; ts += hd[5 * (size_t)e + 2]; }
+            fprintf(stderr, "fix pass %d round %d: %u bad chunks, %zu chains; positions copy %lld scan %lld slow %lld\n", pass, round, nbad, idx.size(), tc, tn, ts);
+            for (size_t q = 0; q < idx.size() && q < 6; q++) { const long long *d = &hd[5 * (size_t)idx[q]]; const ZbSub *unused = 0; (void)unused;
+               fprintf(stderr, "   chain at chunk %lld: copy %lld scan %lld slow %lld cycles %lld\n", d[4], d[0], d[1], d[2], d[3]); }
+         }
          if (g_zb_prof_on) zb_prof_end(st);
          zb_count_launch(1);
          ZB_CUDA_CHECK(cudaGetLastError());
@@ -2740,6 +2971,9 @@ inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams, u
 }
 
 inline void ZbPipe::release_all() {
+#ifndef ZB_EMU
+   stager.release();
+#endif
    win.release(); wbase.release(); in.release(); keyA.release(); keyB.release(); valA.release(); valB.release(); rank.release(); sa.release();
    actA.release(); actB.release(); tmpA.release(); tmpB.release(); scratch.release(); sa_lcp.release(); counters.release(); tiles.release();
    tile_iv.release(); tile_pd.release(); tile_cnt.release(); tile_q.release(); groups.release(); group_words.release(); group_cnt.release(); filt_seg.release(); units.release(); unit_words.release(); unit_cnt.release(); match.release(); glen.release(); goff.release(); exitoff.release(); exitc.release(); gentry.release();

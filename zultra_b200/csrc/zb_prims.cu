@@ -424,3 +424,188 @@ void zb_tile_filter(zb_stream_t st, const uint32_t *src, const uint32_t *src_cnt
    zb_count_launch(3);
    ZB_CUDA_CHECK(cudaGetLastError());
 }
+
+/* --------------------------------------------------------------- unit distribution --------------------------------------------------------------- */
+
+/* The tile filter above gives every consumer its own pass over the producer's list; for the first cut - a window's suffix list
+   (~1.08 M words) into its ~33 units of 32768 main + 32768 look-back positions - that was 26 words streamed per window position
+   over two levels.  Every position belongs to at most TWO units (the one it is a main position of, and the next one, whose
+   look-back it is in), so the cut is a stable partition: the window's list is read in segments of 4096 ranks, twice
+   (count, then scatter), and every entry is routed to its units.  Per segment and unit a 4096-bit membership bitmap in shared
+   memory gives an entry's rank among the unit's entries of the segment (popcounts) and its predecessor there (highest set bit
+   below); the LCP an entry gets in a unit's list is the minimum of the window LCPs after that predecessor up to itself
+   (32-entry block minima bound the scan of a long gap), and across segments the counts and the trailing minima are chained by a
+   small per-unit scan.  Same lists, bit for bit, as filtering the window list for every unit separately. */
+#define DS_SEG 4096
+#define DS_THREADS 256
+#define DS_WORDS (DS_SEG / 32)
+#define DS_BROW (DS_WORDS + 1)      /* bitmap row stride in words, prefix row stride in u16 pairs: rows of different units start in different banks
+                                       (the lanes of a warp look at the SAME word index of DIFFERENT units: unpadded, a 32-way bank conflict per access) */
+#define DS_PROW (DS_WORDS + 2)
+
+__device__ __forceinline__ int ds_find_win(const ZbDistWin *dw, int nwin, uint32_t seg) {
+   int lo = 0, hi = nwin - 1;
+   while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (dw[mid].seg_base <= seg) lo = mid; else hi = mid - 1; }
+   return lo;
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(DS_THREADS) unit_dist_k(const uint32_t *sa_lcp, const ZbDistWin *dw, int nwin, int nu_max, uint32_t *segrec, uint32_t *unit_words) {
+   extern __shared__ uint32_t ds_sm[];
+   uint32_t *bm = ds_sm;                                         /* [nu][DS_WORDS] membership bitmaps */
+   uint16_t *pre = (uint16_t *)(bm + (size_t)nu_max * DS_BROW); /* [nu][DS_WORDS] set bits before each word */
+   uint16_t *lcp = pre + (size_t)nu_max * DS_PROW;              /* [DS_SEG] */
+   uint16_t *bmin = lcp + DS_SEG;                                /* [DS_WORDS] minimum of every 32-entry block */
+   uint32_t *uoff = (uint32_t *)(bmin + DS_WORDS);               /* [nu + 1] SCATTER: where each unit's entries of this segment start in `stage` */
+   uint32_t *stage = uoff + nu_max + 1;                          /* [2 * DS_SEG] SCATTER: the segment's output, unit by unit, so that it leaves in runs */
+   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+   const int w = ds_find_win(dw, nwin, blockIdx.x);
+   const ZbDistWin W = dw[w];
+   const uint32_t seg = blockIdx.x - W.seg_base, r0 = seg * DS_SEG;
+   const uint32_t nr = W.len - r0 < DS_SEG ? W.len - r0 : DS_SEG;
+   const int nu = (int)W.nu;
+   if (nu == 1) {      /* a window of one unit (batches of small streams): its list IS the unit's list */
+      if (!SCATTER) { if (tid == 0) { segrec[(size_t)blockIdx.x * nu_max * 2] = nr; segrec[(size_t)blockIdx.x * nu_max * 2 + 1] = 0x1ffu | 0x10000u; } }
+      else for (uint32_t idx = tid; idx < nr; idx += DS_THREADS) unit_words[(size_t)W.unit_base * (2 * ZB_MAX_OFFSET) + r0 + idx] = __ldg(sa_lcp + W.sa_base + r0 + idx);
+      return;
+   }
+   for (int e = tid; e < nu * DS_BROW; e += DS_THREADS) bm[e] = 0;
+   __syncthreads();
+   uint32_t wv[DS_SEG / DS_THREADS];
+#pragma unroll
+   for (int k = 0; k < DS_SEG / DS_THREADS; k++) {
+      const uint32_t idx = (uint32_t)k * DS_THREADS + tid;
+      uint32_t v = 0x1ffu << ZB_POS_BITS;
+      if (idx < nr) {
+         v = __ldg(sa_lcp + W.sa_base + r0 + idx);
+         const uint32_t p = v & ZB_POS_MASK;
+         const int ua = p < W.hist ? 0 : (int)((p - W.hist) >> 15);
+         atomicOr(bm + ua * DS_BROW + (idx >> 5), 1u << (idx & 31));
+         if (p >= W.hist && ua + 1 < nu) atomicOr(bm + (ua + 1) * DS_BROW + (idx >> 5), 1u << (idx & 31));
+      }
+      wv[k] = v;
+      lcp[idx] = (uint16_t)((v >> ZB_POS_BITS) & 0x1ffu);
+   }
+   __syncthreads();
+   /* block minima (one warp reduction per 32 entries) */
+   for (int b = warp; b < DS_WORDS; b += DS_THREADS / 32) {
+      const uint32_t m = __reduce_min_sync(0xffffffffu, (uint32_t)lcp[b * 32 + lane]);
+      if (lane == 0) bmin[b] = (uint16_t)m;
+   }
+   __syncthreads();
+   uint32_t *rec = segrec + (size_t)blockIdx.x * nu_max * 2;
+   if (!SCATTER) {
+      /* per unit: entries in this segment, and the minimum LCP after its last entry (over the whole segment if it has none) */
+      for (int u = warp; u < nu; u += DS_THREADS / 32) {
+         const uint32_t *b = bm + u * DS_BROW;
+         uint32_t c = 0; int last = -1;
+#pragma unroll
+         for (int j = 0; j < DS_WORDS / 32; j++) {
+            const uint32_t x = b[j * 32 + lane];
+            c += (uint32_t)__popc(x);
+            if (x) last = (j * 32 + lane) * 32 + 31 - __clz((int)x);
+         }
+#pragma unroll
+         for (int d = 16; d > 0; d >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, d); last = max(last, __shfl_xor_sync(0xffffffffu, last, d)); }
+         /* min of lcp[last + 1 .. nr): the rest of last's block, then whole blocks */
+         uint32_t m = 0x1ffu;
+         const int from = last + 1;
+         const int fb = (from + 31) >> 5;
+         { const int i = from + lane; if (i < fb * 32 && i < DS_SEG) m = lcp[i]; }
+         for (int bb = fb + lane; bb < DS_WORDS; bb += 32) m = min(m, (uint32_t)bmin[bb]);
+         m = __reduce_min_sync(0xffffffffu, m);
+         if (lane == 0) { rec[2 * u] = c; rec[2 * u + 1] = m | (last >= 0 ? 0x10000u : 0u); }
+      }
+      return;
+   }
+   /* set bits before every bitmap word */
+   for (int u = warp; u < nu; u += DS_THREADS / 32) {
+      const uint32_t *b = bm + u * DS_BROW;
+      uint32_t run = 0;
+#pragma unroll
+      for (int j = 0; j < DS_WORDS / 32; j++) {
+         const uint32_t c = (uint32_t)__popc(b[j * 32 + lane]);
+         uint32_t inc = c;
+#pragma unroll
+         for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+         pre[u * DS_PROW + j * 32 + lane] = (uint16_t)(run + inc - c);
+         run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) uoff[u + 1] = run;      /* the unit's count, turned into a start below */
+   }
+   __syncthreads();
+   if (tid == 0) { uint32_t acc = 0; uoff[0] = 0; for (int u = 0; u < nu; u++) { const uint32_t c = uoff[u + 1]; uoff[u + 1] = acc + c; acc += c; } }
+   __syncthreads();
+#pragma unroll
+   for (int k = 0; k < DS_SEG / DS_THREADS; k++) {
+      const uint32_t idx = (uint32_t)k * DS_THREADS + tid;
+      if (idx >= nr) continue;
+      const uint32_t p = wv[k] & ZB_POS_MASK;
+      const int ua = p < W.hist ? 0 : (int)((p - W.hist) >> 15);
+      const int nun = (p >= W.hist && ua + 1 < nu) ? 2 : 1;
+      for (int q = 0; q < nun; q++) {
+         const int u = ua + q;
+         const uint32_t *b = bm + u * DS_BROW;
+         const uint32_t wi = idx >> 5, below = b[wi] & ((1u << (idx & 31)) - 1u);
+         const uint32_t rank = (uint32_t)pre[u * DS_PROW + wi] + (uint32_t)__popc(below);
+         int prev = -1;
+         if (below) prev = (int)(wi * 32) + 31 - __clz((int)below);
+         else for (int x = (int)wi - 1; x >= 0; x--) { const uint32_t y = b[x]; if (y) { prev = x * 32 + 31 - __clz((int)y); break; } }
+         /* minimum of lcp[prev + 1 .. idx] */
+         uint32_t m = 0x1ffu;
+         const int from = prev + 1, fb = (from + 31) >> 5, lb = (int)(idx >> 5);
+         if (fb > lb) { for (int i = from; i <= (int)idx; i++) m = min(m, (uint32_t)lcp[i]); }
+         else {
+            for (int i = from; i < fb * 32; i++) m = min(m, (uint32_t)lcp[i]);
+            for (int bb = fb; bb < lb; bb++) m = min(m, (uint32_t)bmin[bb]);
+            for (int i = lb * 32; i <= (int)idx; i++) m = min(m, (uint32_t)lcp[i]);
+         }
+         if (prev < 0) m = min(m, rec[2 * u + 1]);      /* carried in from the segments before */
+         /* unit u of this window: main positions from hist + u * 32768, look-back 32768 before them */
+         const uint32_t m0 = W.hist + (uint32_t)u * ZB_MAX_OFFSET, ulo = m0 > ZB_MAX_OFFSET ? m0 - ZB_MAX_OFFSET : 0;
+         stage[uoff[u] + rank] = (p - ulo) | (m << ZB_POS_BITS);
+      }
+   }
+   __syncthreads();
+   for (int u = warp; u < nu; u += DS_THREADS / 32) {      /* a unit's entries of this segment are one run of its list */
+      const uint32_t a = uoff[u], n = uoff[u + 1] - a;
+      uint32_t *dst = unit_words + (size_t)(W.unit_base + u) * (2 * ZB_MAX_OFFSET) + rec[2 * u];
+      for (uint32_t j = lane; j < n; j += 32) dst[j] = stage[a + j];
+   }
+}
+
+/* per (window, unit): counts -> offsets, trailing minima -> carried-in minima, over the window's segments */
+__global__ void unit_dist_offsets_k(const ZbDistWin *dw, int nwin, int nu_max, uint32_t *segrec, uint32_t *unit_cnt, int total_units) {
+   const int g = blockIdx.x * blockDim.x + threadIdx.x;
+   if (g >= total_units) return;
+   int lo = 0, hi = nwin - 1;
+   while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (dw[mid].unit_base <= (uint32_t)g) lo = mid; else hi = mid - 1; }
+   const ZbDistWin W = dw[lo];
+   const int u = g - (int)W.unit_base;
+   const uint32_t nseg = (W.len + DS_SEG - 1) / DS_SEG;
+   uint32_t acc = 0, carry = 0x1ffu;
+   for (uint32_t sg = 0; sg < nseg; sg++) {
+      uint32_t *rec = segrec + ((size_t)(W.seg_base + sg) * nu_max + u) * 2;
+      const uint32_t c = rec[0], th = rec[1];
+      rec[0] = acc; rec[1] = carry;
+      acc += c;
+      const uint32_t tl = th & 0xffffu;
+      carry = (th >> 16) ? tl : (tl < carry ? tl : carry);
+   }
+   unit_cnt[g] = acc;
+}
+
+void zb_unit_distribute(zb_stream_t st, const uint32_t *sa_lcp, const ZbDistWin *dw, int nwin, int nseg_total, int total_units, int nu_max, uint32_t *segrec,
+                        uint32_t *unit_words, uint32_t *unit_cnt) {
+   if (nseg_total <= 0 || total_units <= 0) return;
+   const size_t smem = (size_t)nu_max * DS_BROW * 4 + (size_t)nu_max * DS_PROW * 2 + DS_SEG * 2 + DS_WORDS * 2 + ((size_t)nu_max + 1) * 4 + 2 * DS_SEG * 4 + 16;
+   ZB_CUDA_CHECK(cudaFuncSetAttribute(unit_dist_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+   ZB_CUDA_CHECK(cudaFuncSetAttribute(unit_dist_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+   PROF_K("mf_unit_dist", st);
+   unit_dist_k<false><<<nseg_total, DS_THREADS, smem, st>>>(sa_lcp, dw, nwin, nu_max, segrec, unit_words);
+   unit_dist_offsets_k<<<(total_units + 127) / 128, 128, 0, st>>>(dw, nwin, nu_max, segrec, unit_cnt, total_units);
+   unit_dist_k<true><<<nseg_total, DS_THREADS, smem, st>>>(sa_lcp, dw, nwin, nu_max, segrec, unit_words);
+   PROF_E(st);
+   zb_count_launch(3);
+   ZB_CUDA_CHECK(cudaGetLastError());
+}

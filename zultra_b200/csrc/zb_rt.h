@@ -115,4 +115,15 @@ struct ZbTileDesc { uint32_t win; uint32_t lo, m0, hi; uint64_t src_base; uint32
 void zb_tile_filter(zb_stream_t st, const uint32_t *src, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt,
                     int nseg /* warps per tile: the source list is cut into that many segments */, uint32_t *seg_scratch /* >= 2 * ntiles * nseg words */);
 
+/*
+ * Unit distribution (CUDA build): the cut of every window's suffix list into its units (32768 main positions + the 32768 before
+ * them) as ONE stable partition - see zb_prims.cu.  dw: one descriptor per window (device memory); unit u of a window covers
+ * main positions [hist + u * 32768, ..) and writes its list to unit_words + (unit_base + u) * 65536, its length to unit_cnt.
+ */
+struct ZbDistWin { uint32_t sa_base, len, hist, unit_base, nu, seg_base, pad[2]; };
+#ifndef ZB_EMU
+void zb_unit_distribute(zb_stream_t st, const uint32_t *sa_lcp, const ZbDistWin *dw, int nwin, int nseg_total, int total_units, int nu_max,
+                        uint32_t *segrec /* >= 2 * nseg_total * nu_max words */, uint32_t *unit_words, uint32_t *unit_cnt);
+#endif
+
 #endif
