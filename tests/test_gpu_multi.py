@@ -165,5 +165,7 @@ def test_multi_device_public_api_and_cli_vs_compiled_reference(z, ref, monkeypat
     src = tmp_path / "in.bin"
     src.write_bytes(raw)
     cli = os.path.join(ROOT, "zultra_b200", "zultra")
-    subprocess.check_call([cli, str(src), str(tmp_path / "out.gz")], stdout=subprocess.DEVNULL)
+    env = dict(os.environ, ZULTRA_CUDA_TRACE="1")
+    r = subprocess.run([cli, str(src), str(tmp_path / "out.gz")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env, check=True)
     assert (tmp_path / "out.gz").read_bytes() == want
+    assert b"devices %d" % n in r.stderr, r.stderr[-400:]      # the CLI really spread the stream over all GPUs

@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 TAGS = {"zb_parse_dp_k": "parse_dp", "zb_mf_scan_k": "mf_scan", "zb_mf_text_k": "mf_text", "rs_scatter_k": "rs_scatter", "rs_hist_k": "rs_hist",
-        "zb_parse_fix_k": "parse_repair", "tile_filter_k": "mf_tile_filter", "zb_sweep_k": "path_sweep"}
+        "zb_parse_fix_k": "parse_repair", "tile_filter_k": "mf_tile_filter", "zb_sweep_k": "path_sweep", "unit_dist_k": "mf_unit_dist", "lcp_pack": "lcp_pack"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/time.h>
+#include <unistd.h>
 #include <zlib.h>
 #include "libzultra.h"
 
@@ -217,9 +218,16 @@ int main(int argc, char **argv) {
    int bad = 0, have_cmd = 0, verify = 0, i;
    char cmd = 'z';
    unsigned int opt = 0;
-   /* the tool drives one GPU: unless the caller chose, expose only the first one to the CUDA runtime, whose start-up
-      otherwise initialises every device of the box (seconds on an 8-GPU node, for a tool that may compress 48 KB) */
-   setenv("CUDA_VISIBLE_DEVICES", "0", 0);
+   /* the tool drives ZULTRA_CUDA_DEVICES GPUs (default one): unless the caller chose, expose only those to the CUDA runtime,
+      whose start-up otherwise initialises every device of the box (seconds on an 8-GPU node, for a tool that may compress 48 KB) */
+   {
+      const char *e = getenv("ZULTRA_CUDA_DEVICES");
+      int n = (e && atoi(e) > 1) ? atoi(e) : 1, k;
+      char list[128]; size_t at = 0;
+      if (n > 16) n = 16;
+      for (k = 0; k < n && at + 4 < sizeof(list); k++) at += (size_t)snprintf(list + at, sizeof(list) - at, k ? ",%d" : "%d", k);
+      setenv("CUDA_VISIBLE_DEVICES", list, 0);
+   }
    for (i = 1; i < argc; i++) {
       const char *a = argv[i];
       if (!strcmp(a, "-d") || !strcmp(a, "-z") || !strcmp(a, "-cbench") || !strcmp(a, "-test") || !strcmp(a, "-quicktest")) {
@@ -256,7 +264,10 @@ int main(int argc, char **argv) {
       if (dict && (opt & FMT_MASK) != FMT_ZLIB) { fprintf(stderr, "dictionaries are only supported for the zlib framing\n"); return 100; }
       r = do_compress(in, out, dict, opt);
       if (r == 0 && verify) r = do_compare(out, in, dict, opt);
-      return r;
+      /* all files are closed: leave without the CUDA runtime's exit handlers, which free gigabytes of device buffers one by
+         one (0.8 - 2 s measured after a 100 MB run); the driver reclaims the process's memory in bulk */
+      fflush(NULL);
+      _exit(r);
    }
    if (cmd == 'B') return do_cbench(in, out, opt);
    return 100;

@@ -86,6 +86,7 @@ int zultra_cuda_ctx_create(zultra_cuda_ctx_t **pp, int device) {
       if ((e = getenv("ZULTRA_CUDA_PARSE_CD")) && atoi(e) >= 64) c->pipe.parse_cd = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_PARSE_WU")) && atoi(e) >= 258) c->pipe.parse_wu = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_TILE")) && atoi(e) >= 256) c->tile = (unsigned)atoi(e);
+      if ((e = getenv("ZULTRA_CUDA_EXACT_SA")) && atoi(e) > 0) c->pipe.sa_exact = true;
       if ((e = getenv("ZULTRA_CUDA_TS_MIN")) && atoi(e) >= 1) c->pipe.mf_ts_min = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_TS_MUL")) && atoi(e) >= 0) c->pipe.mf_ts_mul = atoi(e);
       if ((e = getenv("ZULTRA_CUDA_LANES")) && atoi(e) >= 1 && atoi(e) <= 16) c->nlanes = atoi(e);
@@ -265,7 +266,7 @@ static zultra_cuda_ctx_t *multi_dev_ctx(zultra_cuda_ctx_t *c, int k) {
       zultra_cuda_ctx_t *q = 0;
       const int dev = (c->device + (int)c->peers.size() + 1) % count;
       if (zultra_cuda_ctx_create(&q, dev)) return 0;
-      q->pipe.parse_cd = c->pipe.parse_cd; q->pipe.parse_wu = c->pipe.parse_wu; q->pipe.mf_ts_min = c->pipe.mf_ts_min; q->pipe.mf_ts_mul = c->pipe.mf_ts_mul; q->tile = c->tile;
+      q->pipe.parse_cd = c->pipe.parse_cd; q->pipe.parse_wu = c->pipe.parse_wu; q->pipe.mf_ts_min = c->pipe.mf_ts_min; q->pipe.mf_ts_mul = c->pipe.mf_ts_mul; q->tile = c->tile; q->pipe.sa_exact = c->pipe.sa_exact;
       c->peers.push_back(q);
    }
    return c->peers[k - 1];
@@ -404,6 +405,7 @@ int zultra_cuda_compress_blocks(zultra_cuda_ctx_t *c, const unsigned char *hist,
       const int nd = (int)std::min<size_t>((size_t)c->ndev, nblocks);
       rc = run_multi(c, nd, hist, hist_size, in, n, clamp_block(block), finalize, in_bits, flags, checksum, out, out_cap, out_bits);
       cudaSetDevice(c->device);
+      { char msg[64]; snprintf(msg, sizeof msg, "compress_blocks: end, devices %d", nd); zb_trace(msg, c->ms); }
       return ctx_leave(c, rc);
    }
    {
@@ -704,7 +706,10 @@ int zultra_cuda_window_sa_lcp(zultra_cuda_ctx_t *c, const unsigned char *win, in
    ZbStreamIn s = {win, (size_t)n, 0, 0, 1, 0, 0};
    ZbRunOpts o; ZbDump d; o.dump = &d; o.stop_after = 1;
    std::vector<ZbStreamRes> res;
+   const bool was_exact = c->pipe.sa_exact;
+   c->pipe.sa_exact = true;                          /* the parity artefact is the exact suffix array */
    rc = run_one(c, s, 2097152u + 65536u, o, res);   /* one window: block size above any window */
+   c->pipe.sa_exact = was_exact;
    if (rc == 0) memcpy(words, d.sa_lcp.data(), (size_t)n * 4);
    return ctx_leave(c, rc ? ZULTRA_CUDA_ERR_CUDA : 0);
 }

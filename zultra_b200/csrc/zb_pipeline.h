@@ -200,6 +200,7 @@ struct ZbPipe {
    std::vector<ZbStreamOut> h_sout;
    int nsub = 0;
    /* stats */
+   bool sa_exact = false;       /* run the suffix sort to the end (stage dumps); see stage_sa */
    int parse_cd = 0, parse_wu = ZB_WU;   /* parse chunk (0 = by batch size, see stage_parse) / warm-up positions */
    int mf_ts_min = ZB_TS_MIN, mf_ts_mul = ZB_TS_MUL;   /* rank walk -> text walk switch (zb_mf_scan) */
    int stat_sa_rounds = 0, stat_redo = 0, stat_ub = 0, stat_tiles = 0;
@@ -301,7 +302,11 @@ inline void ZbPipe::stage_sa() {
    int rank_bits = 1; while ((1L << rank_bits) < n) rank_bits++;
    uint64_t *kB = keyB.p; uint32_t *vB = valB.p;
    stat_sa_rounds = 0;
-   for (uint32_t h = (uint32_t)nbytes; m > 0; h <<= 1) {
+   /* Rounds needed: all of them for the exact suffix array (the SA|LCP parity artefact, zultra_cuda_window_sa_lcp); for
+      compression only until every suffix is ordered by its first 258 bytes - the match lists depend on the order only through
+      min(lcp, 258) (matchfinder.c:85-88), how suffixes that agree on 258 bytes or more are ordered among themselves changes no
+      clamped LCP and no record.  A 64 KiB byte run needs 14 rounds for its exact order and 6 for this. */
+   for (uint32_t h = (uint32_t)nbytes; m > 0 && (sa_exact || h < ZB_MAX_MATCH); h <<= 1) {
       stat_sa_rounds++;
       const long mm = m;
       /* key = (current rank, rank of the suffix h further; suffixes running off the window sort first, shorter first) */
@@ -562,7 +567,7 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
 /* Match lists, kernel B: the text walk of zb_mf_scan for the positions kernel A queued, one WARP per position.  The tile's
    text is in shared memory; the 32 lanes test 32 positions j of (best, i) per step for the 3-byte prefix, candidates are
    compared 32 bytes at a time, nearest first.  Control flow is warp-uniform. */
-#define ZB_MT_THREADS 256
+#define ZB_MT_THREADS 512      /* at most; 256 for tiles of <= 8192 main positions */
 __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *td, int first, const uint32_t *lists, size_t stride, const uint32_t *qcnt,
                                                               zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, const ZbWinDesc *wd, const uint8_t *T) {
    extern __shared__ uint32_t zb_smw[];
@@ -675,6 +680,11 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
       7 words per window position instead of 33. */
    if (tile_main > ZB_MF_TILE_MAX) tile_main = ZB_MF_TILE_MAX;
    while (ZB_MAX_OFFSET % tile_main) tile_main >>= 1;
+   {  /* batches of small streams (windows of a few tiles at most): the larger tile only costs occupancy there */
+      uint32_t mx = 0;
+      for (int w = 0; w < nwin; w++) mx = std::max(mx, h_win[w].len);
+      if (mx <= 4 * ZB_MAX_OFFSET && tile_main > 8192) tile_main = 8192;
+   }
    const uint32_t GU = 8, gspan = GU * ZB_MAX_OFFSET;
    uint32_t maxlen = 0;
    for (int w = 0; w < nwin; w++) maxlen = std::max(maxlen, h_win[w].len);
@@ -785,7 +795,11 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
       zb_mf_scan_k<<<cnt, ZB_MF_THREADS, smem, st>>>(td, first, unit_words.p, unit_cnt.p, ivb, qstride, stride, tq, mt, gl, go, wbs, tile_main, mf_ts_min, mf_ts_mul);
       if (g_zb_prof_on) zb_prof_end(st);
       if (g_zb_prof_on) { zb_tag("mf_text"); zb_prof_begin(0, st); }
-      zb_mf_text_k<<<cnt, ZB_MT_THREADS, smem_txt, st>>>(td, first, ivb, qstride, tq, mt, gl, go, wbs, wdp, Tp);
+      {  /* a 16384-position tile has twice the queue and 49 KB of text (4 CTAs per SM): twice the warps per CTA keep the SM as full */
+         static const int mt_thr = getenv("ZULTRA_CUDA_MT_THREADS") ? atoi(getenv("ZULTRA_CUDA_MT_THREADS")) : 0;
+         const int thr = (mt_thr == 256 || mt_thr == 512) ? mt_thr : (tile_main > 8192 ? 512 : 256);
+         zb_mf_text_k<<<cnt, thr, smem_txt, st>>>(td, first, ivb, qstride, tq, mt, gl, go, wbs, wdp, Tp);
+      }
       if (g_zb_prof_on) zb_prof_end(st);
       zb_count_launch(2);
       ZB_CUDA_CHECK(cudaGetLastError());
@@ -1996,38 +2010,46 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
          s = s1 + 1; if (s >= ZB_DW_RING) s -= ZB_DW_RING;
          int bestc = (int)(meta >> 16), bl = 0, bo = 0;
          if (M) {
-            uint32_t keyA = ZB_DW_INF, keyB = ZB_DW_INF;
-            if (K >= ZB_MIN_MATCH) {
-               const int k = ZB_MIN_MATCH + lane;
-               if (k <= K) {
-                  int idx = s1 - (k - 1); if (idx < 0) idx += ZB_DW_RING;
-                  keyA = ((uint32_t)((int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base) + lcA + 8192) << 6) | (uint32_t)(63 - k);
-               }
-               const int k2 = k + 32;
-               if (k2 <= K) {
-                  int idx = s1 - (k2 - 1); if (idx < 0) idx += ZB_DW_RING;
-                  keyB = ((uint32_t)((int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base) + lcB + 8192) << 6) | (uint32_t)(63 - k2);
-               }
+            /* ONE reduction per position: lane L prices the candidate lengths k = 3 + L and 35 + L of every short match that is
+               long enough, lane m the one length of leave-alone match m; key = (cost << 9) | (m << 6) | (63 - k), so the minimum is
+               the cheapest candidate, among equals the earliest match, then its longest length - the reference's order
+               (blockdeflate.c:272-312).  (A reduction per match made a position with 8 matches cost 800 cycles.) */
+            uint32_t valA = ZB_DW_INF, valB = ZB_DW_INF;      /* cost[i + k] - cost[i + 1] + lencost(k) + 8192 */
+            const int k = ZB_MIN_MATCH + lane, k2 = k + 32;
+            if (k <= K) {
+               int idx = s1 - (k - 1); if (idx < 0) idx += ZB_DW_RING;
+               valA = (uint32_t)((int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base) + lcA + 8192);
             }
+            if (k2 <= K) {
+               int idx = s1 - (k2 - 1); if (idx < 0) idx += ZB_DW_RING;
+               valB = (uint32_t)((int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base) + lcB + 8192);
+            }
+            uint32_t key = 0xffffffffu;
 #pragma unroll 1
-            for (int m = 0; m < M; m++) {       /* M is warp-uniform: a real loop, not 8 predicated copies */
-               {
-                  const uint32_t inf = sh.info[x][m];
-                  const int mlm = (int)(inf & 511u), fixed = (int)((inf >> 10) & 63u);
-                  int total = 0x7fffffff, kk = 0;
-                  if ((inf >> 9) & 1u) {   /* >= 40: only the full (clamped) length, even below 3 (SURVEY A-3) */
+            for (int m = 0; m < M; m++) {       /* M is warp-uniform */
+               const uint32_t inf = sh.info[x][m];
+               const int mlm = (int)(inf & 511u);
+               const uint32_t fixed = (inf >> 10) & 63u;
+               if ((inf >> 9) & 1u) {   /* >= 40: only the full (clamped) length, even below 3 (SURVEY A-3) */
+                  if (lane == m) {
                      int idx = s1 - (mlm - 1); if (idx < 0) idx += ZB_DW_RING;
                      const uint32_t cv = mlm == 1 ? base : (uint32_t)ring[idx];     /* cost[i+1] is the register copy */
-                     total = fixed + (int)(int16_t)(uint16_t)(cv - base);
-                     kk = mlm;
-                  } else if (mlm >= ZB_MIN_MATCH) {
-                     uint32_t c = (ZB_MIN_MATCH + lane <= mlm) ? keyA : ZB_DW_INF;
-                     if (mlm > 34) { const uint32_t c2 = (ZB_MIN_MATCH + 32 + lane <= mlm) ? keyB : ZB_DW_INF; c = c2 < c ? c2 : c; }
-                     c = __reduce_min_sync(0xffffffffu, c);
-                     total = (int)(c >> 6) - 8192 + fixed;
-                     kk = 63 - (int)(c & 63u);
+                     const uint32_t c = ((uint32_t)((int)fixed + (int)(int16_t)(uint16_t)(cv - base) + 8192) << 9) | ((uint32_t)m << 6);
+                     key = c < key ? c : key;
                   }
-                  if (total < bestc) { bestc = total; bl = kk; bo = (int)(inf >> 16); }
+               } else {
+                  if (k <= mlm) { const uint32_t c = ((valA + fixed) << 9) | ((uint32_t)m << 6) | (uint32_t)(63 - k); key = c < key ? c : key; }
+                  if (k2 <= mlm) { const uint32_t c = ((valB + fixed) << 9) | ((uint32_t)m << 6) | (uint32_t)(63 - k2); key = c < key ? c : key; }
+               }
+            }
+            key = __reduce_min_sync(0xffffffffu, key);
+            if (key != 0xffffffffu) {
+               const int total = (int)(key >> 9) - 8192;
+               if (total < bestc) {
+                  const uint32_t inf = sh.info[x][(key >> 6) & 7u];
+                  bestc = total;
+                  bl = ((inf >> 9) & 1u) ? (int)(inf & 511u) : 63 - (int)(key & 63u);
+                  bo = (int)(inf >> 16);
                }
             }
          }
