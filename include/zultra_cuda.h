@@ -122,6 +122,9 @@ int zultra_cuda_last_counters(zultra_cuda_ctx_t *pCtx, long long *pCounters8);
 
 /* kernels this library has launched in this process so far (all contexts, all host threads) */
 long long zultra_cuda_launch_count(void);
+/* ZULTRA_CUDA_TRACE=1: one more line "[zb <ms since the first traced event>] what" on stderr (the host library and the tool mark
+   their own milestones with it); a no-op otherwise */
+void zultra_cuda_trace(const char *pszWhat);
 
 /* per-kernel CUDA-event timing: zultra_cuda_profile(1) turns it on; collect returns rows {32-byte name, total ms, launches} and clears */
 void zultra_cuda_profile(int nOn);

@@ -41,6 +41,9 @@ def main():
             data, flags = None, 1
         elif name == "mix256m":
             data, flags = synth.mix(256 << 20), 2
+        elif ":" in name:      # generator:bytes, e.g. mozilla:6400000 (a GPU's share of a strongly scaled configuration)
+            g, n = name.split(":")
+            data, flags = getattr(synth, g)(int(n)), 2
         else:
             data, flags = np.ascontiguousarray(bench.gen_workload(name)), bench.WORKLOADS[name]["flags"]
         ctx = z.CudaCtx()

@@ -160,7 +160,7 @@ static zultra_status_t submit(zultra_stream_t *s, size_t n, int finalize) {
    const size_t cap = n + n / 8 + 4096 + (n / c->block_size + 1) * 64 * 6;
    if (grow(s, &j->out, &j->out_cap, 0, cap)) return ZULTRA_ERROR_MEMORY;
    if (!finalize) {
-      if (grow(s, &o->in, &o->in_cap, 0, keep + rest + 65536)) return ZULTRA_ERROR_MEMORY;
+      if (grow(s, &o->in, &o->in_cap, 0, (size_t)HISTORY_SIZE + (size_t)c->batch_blocks * c->block_size + 65536)) return ZULTRA_ERROR_MEMORY;   /* its final size at once */
       memcpy(o->in, j->in + total - keep, keep + rest);
       o->hist_len = (int)keep; o->in_len = rest;
    } else { o->hist_len = 0; o->in_len = 0; }
@@ -231,7 +231,9 @@ zultra_status_t zultra_stream_compress(zultra_stream_t *pStream, const int nDoFi
       if (pStream->avail_in && f->in_len <= batch) {
          size_t n = batch + 1 - f->in_len;
          if (n > pStream->avail_in) n = pStream->avail_in;
-         if (grow(pStream, &f->in, &f->in_cap, (size_t)f->hist_len + f->in_len, (size_t)f->hist_len + f->in_len + n)) { err = ZULTRA_ERROR_MEMORY; break; }
+         /* the staging buffer is asked for at its final size the first time (untouched pages cost nothing; doubling up to
+            it copied and faulted in as much again as the batch itself) */
+         if (grow(pStream, &f->in, &f->in_cap, (size_t)f->hist_len + f->in_len, f->in_len ? (size_t)f->hist_len + f->in_len + n : (size_t)HISTORY_SIZE + batch + 65536)) { err = ZULTRA_ERROR_MEMORY; break; }
          memcpy(f->in + f->hist_len + f->in_len, pStream->next_in, n);
          f->in_len += n; pStream->next_in += n; pStream->avail_in -= n; pStream->total_in += n;
       }
@@ -260,14 +262,17 @@ void zultra_stream_end(zultra_stream_t *pStream) {
    if (pStream->state && pStream->zfree) {
       zultra_compressor_t *c = pStream->state;
       int k;
+      zultra_cuda_trace("stream_end: begin");
       for (k = 0; k < 2; k++) if (c->job[k].running == 1) { pthread_join(c->job[k].th, NULL); c->job[k].running = 0; }
       if (c->ctx) zultra_cuda_ctx_release(c->ctx);      /* a context that saw a CUDA failure is destroyed there, not pooled */
+      zultra_cuda_trace("stream_end: context released");
       for (k = 0; k < 2; k++) {
          if (c->job[k].in) pStream->zfree(pStream->opaque, c->job[k].in);
          if (c->job[k].out) pStream->zfree(pStream->opaque, c->job[k].out);
       }
       pStream->zfree(pStream->opaque, c);
       pStream->state = NULL;
+      zultra_cuda_trace("stream_end: buffers freed");
    }
 }
 

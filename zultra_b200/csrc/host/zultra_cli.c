@@ -11,6 +11,7 @@
 #include <unistd.h>
 #include <zlib.h>
 #include "libzultra.h"
+#include "zultra_cuda.h"
 
 #define OPT_VERBOSE 1
 #define FMT_DEFLATE 2
@@ -19,6 +20,7 @@
 #define FMT_MASK 14
 #define CHUNK 16384
 
+static long long g_t0;
 static long long now_us(void) { struct timeval t; gettimeofday(&t, NULL); return (long long)t.tv_sec * 1000000LL + t.tv_usec; }
 static unsigned int lib_flags(unsigned int opt) { return (opt & FMT_ZLIB) ? ZULTRA_FLAG_ZLIB_FRAMING : ((opt & FMT_GZIP) ? ZULTRA_FLAG_GZIP_FRAMING : 0); }
 
@@ -49,6 +51,7 @@ static int do_compress(const char *in, const char *out, const char *dictfile, un
    if (!st) st = zultra_dictionary_load(dictfile, &dict, &dict_size);
    if (!st) { ib = (unsigned char *)malloc(CHUNK); ob = (unsigned char *)malloc(CHUNK); if (!ib || !ob) st = ZULTRA_ERROR_MEMORY; }
    if (!st) st = zultra_stream_init(&s, lib_flags(opt), 0);
+   zultra_cuda_trace("cli: stream initialised");
    if (!st && dict) st = zultra_stream_set_dictionary(&s, dict, dict_size);
    while (!flush && !st) {
       int progress = 0;
@@ -76,11 +79,13 @@ static int do_compress(const char *in, const char *out, const char *dictfile, un
    }
    {
       unsigned long long tin = s.total_in, tout = s.total_out;
+      zultra_cuda_trace("cli: last byte written");
       zultra_stream_end(&s);
       free(ob); free(ib);
       zultra_dictionary_free(&dict);
       if (fo) fclose(fo);
       if (fi) fclose(fi);
+      zultra_cuda_trace("cli: files closed");
       if (st != ZULTRA_STREAM_END) { report(st, in, out, dictfile); return 100; }
       if ((opt & OPT_VERBOSE) && tin && tout) {
          double dt = (double)(now_us() - t0) / 1000000.0;
@@ -218,6 +223,7 @@ int main(int argc, char **argv) {
    int bad = 0, have_cmd = 0, verify = 0, i;
    char cmd = 'z';
    unsigned int opt = 0;
+   g_t0 = now_us();
    /* the tool drives ZULTRA_CUDA_DEVICES GPUs (default one): unless the caller chose, expose only those to the CUDA runtime,
       whose start-up otherwise initialises every device of the box (seconds on an 8-GPU node, for a tool that may compress 48 KB) */
    {
@@ -264,10 +270,17 @@ int main(int argc, char **argv) {
       if (dict && (opt & FMT_MASK) != FMT_ZLIB) { fprintf(stderr, "dictionaries are only supported for the zlib framing\n"); return 100; }
       r = do_compress(in, out, dict, opt);
       if (r == 0 && verify) r = do_compare(out, in, dict, opt);
-      /* all files are closed: leave without the CUDA runtime's exit handlers, which free gigabytes of device buffers one by
-         one (0.8 - 2 s measured after a 100 MB run); the driver reclaims the process's memory in bulk */
-      fflush(NULL);
-      _exit(r);
+      /* all files are closed.  ZULTRA_CLI_EXIT: 0 = plain return, 1 = _exit without the CUDA runtime's exit handlers (default),
+         2 = free the pooled contexts first; with ZULTRA_CUDA_TRACE the milestones are printed so that the teardown can be timed */
+      {
+         const char *e = getenv("ZULTRA_CLI_EXIT"), *tr = getenv("ZULTRA_CUDA_TRACE");
+         const int mode = e ? atoi(e) : 1;
+         if (tr && atoi(tr)) fprintf(stderr, "[cli %9.2f ms] streams closed, exit mode %d\n", (double)(now_us() - g_t0) / 1000.0, mode);
+         if (mode == 2) { zultra_cuda_release_cached(); if (tr && atoi(tr)) fprintf(stderr, "[cli %9.2f ms] contexts released\n", (double)(now_us() - g_t0) / 1000.0); }
+         fflush(NULL);
+         if (mode == 1) _exit(r);
+      }
+      return r;
    }
    if (cmd == 'B') return do_cbench(in, out, opt);
    return 100;

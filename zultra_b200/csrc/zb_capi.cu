@@ -36,6 +36,8 @@ static void zb_trace(const char *what, const float *ms = 0) {
    else fprintf(stderr, "[zb %9.2f ms] %s\n", zb_now_ms() - t0, what);
 }
 
+extern "C" void zultra_cuda_trace(const char *what) { zb_trace(what ? what : ""); }
+
 static int ctx_enter(zultra_cuda_ctx_t *c) {
    if (!c) return ZULTRA_CUDA_ERR_ARG;
    if (cudaSetDevice(c->device) != cudaSuccess) return ZULTRA_CUDA_ERR_CUDA;
