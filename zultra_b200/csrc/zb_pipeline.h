@@ -18,8 +18,12 @@
 #include <cuda_pipeline.h>
 #endif
 
+#ifndef ZB_CG
 #define ZB_CG 1024        /* positions per greedy-path chunk */
+#endif
+#ifndef ZB_CP
 #define ZB_CP 1024        /* positions per parsed-path chunk */
+#endif
 #define ZB_CD 2048        /* positions per parse (DP) chunk */
 #define ZB_WU 384         /* parse warm-up positions past the chunk end (>= 258; text re-synchronises well within it, the rest is repaired) */
 #define ZB_TOKI 256       /* tokens per prefix-histogram interval */
@@ -87,6 +91,14 @@ struct ZbStreamOut {
 ZB_HD void zb_tok_count(const uint8_t *T, uint32_t p, uint32_t len, uint32_t off, int *lc, int *oc, int sign) {
    if (len >= ZB_MIN_MATCH) { lc[zb_len_sym(len - ZB_MIN_MATCH)] += sign; oc[zb_off_sym(off)] += sign; }
    else lc[T[p]] += sign;
+}
+
+/* Warm-up of a parse chunk whose candidates read at most `reach` positions past its end: the configured warm-up WU is the
+   258-position horizon plus a settling margin; the same margin above `reach` (stage_parse, D2). */
+ZB_HD int zb_warmup_len(int WU, int reach) {
+   const int margin = WU > ZB_MAX_MATCH ? WU - ZB_MAX_MATCH : 0;
+   const int w = reach + margin;
+   return w < WU ? w : WU;
 }
 
 template <class T> struct ZbBuf {
@@ -195,6 +207,7 @@ struct ZbPipe {
    ZbBuf<ZbSub> sub; ZbBuf<ZbSubTabs> tabs; ZbBuf<uint32_t> dchunk_sub, pchunk_sub;
    ZbBuf<zb_match_t> best; ZbBuf<int16_t> sig_true, sig_warm, sig_new; ZbBuf<uint8_t> dok; ZbBuf<uint32_t> dbad;
    ZbBuf<uint32_t> pentry, pbits, cand /* 16-byte candidate records, zb_cand_pack */; ZbBuf<uint16_t> dpfar;   /* dpfar: cost rows of the thread-per-chunk parse kernel */
+   ZbBuf<int> dreach;       /* per parse chunk: how far past its end its candidates read (0..258), stage_parse */
    /* output */
    ZbBuf<uint32_t> out; ZbBuf<ZbStreamOut> sout;
    std::vector<ZbStreamOut> h_sout;
@@ -389,7 +402,7 @@ inline void ZbPipe::stage_sa() {
 __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *td, int first, const uint32_t *unit_words, const uint32_t *unit_cnt, uint32_t *queues, size_t qstride,
                                                               size_t stride, uint32_t *qcnt, zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, uint32_t tile_main,
                                                               int ts_min, int ts_mul) {
-   extern __shared__ uint32_t zb_smw[];
+   extern __shared__ __align__(16) uint32_t zb_smw[];
    __shared__ uint32_t next_m, nq, wcnt[32], wtail[32];
    const int k = blockIdx.x;
    const ZbTileDesc t = td[first + k];
@@ -570,29 +583,43 @@ __global__ void __launch_bounds__(ZB_MF_THREADS) zb_mf_scan_k(const ZbTileDesc *
 #define ZB_MT_THREADS 512      /* at most; 256 for tiles of <= 8192 main positions */
 __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *td, int first, const uint32_t *lists, size_t stride, const uint32_t *qcnt,
                                                               zb_match_t *mt, uint16_t *gl, uint16_t *go, const uint32_t *wbs, const ZbWinDesc *wd, const uint8_t *T) {
-   extern __shared__ uint32_t zb_smw[];
+   extern __shared__ __align__(16) uint32_t zb_smw[];
    __shared__ uint32_t next_q;
+   __shared__ __align__(8) uint64_t txt_bar;
    const int k = blockIdx.x;
    const uint32_t nq = qcnt[k];
    if (nq == 0) return;
    const ZbTileDesc t = td[first + k];
    const uint32_t nlook = t.m0 - t.lo;
-   uint8_t *txt = (uint8_t *)zb_smw;
    const uint32_t *queue = lists + (size_t)k * stride;
+   /* The tile's text comes in as ONE bulk copy (TMA, cp.async.bulk): global -> shared without passing through registers, one
+      thread issues it and an mbarrier counts the bytes in.  Source, destination and size of a bulk copy are multiples of 16, so
+      the shared copy sits at the same offset modulo 16 as the source (`delta`), the whole 16-byte pieces go by TMA and the
+      ragged head and tail (< 16 bytes each) bytewise.  All text indices below carry `delta`. */
+   const uint8_t *tsrc = T + wd[t.win].in_off + t.lo;
+   const uint32_t delta = (uint32_t)((uintptr_t)tsrc & 15u);
+   uint8_t *txt = (uint8_t *)zb_smw;            /* txt[delta + x] = window byte t.lo + x */
    {
-      const uint8_t *tsrc = T + wd[t.win].in_off + t.lo;
       uint32_t ntxt = t.hi - t.lo + ZB_MAX_MATCH;
       if (ntxt > t.wlen - t.lo) ntxt = t.wlen - t.lo;
-      /* 4 bytes per thread once the source is aligned */
-      const uint32_t head = (uint32_t)((4u - ((uintptr_t)tsrc & 3u)) & 3u);
-      for (uint32_t e = threadIdx.x; e < head && e < ntxt; e += blockDim.x) txt[e] = tsrc[e];
-      /* shared copy keeps the same byte offsets, so word stores need (e & 3) == head & 3: go bytewise unless head == 0 */
-      if (head == 0) {
-         const uint32_t nw4 = ntxt >> 2;
-         for (uint32_t e = threadIdx.x; e < nw4; e += blockDim.x) zb_smw[e] = ((const uint32_t *)tsrc)[e];
-         for (uint32_t e = (nw4 << 2) + threadIdx.x; e < ntxt; e += blockDim.x) txt[e] = tsrc[e];
-      } else {
-         for (uint32_t e = head + threadIdx.x; e < ntxt; e += blockDim.x) txt[e] = tsrc[e];
+      uint32_t head = (16u - delta) & 15u; if (head > ntxt) head = ntxt;
+      const uint32_t bulk = (ntxt - head) & ~15u;
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&txt_bar);
+      if (threadIdx.x == 0) {
+         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar));
+         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      /* the async proxy sees the initialised barrier */
+         if (bulk) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bulk) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(txt + delta + head)), "l"(tsrc + head), "r"(bulk), "r"(bar) : "memory");
+         }
+      }
+      for (uint32_t e = threadIdx.x; e < head; e += blockDim.x) txt[delta + e] = tsrc[e];
+      for (uint32_t e = head + bulk + threadIdx.x; e < ntxt; e += blockDim.x) txt[delta + e] = tsrc[e];
+      __syncthreads();      /* the barrier's initialisation is visible to every thread before any of them polls it */
+      if (bulk) {
+         uint32_t ok = 0;
+         while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar) : "memory");
       }
    }
    if (threadIdx.x == 0) next_q = 0;
@@ -614,40 +641,78 @@ __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *
       const uint32_t m = c0 & 0x3fffu, lvl = c0 >> 19, bound = c1 & 0x1ffu;
       const int nm = (int)((c0 >> 14) & 15u);
       const bool moved = (c0 >> 18) & 1u;
-      const int i = (int)(nlook + m);
+      const int i = (int)(nlook + m + delta);
       const int best = i - 1 - (int)(c1 >> 9);
       const uint32_t k3 = (uint32_t)txt[i] | ((uint32_t)txt[i + 1] << 8) | ((uint32_t)txt[i + 2] << 16);
       /* record number d (in order of discovery = increasing length) is kept by lane d % 32; only the last 8 can survive */
       uint32_t myrec = 0, curmax = 0;
       int nd = 0;
       bool done = false;
-      for (int jb = i - 1; jb > best && !done; jb -= 32) {
-         const int j = jb - lane;
-         bool hit = false;
-         if (j > best) {   /* bytes j..j+2 out of the two aligned words around them (the buffer is padded by a word) */
-            const uint32_t w0 = zb_smw[j >> 2], w1 = zb_smw[(j >> 2) + 1];
-            hit = (__funnelshift_r(w0, w1, (uint32_t)(j & 3) << 3) & 0xffffffu) == k3;
-         }
-         uint32_t hits = __ballot_sync(0xffffffffu, hit);
-         while (hits && !done) {
-            const int h = __ffs((int)hits) - 1;
-            hits &= hits - 1u;
-            const int jh = jb - h;
-            uint32_t len = bound;
-            for (uint32_t o = ZB_MIN_MATCH; o < bound; o += 32) {
-               const uint32_t xo = o + (uint32_t)lane;
-               const bool neq = xo < bound && txt[jh + xo] != txt[i + xo];
-               const uint32_t mm = __ballot_sync(0xffffffffu, neq);
-               if (mm) { len = o + (uint32_t)(__ffs((int)mm) - 1); break; }
+      /* one candidate jh (nearest first): its match length against i, 32 bytes per ballot, kept when strictly longer */
+#define ZB_MT_TRY(jh_)                                                                                              \
+      {                                                                                                             \
+         const int jh = (jh_);                                                                                      \
+         uint32_t len = bound;                                                                                      \
+         for (uint32_t o = ZB_MIN_MATCH; o < bound; o += 32) {                                                      \
+            const uint32_t xo = o + (uint32_t)lane;                                                                 \
+            const bool neq = xo < bound && txt[jh + xo] != txt[i + xo];                                             \
+            const uint32_t mm = __ballot_sync(0xffffffffu, neq);                                                    \
+            if (mm) { len = o + (uint32_t)(__ffs((int)mm) - 1); break; }                                            \
+         }                                                                                                          \
+         if (len > curmax) {                                                                                        \
+            if (lane == (nd & 31)) myrec = len | ((uint32_t)(i - jh) << 16);                                        \
+            nd++;                                                                                                   \
+            curmax = len;                                                                                           \
+            if (len == bound) done = true;                                                                          \
+         }                                                                                                          \
+      }
+      if (i - 1 - best <= 64) {
+         /* short interval (batches of small streams: most of them): one position per lane and step */
+         for (int jb = i - 1; jb > best && !done; jb -= 32) {
+            const int j = jb - lane;
+            bool hit = false;
+            if (j > best) {   /* bytes j..j+2 out of the two aligned words around them (the buffer is padded by a word) */
+               const uint32_t w0 = zb_smw[j >> 2], w1 = zb_smw[(j >> 2) + 1];
+               hit = (__funnelshift_r(w0, w1, (uint32_t)(j & 3) << 3) & 0xffffffu) == k3;
             }
-            if (len > curmax) {
-               if (lane == (nd & 31)) myrec = len | ((uint32_t)(i - jh) << 16);
-               nd++;
-               curmax = len;
-               if (len == bound) done = true;
+            uint32_t hits = __ballot_sync(0xffffffffu, hit);
+            while (hits && !done) {
+               const int h = __ffs((int)hits) - 1;
+               hits &= hits - 1u;
+               ZB_MT_TRY(jb - h)
+            }
+         }
+      } else {
+      /* 128 positions per step: lane L tests the four positions q + 3 .. q (q = jb - 4 L - 3, a multiple of 4) out of the two
+         aligned words at q; bit s of its nibble = position jb - 4 L - s hit.  Hits are then taken nearest first: lanes in order,
+         bits of a lane's nibble in order.  The first step starts at the aligned group holding i - 1; positions >= i and <= best
+         are masked out. */
+      for (int jb = (i - 1) | 3; jb > best && !done; jb -= 128) {
+         const int q = jb - 4 * lane - 3;
+         uint32_t nib = 0;
+         if (q + 3 > best) {
+            const uint32_t w0 = zb_smw[q >> 2], w1 = zb_smw[(q >> 2) + 1];
+            nib = ((((__funnelshift_r(w0, w1, 24) ^ k3) & 0xffffffu) == 0u) ? 1u : 0u) | ((((__funnelshift_r(w0, w1, 16) ^ k3) & 0xffffffu) == 0u) ? 2u : 0u) |
+                  ((((w0 >> 8) ^ k3) == 0u) ? 4u : 0u) | ((((w0 ^ k3) & 0xffffffu) == 0u) ? 8u : 0u);
+            const int hi_s = q + 3 - best;       /* s < hi_s: position above best */
+            if (hi_s < 4) nib &= (1u << hi_s) - 1u;
+            const int lo_s = q + 4 - i;          /* s >= lo_s: position below i (first step only; at most 3) */
+            if (lo_s > 0) nib &= ~((1u << lo_s) - 1u);
+         }
+         uint32_t any = __ballot_sync(0xffffffffu, nib != 0u);
+         while (any && !done) {
+            const int hl = __ffs((int)any) - 1;
+            any &= any - 1u;
+            uint32_t nb = __shfl_sync(0xffffffffu, nib, hl);
+            while (nb && !done) {
+               const int sb = __ffs((int)nb) - 1;
+               nb &= nb - 1u;
+               ZB_MT_TRY(jb - 4 * hl - sb)
             }
          }
       }
+      }
+#undef ZB_MT_TRY
       /* slots nm.. of the record: [pending record of the rank walk, unless a nearer position reached the same level] then
          the text-walk records, longest first; lane z writes slot z */
       const uint32_t p = t.m0 + m;
@@ -771,7 +836,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    stat_tiles = ntile;
 #ifndef ZB_EMU
    const size_t smem = (stride + 2) * 4 + (size_t)tile_main * 2;
-   const size_t smem_txt = (stride + ZB_MAX_MATCH + 7) & ~(size_t)3;
+   const size_t smem_txt = (stride + ZB_MAX_MATCH + 16 + 7) & ~(size_t)3;      /* + the source's offset modulo 16 (zb_mf_text_k) */
    const ZbWinDesc *wdp = win.p; const uint8_t *Tp = in_ptr;
    tile_q.need(nw_tiles);
    if (zb_failed()) return;
@@ -779,7 +844,7 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
    {  /* the limit is a per-function global: always the largest configuration, so concurrent host threads cannot undercut each other */
       const size_t smax = ((size_t)ZB_MAX_OFFSET + ZB_MF_TILE_MAX + 2) * 4 + (size_t)ZB_MF_TILE_MAX * 2;
       ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_mf_scan_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
-      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_mf_text_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)ZB_MAX_OFFSET + ZB_MF_TILE_MAX + ZB_MAX_MATCH + 7) & ~(size_t)3)));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_mf_text_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(((size_t)ZB_MAX_OFFSET + ZB_MF_TILE_MAX + ZB_MAX_MATCH + 16 + 7) & ~(size_t)3)));
    }
 #else
    tile_pd.need((size_t)nw_tiles * tile_main);
@@ -1651,9 +1716,10 @@ struct ZbDpTab { uint8_t lit[256]; uint8_t len[256]; uint8_t off[32]; uint32_t l
 /* the 259 relative costs at `pos0` (the signature two neighbouring chunks are compared by), read back from the scratch row:
    position p was done at step from - 1 - p; positions at and above `from` are the zero guess */
 __device__ __forceinline__ void zb_dp_signature(int16_t *__restrict__ dst, size_t SS, const uint16_t *__restrict__ far0, int pos0, int from, int end, int t, uint32_t cprev, bool warm,
+                                                const int qmax /* entries 0..qmax are written (the verify step reads no others of a warm signature) */,
                                                 const int NT = ZB_DP_THREADS /* elements between consecutive steps of the cost row */) {
    /* loads batched 8 deep: each is an L2 round trip, and nothing else of this thread is in flight here */
-   for (int q0 = 0; q0 <= ZB_MAX_MATCH; q0 += 8) {
+   for (int q0 = 0; q0 <= qmax; q0 += 8) {
       uint32_t v[8];
 #pragma unroll
       for (int j = 0; j < 8; j++) { const int tt = t - 1 - (q0 + j); v[j] = (tt >= 0 && q0 + j <= ZB_MAX_MATCH) ? (uint32_t)far0[(size_t)tt * NT] : 0u; }
@@ -1743,7 +1809,7 @@ __device__ __forceinline__ void zb_dp_range(const uint8_t *__restrict__ T, const
 template <int UNR, int MINB>
 __global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, long ndch, int pass, const ZbWinDesc *wd,
                                                                const uint32_t *wbs, const uint8_t *T, const uint4 *cand, uint32_t *bm, int16_t *sgt, int16_t *sgw,
-                                                               size_t SS, uint16_t *far, int CD, int WU, int nslot) {
+                                                               size_t SS, uint16_t *far, int CD, int WU, int nslot, const int *reach) {
    extern __shared__ __align__(16) uint8_t zb_dp_sm[];
    uint16_t *ring_s = (uint16_t *)zb_dp_sm;                                   /* [ZB_NR][ZB_DP_THREADS] */
    ZbDpTab *tab_s = (ZbDpTab *)(zb_dp_sm + ZB_NR * ZB_DP_THREADS * 2);        /* [nslot] */
@@ -1770,7 +1836,10 @@ __global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub
    const int lo = (int)(s.ps + k * CD);
    const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
    const int end = (int)s.pe;
-   int from = hi + WU; if (from > end) from = end;
+   /* adaptive warm-up (reach != 0): the chunk only reads costs up to `reach` positions past its end, so only those have to be
+      right, and the warm-up is the settling margin above THEM instead of above the full 258-position horizon */
+   const int rc = reach ? reach[c] : ZB_MAX_MATCH;
+   int from = hi + zb_warmup_len(WU, rc); if (from > end) from = end;
    uint16_t *far0 = far + (size_t)blockIdx.x * (size_t)(CD + WU) * ZB_DP_THREADS + threadIdx.x;
    int16_t *sw = sgw + (size_t)c, *sg = sgt + (size_t)c;
    int step = 0; uint32_t cprev = 0;
@@ -1779,7 +1848,7 @@ __global__ void __launch_bounds__(ZB_DP_THREADS, MINB) zb_parse_dp_k(const ZbSub
 #pragma unroll 1
    for (int phase = 0; phase < 2; phase++) {
       zb_dp_range<UNR>(t, cand + gb, tab, phase ? lo : hi, phase ? hi : from, bm + gb, ring0, far0, step, cprev, phase != 0);
-      zb_dp_signature(phase ? sg : sw, SS, far0, phase ? lo : hi, from, end, step, cprev, phase == 0);
+      zb_dp_signature(phase ? sg : sw, SS, far0, phase ? lo : hi, from, end, step, cprev, phase == 0, phase ? ZB_MAX_MATCH : rc);
    }
 }
 
@@ -2073,7 +2142,7 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
    verifies again afterwards, so a race with a neighbouring run costs a round, never correctness. */
 __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb, const ZbSubTabs *tb, const uint32_t *dcs, const uint32_t *badlist, int nbad, const uint8_t *ok,
                                                                 const ZbWinDesc *wd, const uint32_t *wbs, const uint8_t *T, const zb_match_t *mt, zb_match_t *bm,
-                                                                int16_t *sgt, int16_t *sgw, size_t SS, int CD, long long *dbg) {
+                                                                int16_t *sgt, int16_t *sgw, size_t SS, int CD, long long *dbg, const int *reach) {
    __shared__ ZbDwShared sh_all[ZB_DW_WARPS];
    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
    const long g = (long)blockIdx.x * ZB_DW_WARPS + wi;
@@ -2118,13 +2187,14 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
       int16_t *sw = sgw + (size_t)nx;
       if (ok[nx]) {      /* (inside a run of wrong chunks nx is redone whatever it had assumed: no reason to wait for its 259 loads) */
          bool same = true;
+         const int lim = reach ? reach[nx] : ZB_MAX_MATCH;      /* nx reads no cost further out (adaptive warm-up, stage_parse) */
          int16_t got[(ZB_MAX_MATCH + 32) / 32];
 #pragma unroll
-         for (int j = 0; j < (ZB_MAX_MATCH + 32) / 32; j++) { const int e = lane + 32 * j; got[j] = e <= ZB_MAX_MATCH ? sw[(size_t)e * SS] : (int16_t)0; }      /* all in flight together */
+         for (int j = 0; j < (ZB_MAX_MATCH + 32) / 32; j++) { const int e = lane + 32 * j; got[j] = e <= lim ? sw[(size_t)e * SS] : (int16_t)0; }      /* all in flight together */
 #pragma unroll
          for (int j = 0; j < (ZB_MAX_MATCH + 32) / 32; j++) {
             const int e = lane + 32 * j;
-            if (e <= ZB_MAX_MATCH) {
+            if (e <= lim) {
                int sl = slot - e; if (sl < 0) sl += ZB_DW_RING;
                const int16_t v = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
                if (got[j] != v) same = false;
@@ -2212,8 +2282,10 @@ __global__ void __launch_bounds__(ZB_PH_THREADS) zb_path_hist_k(long npch, const
 inline void ZbPipe::stage_parse() {
    /* One thread per chunk: the chunk count is the parallelism.  ZB_CD positions per chunk when that still gives ~40 K chunks,
       shorter chunks (more warm-up overhead, shorter serial chains) for small batches such as one GPU's shard of a stream. */
-   /* (the thread-per-chunk kernel keeps ~1024 chunks resident per SM: aim at one full wave, within [512, ZB_CD]) */
-   int cd_auto = (int)(((long)P / ((long)zb_sm_count() * 1024) + 63) / 64 * 64);
+   /* (the thread-per-chunk kernel can keep 1152 chunks resident per SM; measured with the adaptive warm-up, it is fastest at
+      ~0.7 of that - 832 positions per chunk on the 100 MB text, 512 on the 51 MB binaries: fewer warps fight for the
+      shared-memory ring, and longer chunks carry less warm-up - and much slower just above one full wave) */
+   int cd_auto = (int)(((long)P / ((long)zb_sm_count() * 800) + 63) / 64 * 64);
    if (cd_auto < 128) cd_auto = 128;      /* small inputs (one 48 KB stream, a GPU's share of a strongly scaled 51 MB): short chunks = short serial chains, the warm-up then dominates a chunk */
    if (cd_auto > ZB_CD) cd_auto = ZB_CD;
    int WU = parse_wu; if (WU > 2048) WU = 2048;
@@ -2300,6 +2372,59 @@ inline void ZbPipe::stage_parse() {
    });
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
    const zb_match_t *mt = match.p; zb_match_t *bm = best.p;
+   /* Adaptive warm-up (round 2).  A chunk reads costs past its end only through the candidates of its last positions: `reach`
+      = max over its positions p of p + (longest candidate length of p) - chunk end, 0..258.  The chunk is right iff the relative
+      costs at its end .. end + reach are (all it ever reads), so only those entries of the two signatures are compared and the
+      warm-up is the settling margin above them, not above the full 258-position horizon: ~130 instead of 384 positions on text,
+      where the reach is a handful of positions (99th percentile 28).  With chunks shorter than the horizon (small inputs: CD =
+      128) a chunk's left neighbours read THROUGH it into its warm-up zone, so what a chunk needs right is
+      need(c) = max(reach(c), need(c - 1) - CD) - then every entry any comparison or repair start ever uses is either inside a
+      verified chunk or inside the verified part of a warm-up zone (induction from the exact last chunk of the sub-block).
+      The lists do not change over the passes: once per batch, 8 tasks of 33 positions per chunk. */
+   static const int awu_env = getenv("ZULTRA_CUDA_PARSE_AWU") ? atoi(getenv("ZULTRA_CUDA_PARSE_AWU")) : 1;
+   const bool awu = awu_env && WU > ZB_MAX_MATCH;
+   int *rch = 0;
+   if (awu && ndch > 0) {
+      dreach.need(2 * (size_t)ndch + 2);
+      if (zb_failed()) return;
+      int *need = dreach.p;
+      rch = dreach.p + ndch + 1;      /* raw reach first, need() derived from it below */
+      zb_memset(st, rch, 0, (size_t)ndch * 4);
+      zb_tag("parse_reach");
+      zb_launch(st, ndch * 8, ZB_LAMBDA(long x) {
+         const long c = x >> 3; const int part = (int)(x & 7);
+         const ZbSub sx = sb[dcs[c]];
+         const uint32_t k = (uint32_t)c - sx.dchunk_base;
+         if (k + 1 >= sx.ndchunk) return;      /* the last chunk of a sub-block starts from the exact end */
+         const int lo = (int)(sx.ps + k * CD), hi = lo + CD;
+         const zb_match_t *m0 = mt + ((size_t)wbs[sx.win] << 3);
+         int best_r = 0;
+         for (int p = hi - 1 - part * 33, e = 0; e < 33 && p >= lo && hi - p <= ZB_MAX_MATCH; e++, p--) {
+            const ZbCand cd = zb_cand_pack(zb_load_rec(m0, p), (int)sx.pe - p);
+            int ml = 0;
+            for (int z = 0; z < ZB_NMATCH; z++) {
+               const uint32_t ent = (cd.w[z >> 1] >> (16 * (z & 1))) & 0xffffu;
+               if (!ent) break;
+               const int l = (ent & 0x8000u) ? (int)((ent >> 5) & 511u) : (int)((ent >> 5) & 63u);
+               ml = l > ml ? l : ml;
+            }
+            const int r = p + ml - hi;
+            best_r = r > best_r ? r : best_r;
+         }
+         if (best_r > ZB_MAX_MATCH) best_r = ZB_MAX_MATCH;
+         if (best_r > 0) zb_atomic_max(rch + c, best_r);
+      }, 256);
+      {
+         const int *raw = rch;
+         zb_launch(st, ndch, ZB_LAMBDA(long c) {
+            const ZbSub sx = sb[dcs[c]];
+            int nd = raw[c];
+            for (long j = 1; j * CD < ZB_MAX_MATCH && c - j >= (long)sx.dchunk_base; j++) { const int r = raw[c - j] - (int)j * CD; nd = r > nd ? r : nd; }
+            need[c] = nd;
+         }, 256);
+      }
+      rch = need;
+   }
 #ifndef ZB_EMU
    /* candidate records (once: the match lists do not change over the passes) and the parse kernel's shared memory */
    const int dp_nslot = (int)(hc[2] < 1 ? 1 : (hc[2] > ZB_DP_THREADS ? ZB_DP_THREADS : hc[2]));
@@ -2337,7 +2462,7 @@ inline void ZbPipe::stage_parse() {
             const unsigned grid = (unsigned)((ndch + ZB_DP_THREADS - 1) / ZB_DP_THREADS);
             /* development variants (ZULTRA_CUDA_DP_VAR): k-loop unroll factor x CTAs per SM asked of the compiler */
             static const int var = getenv("ZULTRA_CUDA_DP_VAR") ? atoi(getenv("ZULTRA_CUDA_DP_VAR")) : 0;
-#define ZB_DP_LAUNCH(U_, B_) zb_parse_dp_k<U_, B_><<<grid, ZB_DP_THREADS, dp_smem, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, (const uint4 *)cand.p, (uint32_t *)bm, sgt, sgw, SS, dpfar.p, CD, WU, dp_nslot)
+#define ZB_DP_LAUNCH(U_, B_) zb_parse_dp_k<U_, B_><<<grid, ZB_DP_THREADS, dp_smem, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, (const uint4 *)cand.p, (uint32_t *)bm, sgt, sgw, SS, dpfar.p, CD, WU, dp_nslot, rch)
             if (var == 1) ZB_DP_LAUNCH(1, 9); else if (var == 2) ZB_DP_LAUNCH(2, 9); else if (var == 3) ZB_DP_LAUNCH(4, 10); else if (var == 4) ZB_DP_LAUNCH(2, 10); else if (var == 5) ZB_DP_LAUNCH(1, 10);
             else if (var == 6) ZB_DP_LAUNCH(2, 12); else if (var == 7) ZB_DP_LAUNCH(4, 9); else ZB_DP_LAUNCH(2, 9);      /* measured on B200: unroll 2 at 55 registers is the fastest of these */
 #undef ZB_DP_LAUNCH
@@ -2361,7 +2486,7 @@ inline void ZbPipe::stage_parse() {
             const int lo = (int)(s.ps + kc * CD);
             const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
             const int end = (int)s.pe;
-            int from = hi + WU; if (from > end) from = end;
+            int from = hi + zb_warmup_len(WU, rch ? rch[c] : ZB_MAX_MATCH); if (from > end) from = end;
             const ZbCostTab &ct = tb[dcs[c]].cost;
             std::vector<uint32_t> v((size_t)(from - lo) + 1, 0u);      /* cost of step tt (position from - 1 - tt) */
             uint32_t cprev = 0;
@@ -2396,7 +2521,7 @@ inline void ZbPipe::stage_parse() {
          const int lo = (int)(s.ps + k * CD);
          const int hi = (int)(lo + CD < (int)s.pe ? lo + CD : (int)s.pe);
          const int end = (int)s.pe;
-         int from = hi + WU; if (from > end) from = end;
+         int from = hi + zb_warmup_len(WU, rch ? rch[c] : ZB_MAX_MATCH); if (from > end) from = end;
          ZbRingLocal ring;
          for (int i = 0; i < ZB_RING; i++) ring.v[i] = 0;
          int slot = 0;
@@ -2437,7 +2562,8 @@ inline void ZbPipe::stage_parse() {
             const uint32_t k = (uint32_t)c - s.dchunk_base;
             if (!(pass > 0 && !s.is_dyn) && k + 1 < s.ndchunk) {
                const int16_t *a = sgw + (size_t)c, *b = sgt + (size_t)(c + 1);
-               for (int q = 0; q <= ZB_MAX_MATCH && good; q++) if (a[(size_t)q * SS] != b[(size_t)q * SS]) good = 0;
+               const int lim = rch ? rch[c] : ZB_MAX_MATCH;      /* the chunk reads no cost further out */
+               for (int q = 0; q <= lim && good; q++) if (a[(size_t)q * SS] != b[(size_t)q * SS]) good = 0;
             }
             ok[c] = good;
             if (!good) { const int at = zb_atomic_add((int *)cn + 7, 1); bad[at] = (uint32_t)c; }
@@ -2459,7 +2585,7 @@ inline void ZbPipe::stage_parse() {
          static const int fix_dbg = getenv("ZULTRA_CUDA_FIX_DEBUG") ? atoi(getenv("ZULTRA_CUDA_FIX_DEBUG")) : 0;
          long long *dbgp = 0;
          if (fix_dbg) { scratch.need((size_t)nbad * 10 + 64); dbgp = (long long *)scratch.p; zb_memset(st, dbgp, 0, (size_t)nbad * 40); }
-         zb_parse_fix_k<<<(unsigned)((nbad + ZB_DW_WARPS - 1) / ZB_DW_WARPS), ZB_DW_THREADS, 0, st>>>(sb, tb, dcs, bad, (int)nbad, ok, wd, wbs, T, mt, bm, sgt, sgw, SS, CD, dbgp);
+         zb_parse_fix_k<<<(unsigned)((nbad + ZB_DW_WARPS - 1) / ZB_DW_WARPS), ZB_DW_THREADS, 0, st>>>(sb, tb, dcs, bad, (int)nbad, ok, wd, wbs, T, mt, bm, sgt, sgw, SS, CD, dbgp, rch);
          if (fix_dbg) {
             std::vector<long long> hd((size_t)nbad * 5);
             zb_d2h(st, hd.data(), dbgp, hd.size() * 8); zb_sync(st);
