@@ -1510,22 +1510,35 @@ inline void ZbPipe::stage_split() {
          chk_stat.need((size_t)nchk * 18); chk_flag.need(nchk); chk_delta.need(2 * (size_t)nchk); chk_node.need(nchk);
          if (zb_failed()) return;
          uint16_t *cs = chk_stat.p; uint8_t *cf = chk_flag.p; int *cdl = chk_delta.p; uint32_t *cnode = chk_node.p;
-         zb_launch(st, ncur, ZB_LAMBDA(long x) { for (uint32_t k = 0; k < cur[x].nchk; k++) cnode[cur[x].chk_base + k] = (uint32_t)x; });
+         /* node of every check point: the last node whose base is <= c and that has check points (bases ascend with the node index) */
+         zb_launch(st, nchk, ZB_LAMBDA(long c) {
+            int lo = 0, hi = ncur - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cur[mid].chk_base <= (uint32_t)c) lo = mid; else hi = mid - 1; }
+            while (cur[lo].nchk == 0) lo--;      /* nodes without check points share the base of the next one */
+            cnode[c] = (uint32_t)lo;
+         }, 256);
          /* S2: 18-bin statistics of each check interval (blockdeflate.c:686-703) */
          zb_launch(st, nchk, ZB_LAMBDA(long c) {
             const ZbNode nd = cur[cnode[c]];
             const uint32_t k = (uint32_t)c - nd.chk_base;
             const uint32_t t1 = k == 0 ? 0 : nd.t0 + 256 * (k - 1), t2 = nd.t0 + 256 * k;
-            uint16_t s18[18];
-            for (int i = 0; i < 18; i++) s18[i] = 0;
+            /* the 18 counters (each <= 512: an interval is 256 tokens, the first one at most 512 - 512 bytes are consumed by then)
+               packed four to a 64-bit word and bumped by a shifted add: an indexed local array would live in local memory */
+            uint64_t w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0;
             const uint32_t gb = gv.wbs[nd.win]; const uint8_t *t = gv.T + gv.wd[nd.win].in_off;
             const uint32_t *a = gv.tp + gv.wtb[nd.win] + nd.ts;
             for (uint32_t q = t1; q < t2; q++) {
-               uint32_t p = a[q], l = gv.gl[gb + p];
-               if (l >= ZB_MIN_MATCH) s18[l >= 9 ? 17 : 16]++;
-               else { uint32_t b = t[p]; s18[((b >> 4) & 0xc) | (b & 3)]++; }
+               const uint32_t p = a[q], l = gv.gl[gb + p];
+               uint32_t idx;
+               if (l >= ZB_MIN_MATCH) idx = l >= 9 ? 17u : 16u;
+               else { const uint32_t b = t[p]; idx = ((b >> 4) & 0xcu) | (b & 3u); }
+               const uint64_t one = (uint64_t)1 << ((idx & 3u) * 16u);
+               const uint32_t wsel = idx >> 2;
+               w0 += wsel == 0 ? one : 0; w1 += wsel == 1 ? one : 0; w2 += wsel == 2 ? one : 0; w3 += wsel == 3 ? one : 0; w4 += wsel == 4 ? one : 0;
             }
-            for (int i = 0; i < 18; i++) cs[(size_t)c * 18 + i] = s18[i];
+            uint16_t *dst = cs + (size_t)c * 18;
+            for (int i = 0; i < 4; i++) { dst[i] = (uint16_t)(w0 >> (16 * i)); dst[4 + i] = (uint16_t)(w1 >> (16 * i)); dst[8 + i] = (uint16_t)(w2 >> (16 * i)); dst[12 + i] = (uint16_t)(w3 >> (16 * i)); }
+            dst[16] = (uint16_t)w4; dst[17] = (uint16_t)(w4 >> 16);
          });
          /* S3: drift test per check point (blockdeflate.c:706-721, unsigned arithmetic) */
 #ifndef ZB_EMU
@@ -1872,6 +1885,7 @@ struct ZbDwShared {            /* per warp */
    uint32_t info[32][ZB_NMATCH + 1];  /* decoded matches of the 32 positions of the current block (+1: bank spread) */
    uint32_t meta[32];                 /* M | K << 4 | literal cost << 16 */
    ZbCostTab tab;                     /* the sub-block's bit costs */
+   uint32_t pch[ZB_MAX_MATCH + 2];    /* byte-run shortcut: the 258 choice words one period of the run repeats (ZbDwUni::aE anchors them) */
 };
 
 /* Positions [lo, from) of one sub-block, descending.  Per block of 32 positions the lanes first decode one position each, in
@@ -1885,7 +1899,8 @@ struct ZbDwShared {            /* per warp */
    records stay the same.  The walker tracks the stretch of identical records it is in (whole blocks of 32), tests that
    periodicity once the stretch is 517 positions long, and from then on copies 32 choices per step instead of scanning them -
    a 64 KiB run of a mozilla-shaped input is one serial chain of 128 chunks, and this chain is what the repair's time is. */
-struct ZbDwUni { uint4 ra, rb; uint32_t rl, delta; int len, top; bool periodic; int n_copy, n_scan, n_slow; /* positions done by each path (ZULTRA_CUDA_FIX_DEBUG) */ };
+struct ZbDwUni { uint4 ra, rb; uint32_t rl, delta; int len, top; bool periodic; int aE; bool a_valid;      /* pch[j] = choice of position aE + 1 + j, while a_valid */
+                 int n_copy, n_scan, n_slow; /* positions done by each path (ZULTRA_CUDA_FIX_DEBUG) */ };
 
 __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const zb_match_t *__restrict__ match, int lo, int from, int end,
                                           zb_match_t *__restrict__ best, ZbDwShared &sh, int &slot, ZbDwUni &U, const int lane,
@@ -1920,7 +1935,7 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
             int y_ = x_ - ZB_MAX_MATCH; if (y_ < 0) y_ += ZB_DW_RING; \
             if ((((uint32_t)ring[x_] - (uint32_t)ring[y_]) & 0xffffu) != d_) ok_ = false; \
          } \
-         if (__all_sync(0xffffffffu, ok_)) { U.periodic = true; U.delta = d_; } \
+         if (__all_sync(0xffffffffu, ok_)) { U.periodic = true; U.delta = d_; U.a_valid = false; } \
       } \
    } while (0)
    for (int i0 = from - 1; i0 >= lo;) {      /* every path below steps i0 itself */
@@ -1934,52 +1949,65 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
          const bool mine = lane >= nb_pos || (na.x == a0.x && na.y == a0.y && na.z == a0.z && na.w == a0.w && nb.x == b0.x && nb.y == b0.y && nb.z == b0.z && nb.w == b0.w && nl == l0);
          const bool uniform = __all_sync(0xffffffffu, mine);
          cont = uniform && U.len > 0 && a0.x == U.ra.x && a0.y == U.ra.y && a0.z == U.ra.z && a0.w == U.ra.w && b0.x == U.rb.x && b0.y == U.rb.y && b0.z == U.rb.z && b0.w == U.rb.w && l0 == U.rl;
-         if (!uniform) { U.len = 0; U.periodic = false; }
-         else if (!cont) { U.ra = a0; U.rb = b0; U.rl = l0; U.len = 0; U.top = i0; U.periodic = false; }
+         if (!uniform) { U.len = 0; U.periodic = false; U.a_valid = false; }
+         else if (!cont) { U.ra = a0; U.rb = b0; U.rl = l0; U.len = 0; U.top = i0; U.periodic = false; U.a_valid = false; }
       }
       if (U.periodic && cont) {
-         /* The run shortcut, four blocks at a time while the chunk has them: one record per lane and block, all loads of a
-            round in flight together (a block a round exposed a full memory round trip per 32 positions: 52 cycles a position,
-            no better than the scan), the records of the next kilobyte pulled into L2 meanwhile. */
+         /* The run shortcut, four blocks (128 positions) a round while the chunk has them.  Inside the periodic stretch every
+            choice is the choice 258 above it, i.e. one of the 258 choice words above the place the shortcut first applied: they
+            are read once into shared memory (pch), so a round reads nothing it has just written - only the records, to see
+            that the run goes on, and those are loaded ONE ROUND AHEAD (and pulled into L2 a kilobyte ahead): the chain no
+            longer waits for a memory round trip per round (it did: ~1.5 us per 128 positions, 0.8 ms for a 64 KiB run). */
          bool wide = false;
-         while (i0 - 127 >= lo) {
-            uint4 xa[3], xb[3]; uint32_t xl[3];
+         if (i0 - 127 >= lo) {
+            if (!U.a_valid) {
+               for (int j = lane; j < ZB_MAX_MATCH; j += 32) sh.pch[j] = ((const uint32_t *)best)[i0 + 1 + j];
+               U.aE = i0; U.a_valid = true;
+               __syncwarp();
+            }
+            uint4 ca[3], cb[3]; uint32_t cl[3];
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                const int p = i0 - 32 * (k + 1) - lane;
                const uint4 *q = (const uint4 *)(match + ((size_t)p << 3));
-               xa[k] = __ldg(q); xb[k] = __ldg(q + 1); xl[k] = t[p];
+               ca[k] = __ldg(q); cb[k] = __ldg(q + 1); cl[k] = t[p];
             }
-            uint32_t cw[4];
+            while (i0 - 127 >= lo) {
+               uint4 ya[4], yb[4]; uint32_t yl[4];      /* the next round's records */
 #pragma unroll
-            for (int k = 0; k < 4; k++) cw[k] = ((const uint32_t *)best)[i0 - 32 * k - lane + ZB_MAX_MATCH];
+               for (int k = 0; k < 4; k++) {
+                  const int p = i0 - 128 - 32 * k - lane;
+                  ya[k] = make_uint4(0u, 0u, 0u, 0u); yb[k] = ya[k]; yl[k] = 0;
+                  if (p >= lo) { const uint4 *q = (const uint4 *)(match + ((size_t)p << 3)); ya[k] = __ldg(q); yb[k] = __ldg(q + 1); yl[k] = t[p]; }
+               }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-               const int pf = i0 - 1024 - 32 * k - lane;
-               if (pf >= pf_lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(match + ((size_t)pf << 3)));
+               for (int k = 0; k < 4; k++) {
+                  const int pf = i0 - 1024 - 32 * k - lane;
+                  if (pf >= pf_lo) asm volatile("prefetch.global.L2 [%0];" :: "l"(match + ((size_t)pf << 3)));
+               }
+               bool okb = na.x == U.ra.x && na.y == U.ra.y && na.z == U.ra.z && na.w == U.ra.w && nb.x == U.rb.x && nb.y == U.rb.y && nb.z == U.rb.z && nb.w == U.rb.w && nl == U.rl;
+#pragma unroll
+               for (int k = 0; k < 3; k++)
+                  okb = okb && ca[k].x == U.ra.x && ca[k].y == U.ra.y && ca[k].z == U.ra.z && ca[k].w == U.ra.w && cb[k].x == U.rb.x && cb[k].y == U.rb.y && cb[k].z == U.rb.z && cb[k].w == U.rb.w && cl[k] == U.rl;
+               if (!__all_sync(0xffffffffu, okb)) break;      /* the single-block logic below takes it from here (this block is still `cont`) */
+#pragma unroll
+               for (int k = 0; k < 4; k++) {
+                  int sl = s + 1 + 32 * k + lane; if (sl >= ZB_DW_RING) sl -= ZB_DW_RING;
+                  int sh258 = sl - ZB_MAX_MATCH; if (sh258 < 0) sh258 += ZB_DW_RING;
+                  ring[sl] = (uint16_t)((uint32_t)ring[sh258] + U.delta);
+                  const int i = i0 - 32 * k - lane;
+                  ((uint32_t *)best)[i] = sh.pch[ZB_MAX_MATCH - 1 - (U.aE - i) % ZB_MAX_MATCH];
+               }
+               wide = true;
+               i0 -= 128;
+               s += 128; if (s >= ZB_DW_RING) s -= ZB_DW_RING;
+               U.len += 128; U.n_copy += 128;
+               na = ya[0]; nb = yb[0]; nl = yl[0];
+#pragma unroll
+               for (int k = 0; k < 3; k++) { ca[k] = ya[k + 1]; cb[k] = yb[k + 1]; cl[k] = yl[k + 1]; }
+               __syncwarp();
+               base = ring[s];
             }
-            bool okb = na.x == U.ra.x && na.y == U.ra.y && na.z == U.ra.z && na.w == U.ra.w && nb.x == U.rb.x && nb.y == U.rb.y && nb.z == U.rb.z && nb.w == U.rb.w && nl == U.rl;
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-               okb = okb && xa[k].x == U.ra.x && xa[k].y == U.ra.y && xa[k].z == U.ra.z && xa[k].w == U.ra.w && xb[k].x == U.rb.x && xb[k].y == U.rb.y && xb[k].z == U.rb.z && xb[k].w == U.rb.w && xl[k] == U.rl;
-            if (!__all_sync(0xffffffffu, okb)) break;      /* the single-block logic below takes it from here (this block is still `cont`) */
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-               int sl = s + 1 + 32 * k + lane; if (sl >= ZB_DW_RING) sl -= ZB_DW_RING;
-               int sh258 = sl - ZB_MAX_MATCH; if (sh258 < 0) sh258 += ZB_DW_RING;
-               ring[sl] = (uint16_t)((uint32_t)ring[sh258] + U.delta);
-               ((uint32_t *)best)[i0 - 32 * k - lane] = cw[k];
-            }
-            wide = true;
-            i0 -= 128;
-            s += 128; if (s >= ZB_DW_RING) s -= ZB_DW_RING;
-            U.len += 128; U.n_copy += 128;
-            {
-               const int p = i0 - lane;
-               if (p >= lo) { const uint4 *q = (const uint4 *)(match + ((size_t)p << 3)); na = __ldg(q); nb = __ldg(q + 1); nl = t[p]; }
-            }
-            __syncwarp();
-            base = ring[s];
          }
          if (wide) continue;      /* a fresh look at the block now at i0 (its records are loaded) */
       }
@@ -2072,8 +2100,22 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
          i0 -= 32;
          continue;
       }
+      /* what the lanes decoded for the block's positions is read one position ahead: the position's own chain (ring reads,
+         pricing, one reduction, ring write) then starts with its inputs already in registers */
+      uint32_t meta_n = sh.meta[0], infs_n[ZB_NMATCH];
+#pragma unroll
+      for (int m = 0; m < ZB_NMATCH; m++) infs_n[m] = sh.info[0][m];
       for (int x = 0; x < nb_pos; x++) {
-         const uint32_t meta = sh.meta[x];
+         const uint32_t meta = meta_n;
+         uint32_t infs[ZB_NMATCH];
+#pragma unroll
+         for (int m = 0; m < ZB_NMATCH; m++) infs[m] = infs_n[m];
+         {
+            const int xn = x + 1 < 32 ? x + 1 : 31;
+            meta_n = sh.meta[xn];
+#pragma unroll
+            for (int m = 0; m < ZB_NMATCH; m++) infs_n[m] = sh.info[xn][m];
+         }
          const int M = (int)(meta & 15u), K = (int)((meta >> 4) & 0xfffu);
          const int s1 = s;                           /* slot of i+1 */
          s = s1 + 1; if (s >= ZB_DW_RING) s -= ZB_DW_RING;
@@ -2094,9 +2136,10 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
                valB = (uint32_t)((int)(int16_t)(uint16_t)((uint32_t)ring[idx] - base) + lcB + 8192);
             }
             uint32_t key = 0xffffffffu;
-#pragma unroll 1
-            for (int m = 0; m < M; m++) {       /* M is warp-uniform */
-               const uint32_t inf = sh.info[x][m];
+#pragma unroll
+            for (int m = 0; m < ZB_NMATCH; m++) {
+               if (m >= M) break;                /* M is warp-uniform */
+               const uint32_t inf = infs[m];
                const int mlm = (int)(inf & 511u);
                const uint32_t fixed = (inf >> 10) & 63u;
                if ((inf >> 9) & 1u) {   /* >= 40: only the full (clamped) length, even below 3 (SURVEY A-3) */
@@ -2115,7 +2158,7 @@ __device__ __forceinline__ void zb_dw_run(const uint8_t *__restrict__ t, const z
             if (key != 0xffffffffu) {
                const int total = (int)(key >> 9) - 8192;
                if (total < bestc) {
-                  const uint32_t inf = sh.info[x][(key >> 6) & 7u];
+                  const uint32_t inf = sh.info[x][(key >> 6) & 7u];      /* (a dynamic pick out of infs[] would go through local memory) */
                   bestc = total;
                   bl = ((inf >> 9) & 1u) ? (int)(inf & 511u) : 63 - (int)(key & 63u);
                   bo = (int)(inf >> 16);
@@ -2159,7 +2202,7 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
    zb_match_t *b0 = bm + gb;
    const int end = (int)s.pe;
    int slot = 0;
-   ZbDwUni U; U.ra = make_uint4(0u, 0u, 0u, 0u); U.rb = U.ra; U.rl = 0; U.delta = 0; U.len = 0; U.top = -1; U.periodic = false; U.n_copy = U.n_scan = U.n_slow = 0;
+   ZbDwUni U; U.ra = make_uint4(0u, 0u, 0u, 0u); U.rb = U.ra; U.rl = 0; U.delta = 0; U.len = 0; U.top = -1; U.periodic = false; U.aE = 0; U.a_valid = false; U.n_copy = U.n_scan = U.n_slow = 0;
    const long long clk0 = clock64();
    {
       const uint32_t *src = (const uint32_t *)&tb[x].cost; uint32_t *dstw = (uint32_t *)&sh.tab;
@@ -2173,6 +2216,8 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
    __syncwarp();
    for (;;) {
       const int lo = (int)(s.ps + ((uint32_t)c - s.dchunk_base) * CD), hi = lo + CD;
+      const bool has_nx = (uint32_t)c != s.dchunk_base;
+      const uint8_t ok_c = ok[c], ok_nx = has_nx ? ok[c - 1] : (uint8_t)0;      /* asked for before the chunk's walk, there after it */
       zb_dw_run(t, m0, lo, hi, end, b0, sh, slot, U, lane, (int)s.ps);
       /* this chunk's true costs at its start */
       const uint16_t b = ring[slot];
@@ -2181,11 +2226,11 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
          int sl = slot - e; if (sl < 0) sl += ZB_DW_RING;
          sg[(size_t)e * SS] = (lo + e <= end) ? (int16_t)(uint16_t)(ring[sl] - b) : (int16_t)0;
       }
-      if ((uint32_t)c == s.dchunk_base) break;
+      if (!has_nx) break;
       const long nx = c - 1;
-      if (!ok[nx] && ok[c]) break;   /* c had been right, so nx heads a run of its own: another warp owns it */
+      if (!ok_nx && ok_c) break;   /* c had been right, so nx heads a run of its own: another warp owns it */
       int16_t *sw = sgw + (size_t)nx;
-      if (ok[nx]) {      /* (inside a run of wrong chunks nx is redone whatever it had assumed: no reason to wait for its 259 loads) */
+      if (ok_nx) {      /* (inside a run of wrong chunks nx is redone whatever it had assumed: no reason to wait for its 259 loads) */
          bool same = true;
          const int lim = reach ? reach[nx] : ZB_MAX_MATCH;      /* nx reads no cost further out (adaptive warm-up, stage_parse) */
          int16_t got[(ZB_MAX_MATCH + 32) / 32];
@@ -2283,9 +2328,9 @@ inline void ZbPipe::stage_parse() {
    /* One thread per chunk: the chunk count is the parallelism.  ZB_CD positions per chunk when that still gives ~40 K chunks,
       shorter chunks (more warm-up overhead, shorter serial chains) for small batches such as one GPU's shard of a stream. */
    /* (the thread-per-chunk kernel can keep 1152 chunks resident per SM; measured with the adaptive warm-up, it is fastest at
-      ~0.7 of that - 832 positions per chunk on the 100 MB text, 512 on the 51 MB binaries: fewer warps fight for the
+      ~0.65 of that - 960 positions per chunk on the 100 MB text, 512 on the 51 MB binaries: fewer warps fight for the
       shared-memory ring, and longer chunks carry less warm-up - and much slower just above one full wave) */
-   int cd_auto = (int)(((long)P / ((long)zb_sm_count() * 800) + 63) / 64 * 64);
+   int cd_auto = (int)(((long)P / ((long)zb_sm_count() * 720) + 32) / 64 * 64);
    if (cd_auto < 128) cd_auto = 128;      /* small inputs (one 48 KB stream, a GPU's share of a strongly scaled 51 MB): short chunks = short serial chains, the warm-up then dominates a chunk */
    if (cd_auto > ZB_CD) cd_auto = ZB_CD;
    int WU = parse_wu; if (WU > 2048) WU = 2048;
@@ -2438,6 +2483,9 @@ inline void ZbPipe::stage_parse() {
       ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
       ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<1, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
       ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<2, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<2, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+      ZB_CUDA_CHECK(cudaFuncSetAttribute(zb_parse_dp_k<2, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
    }
    if (npch > 0) {
       if (g_zb_prof_on) { zb_tag("parse_cand"); zb_prof_begin(0, st); }
@@ -2464,7 +2512,8 @@ inline void ZbPipe::stage_parse() {
             static const int var = getenv("ZULTRA_CUDA_DP_VAR") ? atoi(getenv("ZULTRA_CUDA_DP_VAR")) : 0;
 #define ZB_DP_LAUNCH(U_, B_) zb_parse_dp_k<U_, B_><<<grid, ZB_DP_THREADS, dp_smem, st>>>(sb, tb, dcs, ndch, pass, wd, wbs, T, (const uint4 *)cand.p, (uint32_t *)bm, sgt, sgw, SS, dpfar.p, CD, WU, dp_nslot, rch)
             if (var == 1) ZB_DP_LAUNCH(1, 9); else if (var == 2) ZB_DP_LAUNCH(2, 9); else if (var == 3) ZB_DP_LAUNCH(4, 10); else if (var == 4) ZB_DP_LAUNCH(2, 10); else if (var == 5) ZB_DP_LAUNCH(1, 10);
-            else if (var == 6) ZB_DP_LAUNCH(2, 12); else if (var == 7) ZB_DP_LAUNCH(4, 9); else ZB_DP_LAUNCH(2, 9);      /* measured on B200: unroll 2 at 55 registers is the fastest of these */
+            else if (var == 6) ZB_DP_LAUNCH(2, 12); else if (var == 7) ZB_DP_LAUNCH(4, 9); else if (var == 8) ZB_DP_LAUNCH(2, 6); else if (var == 9) ZB_DP_LAUNCH(4, 6);
+            else if (var == 10) ZB_DP_LAUNCH(2, 9); else ZB_DP_LAUNCH(2, 7);      /* measured on B200: unroll 2 at 62 registers (8 CTAs per SM) */
 #undef ZB_DP_LAUNCH
          }
          if (g_zb_prof_on) zb_prof_end(st);

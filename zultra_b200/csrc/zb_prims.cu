@@ -464,20 +464,33 @@ __global__ void __launch_bounds__(DS_THREADS) unit_dist_k(const uint32_t *sa_lcp
    const uint32_t seg = blockIdx.x - W.seg_base, r0 = seg * DS_SEG;
    const uint32_t nr = W.len - r0 < DS_SEG ? W.len - r0 : DS_SEG;
    const int nu = (int)W.nu;
+   {  /* A CTA lives for one load round trip plus a little work, and only a few fit an SM: pull the words of the CTA that will run
+         ~1024 segments from now (16 MB further on in the same array) into L2, one 128-byte line per thread.  The address is
+         exact inside a window and a few ranks off across a window end - it is only a hint. */
+      const size_t tot = (size_t)dw[nwin - 1].sa_base + dw[nwin - 1].len;
+      const size_t pf = (size_t)W.sa_base + r0 + (size_t)1024 * DS_SEG + (size_t)tid * 32;
+      if (tid < DS_SEG / 32 && pf < tot) asm volatile("prefetch.global.L2 [%0];" :: "l"(sa_lcp + pf));
+   }
    if (nu == 1) {      /* a window of one unit (batches of small streams): its list IS the unit's list */
       if (!SCATTER) { if (tid == 0) { segrec[(size_t)blockIdx.x * nu_max * 2] = nr; segrec[(size_t)blockIdx.x * nu_max * 2 + 1] = 0x1ffu | 0x10000u; } }
       else for (uint32_t idx = tid; idx < nr; idx += DS_THREADS) unit_words[(size_t)W.unit_base * (2 * ZB_MAX_OFFSET) + r0 + idx] = __ldg(sa_lcp + W.sa_base + r0 + idx);
       return;
    }
-   for (int e = tid; e < nu * DS_BROW; e += DS_THREADS) bm[e] = 0;
-   __syncthreads();
    uint32_t wv[DS_SEG / DS_THREADS];
+   /* all 16 loads of a thread first, in flight together (interleaved with the shared-memory atomics below they went out one
+      at a time: 57 % of the kernel's samples sat on the first use of the loaded word) */
 #pragma unroll
    for (int k = 0; k < DS_SEG / DS_THREADS; k++) {
       const uint32_t idx = (uint32_t)k * DS_THREADS + tid;
-      uint32_t v = 0x1ffu << ZB_POS_BITS;
+      wv[k] = idx < nr ? __ldg(sa_lcp + W.sa_base + r0 + idx) : (0x1ffu << ZB_POS_BITS);
+   }
+   for (int e = tid; e < nu * DS_BROW; e += DS_THREADS) bm[e] = 0;
+   __syncthreads();
+#pragma unroll
+   for (int k = 0; k < DS_SEG / DS_THREADS; k++) {
+      const uint32_t idx = (uint32_t)k * DS_THREADS + tid;
+      uint32_t v = wv[k];
       if (idx < nr) {
-         v = __ldg(sa_lcp + W.sa_base + r0 + idx);
          const uint32_t p = v & ZB_POS_MASK;
          const int ua = p < W.hist ? 0 : (int)((p - W.hist) >> 15);
          atomicOr(bm + ua * DS_BROW + (idx >> 5), 1u << (idx & 31));
@@ -602,7 +615,7 @@ void zb_unit_distribute(zb_stream_t st, const uint32_t *sa_lcp, const ZbDistWin 
    ZB_CUDA_CHECK(cudaFuncSetAttribute(unit_dist_k<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
    ZB_CUDA_CHECK(cudaFuncSetAttribute(unit_dist_k<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
    PROF_K("mf_unit_dist", st);
-   unit_dist_k<false><<<nseg_total, DS_THREADS, smem, st>>>(sa_lcp, dw, nwin, nu_max, segrec, unit_words);
+   unit_dist_k<false><<<nseg_total, DS_THREADS, smem - 2 * DS_SEG * 4, st>>>(sa_lcp, dw, nwin, nu_max, segrec, unit_words);      /* the count pass has no staging area: twice the CTAs per SM */
    unit_dist_offsets_k<<<(total_units + 127) / 128, 128, 0, st>>>(dw, nwin, nu_max, segrec, unit_cnt, total_units);
    unit_dist_k<true><<<nseg_total, DS_THREADS, smem, st>>>(sa_lcp, dw, nwin, nu_max, segrec, unit_words);
    PROF_E(st);
