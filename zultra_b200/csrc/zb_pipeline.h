@@ -315,6 +315,10 @@ inline void ZbPipe::stage_sa() {
    int rank_bits = 1; while ((1L << rank_bits) < n) rank_bits++;
    uint64_t *kB = keyB.p; uint32_t *vB = valB.p;
    stat_sa_rounds = 0;
+   uint32_t maxwin = 0;
+   for (int w = 0; w < nwin; w++) maxwin = std::max(maxwin, h_win[w].len);
+   int r2_bits = 1; while ((1L << r2_bits) < (long)maxwin + 512) r2_bits++;
+   const bool packed_keys = !sa_exact;      /* the exact sort doubles h past 512 and keeps the flag-bit form below */
    /* Rounds needed: all of them for the exact suffix array (the SA|LCP parity artefact, zultra_cuda_window_sa_lcp); for
       compression only until every suffix is ordered by its first 258 bytes - the match lists depend on the order only through
       min(lcp, 258) (matchfinder.c:85-88), how suffixes that agree on 258 bytes or more are ordered among themselves changes no
@@ -324,6 +328,21 @@ inline void ZbPipe::stage_sa() {
       const long mm = m;
       /* key = (current rank, rank of the suffix h further; suffixes running off the window sort first, shorter first) */
       zb_tag("sa_round_keys");
+      if (packed_keys) {
+         /* compression mode (h <= 258 < 512): a suffix running off its window gets wend - g (1..h), one inside rank + 512, so the
+            second key fits r2_bits and the pair is ONE contiguous key: 6 radix passes for 100 MB instead of 3 + 4 */
+         zb_launch(st, mm, ZB_LAMBDA(long a) {
+            uint32_t j = act[a], g = SA[j];
+            int w = zb_find_win(wbs, nw, g);
+            uint32_t wend = wbs[w + 1];
+            uint32_t r2;
+            if ((uint64_t)g + h < wend) r2 = (rk[g + h] - wbs[w]) + 512u;
+            else r2 = wend - g;
+            kA[a] = ((uint64_t)rk[g] << r2_bits) | r2;
+            vA[a] = g;
+         }, 256);
+         zb_sort_pairs(st, keyA.p, valA.p, keyB.p, valB.p, mm, 0, r2_bits + rank_bits, scratch.p);
+      } else {
       zb_launch(st, mm, ZB_LAMBDA(long a) {
          uint32_t j = act[a], g = SA[j];
          int w = zb_find_win(wbs, nw, g);
@@ -336,6 +355,7 @@ inline void ZbPipe::stage_sa() {
       }, 256);
       zb_sort_pairs(st, keyA.p, valA.p, keyB.p, valB.p, mm, 0, 23, scratch.p);
       zb_sort_pairs(st, keyA.p, valA.p, keyB.p, valB.p, mm, 32, 32 + rank_bits, scratch.p);
+      }
       zb_launch(st, mm, ZB_LAMBDA(long a) { head[a] = (a == 0 || kA[a] != kA[a - 1]) ? (uint32_t)a : 0u; SA[act[a]] = vA[a]; }, 256);
       zb_inclusive_max(st, head, grp, mm, scratch.p);
       zb_launch(st, mm, ZB_LAMBDA(long a) {
