@@ -1,0 +1,8 @@
+set -x
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_zconfigs.py -m gpu -x -q -k "not mix1g and not batch100k" ) > gpurun_out/r2_pytest31.log 2>&1
+tail -3 gpurun_out/r2_pytest31.log
+timeout 600 python tools/gpu_probe.py js48k enwik100m mozilla51m mix256m batch10k --out gpurun_out/r2_probe31.jsonl > gpurun_out/r2_probe31.log 2>&1
+for nb in 6 5; do
+  ZULTRA_CUDA_SA_NBYTES=$nb timeout 600 python tools/gpu_probe.py enwik100m mozilla51m batch10k --out gpurun_out/r2_probe31_nb$nb.jsonl > /dev/null 2>&1
+done

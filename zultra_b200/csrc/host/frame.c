@@ -7,6 +7,7 @@
  * GPU (zb_pipeline.h stage_checksum); the host versions here serve the public zultra_frame_update_checksum
  * entry point and the dictionary id.
  */
+#include <pthread.h>
 #include "libzultra.h"
 
 #define ADLER_MOD 65521u
@@ -23,7 +24,7 @@ static unsigned int adler32_update(unsigned int adler, const unsigned char *p, s
 }
 
 static unsigned int g_crc_tab[8][256];
-static int g_crc_ready = 0;
+static pthread_once_t g_crc_once = PTHREAD_ONCE_INIT;      /* streams of different host threads may meet here first */
 static void crc_init(void) {
    unsigned int i, k;
    for (i = 0; i < 256; i++) {
@@ -33,10 +34,9 @@ static void crc_init(void) {
    }
    for (i = 0; i < 256; i++)
       for (k = 1; k < 8; k++) g_crc_tab[k][i] = (g_crc_tab[k - 1][i] >> 8) ^ g_crc_tab[0][g_crc_tab[k - 1][i] & 0xff];
-   g_crc_ready = 1;
 }
 static unsigned int crc32_update(unsigned int crc, const unsigned char *p, size_t n) {
-   if (!g_crc_ready) crc_init();
+   pthread_once(&g_crc_once, crc_init);
    crc = ~crc;
    while (n >= 8) {
       unsigned int lo = ((unsigned int)p[0] | ((unsigned int)p[1] << 8) | ((unsigned int)p[2] << 16) | ((unsigned int)p[3] << 24)) ^ crc;

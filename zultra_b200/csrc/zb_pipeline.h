@@ -283,6 +283,10 @@ inline void ZbPipe::stage_sa() {
    if (zb_failed()) return;      /* fail fast: no launch ever sees a missing buffer (zb_run_batch reports the error) */
    int wb = 0; while ((1L << wb) < nwin) wb++;
    int nbytes = (64 - wb) / 8; if (nbytes > 7) nbytes = 7;
+   {  /* development knob: fewer key bytes = fewer radix passes over all suffixes, more suffixes left to the doubling rounds */
+      static const int nb_env = getenv("ZULTRA_CUDA_SA_NBYTES") ? atoi(getenv("ZULTRA_CUDA_SA_NBYTES")) : 0;
+      if (nb_env >= 3 && nb_env < nbytes) nbytes = nb_env;
+   }
    const uint8_t *T = in_ptr; const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const int nw = nwin;
    uint64_t *kA = keyA.p; uint32_t *vA = valA.p;
    zb_tag("sa_keys");
