@@ -135,11 +135,14 @@ def test_one_shot_across_256_block_batches_vs_compiled_reference(z, ref):
         assert z.memory_compress(data, flags, 32768) == ref.compress(data, flags=flags, block=32768), flags
 
 
-@pytest.mark.parametrize("cd", [704, 1024, 1856, 2048])
-def test_forced_parse_chunk_vs_compiled_reference(z, ref, monkeypatch, cd):
-    """The parse chunk length is chosen from the batch size (704 at 100 MB, up to 1856 for 256-block batches): force the
-    lengths the big configurations use on an input the reference finishes in seconds."""
+@pytest.mark.parametrize("cd,awu", [(704, 1), (960, 1), (1856, 1), (2048, 1), (64, 1), (128, 1), (200, 1), (320, 1), (512, 0), (128, 0)])
+def test_forced_parse_chunk_vs_compiled_reference(z, ref, monkeypatch, cd, awu):
+    """The parse chunk length is chosen from the batch size (960 at 100 MB, up to 1856 for 256-block batches, 128 for small
+    inputs): force the lengths the configurations use on an input the reference finishes in seconds - with the adaptive
+    warm-up (a chunk's warm-up and the verified part of its signature follow what its candidates reach; chunks shorter than
+    the 258-position horizon take the propagated form need(c) = max(reach(c), need(c - 1) - CD)) and with it switched off."""
     monkeypatch.setenv("ZULTRA_CUDA_PARSE_CD", str(cd))
+    monkeypatch.setenv("ZULTRA_CUDA_PARSE_AWU", str(awu))
     data = synth.mix(6 << 20, seed=300 + cd, seg_lo=400000, seg_hi=2 << 20)
     c = z.CudaCtx()
     try:

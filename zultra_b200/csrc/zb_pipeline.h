@@ -2450,7 +2450,7 @@ inline void ZbPipe::stage_parse() {
       need(c) = max(reach(c), need(c - 1) - CD) - then every entry any comparison or repair start ever uses is either inside a
       verified chunk or inside the verified part of a warm-up zone (induction from the exact last chunk of the sub-block).
       The lists do not change over the passes: once per batch, 8 tasks of 33 positions per chunk. */
-   static const int awu_env = getenv("ZULTRA_CUDA_PARSE_AWU") ? atoi(getenv("ZULTRA_CUDA_PARSE_AWU")) : 1;
+   const int awu_env = getenv("ZULTRA_CUDA_PARSE_AWU") ? atoi(getenv("ZULTRA_CUDA_PARSE_AWU")) : 1;      /* read per call: the tests flip it */
    const bool awu = awu_env && WU > ZB_MAX_MATCH;
    int *rch = 0;
    if (awu && ndch > 0) {
