@@ -676,8 +676,6 @@ __global__ void __launch_bounds__(ZB_MT_THREADS) zb_mf_text_k(const ZbTileDesc *
 #define ZB_MT_TRY(jh_)                                                                                              \
       {                                                                                                             \
          const int jh = (jh_);                                                                                      \
-         /* only a strictly longer match is kept: its byte at offset curmax must agree (curmax < bound here) */     \
-         if (curmax >= ZB_MIN_MATCH && txt[jh + curmax] != txt[i + curmax]) continue;                               \
          uint32_t len = bound;                                                                                      \
          for (uint32_t o = ZB_MIN_MATCH; o < bound; o += 32) {                                                      \
             const uint32_t xo = o + (uint32_t)lane;                                                                 \
