@@ -1,3 +1,4 @@
+# Full GPU test suite followed by the one-GPU evidence (superset of capture_n1.sh, with CLI traces).
 set -x
 mkdir -p gpurun_out
 ( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2_pytest28.log 2>&1

@@ -1,3 +1,4 @@
+# compute-sanitizer memcheck (all small paths) and racecheck (48 KB stream): gpurun --timeout 1800 -- 'bash tools/capture_sanitizer.sh'
 set -x
 mkdir -p gpurun_out
 which compute-sanitizer || ls /usr/local/cuda/bin | grep -i sanit
