@@ -317,117 +317,9 @@ void zb_sort_pairs(zb_stream_t st, uint64_t *keys, uint32_t *vals, uint64_t *key
    }
 }
 
-/* --------------------------------------------------------------- tile filter --------------------------------------------------------------- */
-
-/* Every tile's source list is cut into nseg segments, one warp each, so that the sequential part of a stream is short:
-   pass 1 counts the kept entries of every segment and the running LCP minimum it leaves behind, a per-tile scan turns that
-   into output offsets and carried-in minima, pass 2 streams again and writes. */
-__device__ __forceinline__ void tile_seg_range(const ZbTileDesc &t, const uint32_t *src_cnt, int nseg, int sg, uint32_t &r_lo, uint32_t &r_hi) {
-   const uint32_t n = t.src_cnt_idx >= 0 ? src_cnt[t.src_cnt_idx] : t.src_n;
-   const uint32_t seglen = (((n + (uint32_t)nseg - 1u) / (uint32_t)nseg) + 31u) & ~31u;
-   r_lo = (uint32_t)sg * seglen; if (r_lo > n) r_lo = n;
-   r_hi = r_lo + seglen; if (r_hi > n) r_hi = n;
-}
-
-__global__ void __launch_bounds__(128) tile_filter_count_k(const uint32_t *srcw, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first_tile, int nseg, uint32_t *seg) {
-   const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-   if (wid >= (long)ntiles * nseg) return;
-   const int lane = threadIdx.x & 31;
-   const ZbTileDesc t = tiles[first_tile + (int)(wid / nseg)];
-   const uint32_t *src = srcw + t.src_base;
-   uint32_t r_lo, r_hi;
-   tile_seg_range(t, src_cnt, nseg, (int)(wid % nseg), r_lo, r_hi);
-   const uint32_t lo = t.lo - t.src_lo, span = t.hi - t.lo;
-   uint32_t count = 0, tail = 0x1ffu, has = 0;
-   for (uint32_t r0 = r_lo; r0 < r_hi; r0 += 32) {
-      const uint32_t r = r0 + lane;
-      const bool valid = r < r_hi;
-      const uint32_t w = valid ? __ldg(src + r) : 0u;
-      const uint32_t v = valid ? ((w >> ZB_POS_BITS) & 0x1ffu) : 0x1ffu;
-      const bool keep = valid && ((w & ZB_POS_MASK) - lo) < span;
-      const uint32_t kmask = __ballot_sync(0xffffffffu, keep);
-      if (kmask) {
-         const int lastk = 31 - __clz((int)kmask);
-         tail = __reduce_min_sync(0xffffffffu, lane > lastk ? v : 0x1ffu);
-         has = 1; count += __popc(kmask);
-      } else {
-         const uint32_t mn = __reduce_min_sync(0xffffffffu, v);
-         tail = mn < tail ? mn : tail;
-      }
-   }
-   if (lane == 0) { seg[2 * wid] = count; seg[2 * wid + 1] = tail | (has << 16); }
-}
-
-__global__ void tile_filter_offsets_k(uint32_t *seg, int ntiles, int nseg, uint32_t *cnt) {
-   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-   if (k >= ntiles) return;
-   uint32_t acc = 0, carry = 0x1ffu;
-   for (int sg = 0; sg < nseg; sg++) {
-      const size_t i = (size_t)k * nseg + sg;
-      const uint32_t c = seg[2 * i], th = seg[2 * i + 1];
-      seg[2 * i] = acc; seg[2 * i + 1] = carry;
-      acc += c;
-      const uint32_t tl = th & 0xffffu;
-      carry = (th >> 16) ? tl : (tl < carry ? tl : carry);
-   }
-   cnt[k] = acc;
-}
-
-__global__ void __launch_bounds__(128) tile_filter_k(const uint32_t *srcw, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride,
-                                                     int nseg, const uint32_t *seg) {
-   const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-   if (wid >= (long)ntiles * nseg) return;
-   const int lane = threadIdx.x & 31;
-   const int tile = (int)(wid / nseg);
-   const ZbTileDesc t = tiles[first_tile + tile];
-   const uint32_t *src = srcw + t.src_base;
-   uint32_t *dst = out + (size_t)tile * stride;
-   uint32_t r_lo, r_hi;
-   tile_seg_range(t, src_cnt, nseg, (int)(wid % nseg), r_lo, r_hi);
-   const uint32_t lo = t.lo - t.src_lo, span = t.hi - t.lo;
-   const uint32_t lt = (1u << lane) - 1u;
-   uint32_t carry = seg[2 * wid + 1], count = seg[2 * wid];
-   for (uint32_t r0 = r_lo; r0 < r_hi; r0 += 32) {
-      const uint32_t r = r0 + lane;
-      const bool valid = r < r_hi;
-      const uint32_t w = valid ? __ldg(src + r) : 0u;
-      const uint32_t pos = (w & ZB_POS_MASK) - lo;
-      uint32_t v = valid ? ((w >> ZB_POS_BITS) & 0x1ffu) : 0x1ffu;
-      const bool keep = valid && pos < span;
-      const uint32_t kmask = __ballot_sync(0xffffffffu, keep);
-      const uint32_t below = kmask & lt;
-      const int start = below ? (32 - __clz((int)below)) : 0;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-         uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
-         if (lane >= start + d) v = min(v, o);
-      }
-      if (start == 0) v = min(v, carry);
-      if (keep) dst[count + __popc(below)] = pos | (v << ZB_POS_BITS);
-      const uint32_t v31 = __shfl_sync(0xffffffffu, v, 31);
-      carry = (kmask >> 31) ? 0x1ffu : v31;
-      count += __popc(kmask);
-   }
-}
-
-void zb_tile_filter(zb_stream_t st, const uint32_t *src, const uint32_t *src_cnt, const ZbTileDesc *tiles, int ntiles, int first_tile, uint32_t *out, size_t stride, uint32_t *cnt,
-                    int nseg, uint32_t *seg_scratch) {
-   if (ntiles <= 0) return;
-   if (nseg < 1) nseg = 1;
-   const int wpb = 4;
-   const long nwarp = (long)ntiles * nseg;
-   PROF_K("mf_tile_filter", st);
-   tile_filter_count_k<<<(unsigned)((nwarp + wpb - 1) / wpb), wpb * 32, 0, st>>>(src, src_cnt, tiles, ntiles, first_tile, nseg, seg_scratch);
-   tile_filter_offsets_k<<<(ntiles + 127) / 128, 128, 0, st>>>(seg_scratch, ntiles, nseg, cnt);
-   tile_filter_k<<<(unsigned)((nwarp + wpb - 1) / wpb), wpb * 32, 0, st>>>(src, src_cnt, tiles, ntiles, first_tile, out, stride, nseg, seg_scratch);
-   PROF_E(st);
-   zb_count_launch(3);
-   ZB_CUDA_CHECK(cudaGetLastError());
-}
-
 /* --------------------------------------------------------------- unit distribution --------------------------------------------------------------- */
 
-/* The tile filter above gives every consumer its own pass over the producer's list; for the first cut - a window's suffix list
+/* A list filter (round 1; the host build still has one, tests/emu) gives every consumer its own pass over the producer's list; for the first cut - a window's suffix list
    (~1.08 M words) into its ~33 units of 32768 main + 32768 look-back positions - that was 26 words streamed per window position
    over two levels.  Every position belongs to at most TWO units (the one it is a main position of, and the next one, whose
    look-back it is in), so the cut is a stable partition: the window's list is read in segments of 4096 ranks, twice
