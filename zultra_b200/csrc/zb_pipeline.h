@@ -207,6 +207,7 @@ struct ZbPipe {
    ZbBuf<ZbSub> sub; ZbBuf<ZbSubTabs> tabs; ZbBuf<uint32_t> dchunk_sub, pchunk_sub;
    ZbBuf<zb_match_t> best; ZbBuf<int16_t> sig_true, sig_warm, sig_new; ZbBuf<uint8_t> dok; ZbBuf<uint32_t> dbad;
    ZbBuf<uint32_t> pentry, pbits, cand /* 16-byte candidate records, zb_cand_pack */; ZbBuf<uint16_t> dpfar;   /* dpfar: cost rows of the thread-per-chunk parse kernel */
+   int cp = ZB_CP;          /* positions per parsed-path chunk of this batch (stage_parse decides: shorter for small batches) */
    ZbBuf<int> dreach;       /* per parse chunk: how far past its end its candidates read (0..258), stage_parse */
    /* output */
    ZbBuf<uint32_t> out; ZbBuf<ZbStreamOut> sout;
@@ -936,7 +937,8 @@ inline void ZbPipe::stage_match(uint32_t tile_main) {
 #define ZB_EXROW 264          /* u16 per chunk row: 258 used, 528 bytes = 33 x 16 */
 template <int MODE>
 __global__ void __launch_bounds__(ZB_SW_THREADS) zb_sweep_k(long nchunk, const ZbWinDesc *wd, const uint32_t *wbs, const uint32_t *gcf, int nw, uint32_t *gcw,
-                                                            const uint16_t *gl, const ZbSub *sb, const uint32_t *pcs, int pass, const zb_match_t *bm, uint16_t *exc) {
+                                                            const uint16_t *gl, const ZbSub *sb, const uint32_t *pcs, int pass, const zb_match_t *bm, uint16_t *exc,
+                                                            uint32_t cpv /* MODE 1: positions per path chunk (ZbPipe::cp) */) {
    __shared__ uint16_t ring_s[ZB_SW_RING * ZB_SW_THREADS];
    const long c = (long)blockIdx.x * ZB_SW_THREADS + threadIdx.x;
    if (c >= nchunk) return;
@@ -952,7 +954,7 @@ __global__ void __launch_bounds__(ZB_SW_THREADS) zb_sweep_k(long nchunk, const Z
       if (pass > 0 && !s.is_dyn) return;
       const uint32_t k = (uint32_t)c - s.pchunk_base;
       gb = wbs[s.win];
-      lo = s.ps + k * ZB_CP; hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      lo = s.ps + k * cpv; hi = lo + cpv < s.pe ? lo + cpv : s.pe;
    }
    uint16_t *ring = ring_s + threadIdx.x;
    uint16_t *row = exc + (size_t)c * ZB_EXROW;
@@ -1009,7 +1011,7 @@ __global__ void __launch_bounds__(ZB_SW_THREADS) zb_sweep_k(long nchunk, const Z
    the pass's fresh histogram (blockdeflate.c:887-891; EOB counted here) when pass >= 0. */
 #define ZB_HOP_G 8
 template <int MODE>
-__global__ void __launch_bounds__(32) zb_hop_k(int nunits, const ZbWinDesc *wd, const uint32_t *gcf, const ZbSub *sb, ZbSubTabs *tb, int pass, const uint16_t *exc, uint32_t *ent) {
+__global__ void __launch_bounds__(32) zb_hop_k(int nunits, const ZbWinDesc *wd, const uint32_t *gcf, const ZbSub *sb, ZbSubTabs *tb, int pass, const uint16_t *exc, uint32_t *ent, uint32_t cpv) {
    __shared__ __align__(16) uint16_t buf[2][ZB_HOP_G][ZB_EXROW];
    const int x = blockIdx.x, lane = threadIdx.x;
    if (x >= nunits) return;
@@ -1018,7 +1020,7 @@ __global__ void __launch_bounds__(32) zb_hop_k(int nunits, const ZbWinDesc *wd, 
    else {
       const ZbSub s = sb[x];
       if (pass > 0 && !s.is_dyn) return;
-      start = s.ps; end = s.pe; cbase = s.pchunk_base; nchunk = s.npchunk; clen = ZB_CP;
+      start = s.ps; end = s.pe; cbase = s.pchunk_base; nchunk = s.npchunk; clen = cpv;
       if (pass >= 0 && s.is_dyn) {
          ZbSubTabs &t = tb[x];
          for (int i = lane; i < ZB_NLIT; i += 32) t.lcnt[i] = i == ZB_EOB ? 1 : 0;
@@ -1081,10 +1083,10 @@ inline void ZbPipe::stage_greedy() {
 #ifndef ZB_EMU
    if (nch > 0) {
       if (g_zb_prof_on) { zb_tag("path_sweep"); zb_prof_begin(0, st); }
-      zb_sweep_k<0><<<(unsigned)((nch + ZB_SW_THREADS - 1) / ZB_SW_THREADS), ZB_SW_THREADS, 0, st>>>(nch, wd, wbs, gcf, nw, gcw, gl, 0, 0, -1, 0, exitc.p);
+      zb_sweep_k<0><<<(unsigned)((nch + ZB_SW_THREADS - 1) / ZB_SW_THREADS), ZB_SW_THREADS, 0, st>>>(nch, wd, wbs, gcf, nw, gcw, gl, 0, 0, -1, 0, exitc.p, ZB_CG);
       if (g_zb_prof_on) zb_prof_end(st);
       if (g_zb_prof_on) { zb_tag("path_hop"); zb_prof_begin(0, st); }
-      zb_hop_k<0><<<nwin, 32, 0, st>>>(nwin, wd, gcf, 0, 0, -1, exitc.p, ent);
+      zb_hop_k<0><<<nwin, 32, 0, st>>>(nwin, wd, gcf, 0, 0, -1, exitc.p, ent, ZB_CG);
       if (g_zb_prof_on) zb_prof_end(st);
       zb_count_launch(2);
       ZB_CUDA_CHECK(cudaGetLastError());
@@ -1704,12 +1706,12 @@ ZB_HD void zb_walk_best(const zb_match_t *best, uint32_t entry, uint32_t hi, F &
 
 #ifndef ZB_EMU
 /* ---- candidate records: once per batch, one thread per position of every sub-block (zb_cand_pack, zb_core.h) ---- */
-__global__ void __launch_bounds__(256) zb_cand_k(long npch, const ZbSub *sb, const uint32_t *pcs, const uint32_t *wbs, const zb_match_t *mt, uint4 *cand) {
+__global__ void __launch_bounds__(256) zb_cand_k(long npch, const ZbSub *sb, const uint32_t *pcs, const uint32_t *wbs, const zb_match_t *mt, uint4 *cand, uint32_t cpv) {
    const long c = blockIdx.x;
    if (c >= npch) return;
    const ZbSub s = sb[pcs[c]];
    const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
-   const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+   const uint32_t lo = s.ps + k * cpv, hi = lo + cpv < s.pe ? lo + cpv : s.pe;
    for (uint32_t p = lo + threadIdx.x; p < hi; p += 256) {
       const ZbMatchRec rec = zb_load_rec(mt + ((size_t)gb << 3), (int)p);
       const ZbCand cd = zb_cand_pack(rec, (int)(s.pe - p));
@@ -1718,12 +1720,12 @@ __global__ void __launch_bounds__(256) zb_cand_k(long npch, const ZbSub *sb, con
 }
 
 /* after the last pass: choice words -> {length, offset} (private.h:59), the offset fetched from the match list */
-__global__ void __launch_bounds__(256) zb_choice_k(long npch, const ZbSub *sb, const uint32_t *pcs, const uint32_t *wbs, const zb_match_t *mt, uint32_t *bm) {
+__global__ void __launch_bounds__(256) zb_choice_k(long npch, const ZbSub *sb, const uint32_t *pcs, const uint32_t *wbs, const zb_match_t *mt, uint32_t *bm, uint32_t cpv) {
    const long c = blockIdx.x;
    if (c >= npch) return;
    const ZbSub s = sb[pcs[c]];
    const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
-   const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+   const uint32_t lo = s.ps + k * cpv, hi = lo + cpv < s.pe ? lo + cpv : s.pe;
    for (uint32_t p = lo + threadIdx.x; p < hi; p += 256) {
       const uint32_t w = bm[gb + p];
       uint32_t v = 0;
@@ -2288,7 +2290,7 @@ __global__ void __launch_bounds__(ZB_DW_THREADS) zb_parse_fix_k(const ZbSub *sb,
    global atomic per token); a chunk of another sub-block (one CTA per sub-block boundary) counts straight into global memory. */
 #define ZB_PH_THREADS 128
 __global__ void __launch_bounds__(ZB_PH_THREADS) zb_path_hist_k(long npch, const ZbSub *sb, ZbSubTabs *tb, const uint32_t *pcs, const ZbWinDesc *wd, const uint32_t *wbs,
-                                                                const uint8_t *T, const zb_match_t *bm, const uint32_t *pen) {
+                                                                const uint8_t *T, const zb_match_t *bm, const uint32_t *pen, uint32_t cpv) {
    __shared__ int hl[ZB_NLIT], ho[ZB_NOFF];
    const long c0 = (long)blockIdx.x * ZB_PH_THREADS, c = c0 + threadIdx.x;
    const uint32_t x0 = pcs[c0];
@@ -2300,7 +2302,7 @@ __global__ void __launch_bounds__(ZB_PH_THREADS) zb_path_hist_k(long npch, const
       const ZbSub s = sb[x];
       if (s.is_dyn) {
          const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
-         const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+         const uint32_t lo = s.ps + k * cpv, hi = lo + cpv < s.pe ? lo + cpv : s.pe;
          const uint8_t *t = T + wd[s.win].in_off;
          int *lc = x == x0 ? hl : tb[x].lcnt, *oc = x == x0 ? ho : tb[x].ocnt;
          /* The path is a pointer chase (the next token starts where this one ends); followed load by load it is one DRAM
@@ -2355,6 +2357,11 @@ inline void ZbPipe::stage_parse() {
       ~0.65 of that - 960 positions per chunk on the 100 MB text, 512 on the 51 MB binaries: fewer warps fight for the
       shared-memory ring, and longer chunks carry less warm-up - and much slower just above one full wave) */
    int cd_auto = (int)(((long)P / ((long)zb_sm_count() * 720) + 32) / 64 * 64);
+   /* the path chunks (sweep, histogram, token bits, emission: one thread walks a chunk) are half as long for small batches, where
+      the walk of one chunk is the whole kernel's time (48 KB stream: path_hist 0.90 -> 0.45 ms); big batches have chunks to spare
+      and the sweep's per-chunk overhead makes the short form slower there */
+   cp = P <= (1L << 20) ? ZB_CP / 2 : ZB_CP;
+   const uint32_t CPv = (uint32_t)cp;
    if (cd_auto < 128) cd_auto = 128;      /* small inputs (one 48 KB stream, a GPU's share of a strongly scaled 51 MB): short chunks = short serial chains, the warm-up then dominates a chunk */
    if (cd_auto > ZB_CD) cd_auto = ZB_CD;
    int WU = parse_wu; if (WU > 2048) WU = 2048;
@@ -2416,7 +2423,7 @@ inline void ZbPipe::stage_parse() {
             if (g1 != g0) { curg = g1; cnt = 1; }
          }
          d += nd;
-         sb[x].pchunk_base = p; sb[x].npchunk = (size + ZB_CP - 1) / ZB_CP; p += sb[x].npchunk;
+         sb[x].pchunk_base = p; sb[x].npchunk = (size + CPv - 1) / CPv; p += sb[x].npchunk;
       }
       cn[4] = d; cn[5] = p; cn[6] = mx;
    });
@@ -2513,7 +2520,7 @@ inline void ZbPipe::stage_parse() {
    }
    if (npch > 0) {
       if (g_zb_prof_on) { zb_tag("parse_cand"); zb_prof_begin(0, st); }
-      zb_cand_k<<<(unsigned)npch, 256, 0, st>>>(npch, sb, pcs, wbs, mt, (uint4 *)cand.p);
+      zb_cand_k<<<(unsigned)npch, 256, 0, st>>>(npch, sb, pcs, wbs, mt, (uint4 *)cand.p, CPv);
       if (g_zb_prof_on) zb_prof_end(st);
       zb_count_launch(1);
       ZB_CUDA_CHECK(cudaGetLastError());
@@ -2709,10 +2716,10 @@ inline void ZbPipe::stage_parse() {
 #ifndef ZB_EMU
       if (npch > 0) {
          if (g_zb_prof_on) { zb_tag("path_sweep"); zb_prof_begin(0, st); }
-         zb_sweep_k<1><<<(unsigned)((npch + ZB_SW_THREADS - 1) / ZB_SW_THREADS), ZB_SW_THREADS, 0, st>>>(npch, wd, wbs, 0, 0, 0, 0, sb, pcs, pass, bm, exitc.p);
+         zb_sweep_k<1><<<(unsigned)((npch + ZB_SW_THREADS - 1) / ZB_SW_THREADS), ZB_SW_THREADS, 0, st>>>(npch, wd, wbs, 0, 0, 0, 0, sb, pcs, pass, bm, exitc.p, CPv);
          if (g_zb_prof_on) zb_prof_end(st);
          if (g_zb_prof_on) { zb_tag("path_hop"); zb_prof_begin(0, st); }
-         zb_hop_k<1><<<ns, 32, 0, st>>>(ns, wd, 0, sb, tb, pass, exitc.p, pen);
+         zb_hop_k<1><<<ns, 32, 0, st>>>(ns, wd, 0, sb, tb, pass, exitc.p, pen, CPv);
          if (g_zb_prof_on) zb_prof_end(st);
          zb_count_launch(2);
          ZB_CUDA_CHECK(cudaGetLastError());
@@ -2723,7 +2730,7 @@ inline void ZbPipe::stage_parse() {
          const ZbSub s = sb[pcs[c]];
          if (pass > 0 && !s.is_dyn) return;
          const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
-         const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+         const uint32_t lo = s.ps + k * CPv, hi = lo + CPv < s.pe ? lo + CPv : s.pe;
          for (uint32_t p = hi; p-- > lo;) {
             uint32_t l = bm[gb + p].length; if (l < ZB_MIN_MATCH) l = 1;
             uint32_t j = p + l;
@@ -2736,7 +2743,7 @@ inline void ZbPipe::stage_parse() {
          const uint32_t gb = wbs[s.win];
          uint32_t e = s.ps;
          for (uint32_t k = 0; k < s.npchunk; k++) {
-            const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+            const uint32_t lo = s.ps + k * CPv, hi = lo + CPv < s.pe ? lo + CPv : s.pe;
             pen[s.pchunk_base + k] = e;
             if (e < hi) e = hi + ex[gb + e];
          }
@@ -2753,7 +2760,7 @@ inline void ZbPipe::stage_parse() {
 #ifndef ZB_EMU
       if (npch > 0) {
          if (g_zb_prof_on) { zb_tag("path_hist"); zb_prof_begin(0, st); }
-         zb_path_hist_k<<<(unsigned)((npch + ZB_PH_THREADS - 1) / ZB_PH_THREADS), ZB_PH_THREADS, 0, st>>>(npch, sb, tb, pcs, wd, wbs, T, bm, pen);
+         zb_path_hist_k<<<(unsigned)((npch + ZB_PH_THREADS - 1) / ZB_PH_THREADS), ZB_PH_THREADS, 0, st>>>(npch, sb, tb, pcs, wd, wbs, T, bm, pen, CPv);
          if (g_zb_prof_on) zb_prof_end(st);
          zb_count_launch(1);
          ZB_CUDA_CHECK(cudaGetLastError());
@@ -2764,7 +2771,7 @@ inline void ZbPipe::stage_parse() {
          const ZbSub s = sb[x];
          if (!s.is_dyn) return;
          const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
-         const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+         const uint32_t lo = s.ps + k * CPv, hi = lo + CPv < s.pe ? lo + CPv : s.pe;
          const uint8_t *t = T + wd[s.win].in_off;
          int *lc = tb[x].lcnt, *oc = tb[x].ocnt;
          for (uint32_t p = pen[c]; p < hi;) {
@@ -2813,7 +2820,7 @@ inline void ZbPipe::stage_parse() {
 #ifndef ZB_EMU
    if (npch > 0) {      /* choice words -> {length, offset} */
       if (g_zb_prof_on) { zb_tag("parse_choice"); zb_prof_begin(0, st); }
-      zb_choice_k<<<(unsigned)npch, 256, 0, st>>>(npch, sb, pcs, wbs, mt, (uint32_t *)bm);
+      zb_choice_k<<<(unsigned)npch, 256, 0, st>>>(npch, sb, pcs, wbs, mt, (uint32_t *)bm, CPv);
       if (g_zb_prof_on) zb_prof_end(st);
       zb_count_launch(1);
       ZB_CUDA_CHECK(cudaGetLastError());
@@ -2825,7 +2832,7 @@ inline void ZbPipe::stage_parse() {
       const ZbSub s = sb[x];
       if (!s.is_dyn) return;
       const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
-      const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      const uint32_t lo = s.ps + k * CPv, hi = lo + CPv < s.pe ? lo + CPv : s.pe;
       const uint8_t *t = T + wd[s.win].in_off;
       const ZbCostTab &ct = tb[x].cost;
       for (uint32_t p = pen[c]; p < hi;) {
@@ -2945,6 +2952,7 @@ inline void ZbPipe::stage_parse() {
  * every chunk writes its tokens at its absolute bit offset.
  */
 inline void ZbPipe::stage_emit_prepare() {
+   const uint32_t CPv = (uint32_t)cp;
    const int ns = nsub;
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
@@ -2957,10 +2965,10 @@ inline void ZbPipe::stage_emit_prepare() {
 #ifndef ZB_EMU
    if (npch > 0) {
       if (g_zb_prof_on) { zb_tag("path_sweep"); zb_prof_begin(0, st); }
-      zb_sweep_k<1><<<(unsigned)((npch + ZB_SW_THREADS - 1) / ZB_SW_THREADS), ZB_SW_THREADS, 0, st>>>(npch, wd, wbs, 0, 0, 0, 0, sb, pcs, -1, bm, exitc.p);
+      zb_sweep_k<1><<<(unsigned)((npch + ZB_SW_THREADS - 1) / ZB_SW_THREADS), ZB_SW_THREADS, 0, st>>>(npch, wd, wbs, 0, 0, 0, 0, sb, pcs, -1, bm, exitc.p, CPv);
       if (g_zb_prof_on) zb_prof_end(st);
       if (g_zb_prof_on) { zb_tag("path_hop"); zb_prof_begin(0, st); }
-      zb_hop_k<1><<<ns, 32, 0, st>>>(ns, wd, 0, sb, tb, -1, exitc.p, pen);
+      zb_hop_k<1><<<ns, 32, 0, st>>>(ns, wd, 0, sb, tb, -1, exitc.p, pen, CPv);
       if (g_zb_prof_on) zb_prof_end(st);
       zb_count_launch(2);
       ZB_CUDA_CHECK(cudaGetLastError());
@@ -2970,7 +2978,7 @@ inline void ZbPipe::stage_emit_prepare() {
    zb_launch(st, npch, ZB_LAMBDA(long c) {
       const ZbSub s = sb[pcs[c]];
       const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
-      const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      const uint32_t lo = s.ps + k * CPv, hi = lo + CPv < s.pe ? lo + CPv : s.pe;
       for (uint32_t p = hi; p-- > lo;) {
          uint32_t l = bm[gb + p].length; if (l < ZB_MIN_MATCH) l = 1;
          uint32_t j = p + l;
@@ -2982,7 +2990,7 @@ inline void ZbPipe::stage_emit_prepare() {
       const uint32_t gb = wbs[s.win];
       uint32_t e = s.ps;
       for (uint32_t k = 0; k < s.npchunk; k++) {
-         const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+         const uint32_t lo = s.ps + k * CPv, hi = lo + CPv < s.pe ? lo + CPv : s.pe;
          pen[s.pchunk_base + k] = e;
          if (e < hi) e = hi + ex[gb + e];
       }
@@ -2993,7 +3001,7 @@ inline void ZbPipe::stage_emit_prepare() {
       const uint32_t x = pcs[c];
       const ZbSub s = sb[x];
       const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
-      const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      const uint32_t lo = s.ps + k * CPv, hi = lo + CPv < s.pe ? lo + CPv : s.pe;
       const uint8_t *t = T + wd[s.win].in_off;
       const ZbCostTab &ct = tb[x].cost;
       uint32_t bits = 0;
@@ -3042,6 +3050,7 @@ inline void ZbPipe::phase_maps(const std::vector<ZbStreamOut> &streams, unsigned
 }
 
 inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams, uint32_t *ext_words) {
+   const uint32_t CPv = (uint32_t)cp;
    const int ns = nsub;
    ZbSub *sb = sub.p; ZbSubTabs *tb = tabs.p; uint32_t *cn = counters.p;
    const ZbWinDesc *wd = win.p; const uint32_t *wbs = wbase.p; const uint8_t *T = in_ptr;
@@ -3112,7 +3121,7 @@ inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams, u
       const ZbSub s = sb[x];
       if (s.stored) return;
       const uint32_t k = (uint32_t)c - s.pchunk_base, gb = wbs[s.win];
-      const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      const uint32_t lo = s.ps + k * CPv, hi = lo + CPv < s.pe ? lo + CPv : s.pe;
       const uint8_t *t = T + wd[s.win].in_off;
       const ZbSubTabs &tt = tb[x];
       ZbBitSink sink;
@@ -3180,7 +3189,7 @@ inline void ZbPipe::stage_emit_finish(const std::vector<ZbStreamOut> &streams, u
       const ZbSub s = sb[x];
       if (!s.stored) return;
       const uint32_t k = (uint32_t)c - s.pchunk_base;
-      const uint32_t lo = s.ps + k * ZB_CP, hi = lo + ZB_CP < s.pe ? lo + ZB_CP : s.pe;
+      const uint32_t lo = s.ps + k * CPv, hi = lo + CPv < s.pe ? lo + CPv : s.pe;
       uint8_t *bytes = (uint8_t *)(ow + so[wd[s.win].stream].out_word_off);
       const uint8_t *t = T + wd[s.win].in_off;
       const uint64_t first_payload = ((s.bit_off + 3 + 7) >> 3) + 4;
